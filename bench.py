@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the ft_grandprix hot path on B200 (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload tick|lidar|step] [--cars C]
+    python bench.py --impl reference ...        # the CPU arm (oracle port, all host threads)
+
+One "step" = one pass of the hot path over the whole fleet:
+  workload tick  (default; BASELINE config 3): lap update + batched nidc driver + 90-beam lidar +
+                 vehicle step for 65,536 cars per GPU on track.png  -> metric car-steps/s
+                 (rays/s = 90 x car-steps/s is reported beside it)
+  workload lidar (BASELINE config 2): 90-beam scan of 4,096 cars at random poses -> rays/s
+  workload step  : vehicle step only, 65,536 cars
+Cars are sharded over the N ranks with no collective on the step path (weak scaling: the per-GPU
+fleet is fixed); only the final timing / stats are gathered.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES = {  # algorithmic bytes per unit (SURVEY §8 d)
+    "tick": 2328.0,    # per car-tick, unfused sum: step 1488 + scan 416 + driver 376 + lap 48
+    "step": 1488.0,    # per car-step: qpos/qvel/warm in+out + ctrl
+    "lidar": 416.0,    # per scan of 90 rays: pose 56 B + ranges 360 B
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].startswith("Active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_poses(path, n, seed, level):
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, 100, n)
+    nxt = (idx + 1) % 100
+    heading = np.arctan2(path[nxt, 1] - path[idx, 1], path[nxt, 0] - path[idx, 0])
+    xy = path[idx] + rng.normal(0, 0.10, (n, 2))
+    yaw = heading + rng.normal(0, 0.3, n)
+    if level:
+        return xy, yaw, None
+    z = 0.0156 + rng.uniform(-0.002, 0.002, n)
+    roll, pitch = rng.normal(0, 0.01, n), rng.normal(0, 0.01, n)
+    cy, sy, cp, sp, cr, sr = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
+    q = np.stack([cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy,
+                  cr * cp * sy - sr * sp * cy], 1)
+    return xy, yaw, np.concatenate([xy, z[:, None], q], 1)
+
+
+def workload_name(wl, cars):
+    return {"tick": f"full tick (lap + nidc + 90-beam lidar + vehicle step), {cars} cars/GPU on track.png (BASELINE config 3)",
+            "lidar": f"lidar-only, {cars} cars/GPU at random poses on track.png, 90 beams, no cutoff (BASELINE config 2)",
+            "step": f"vehicle step only, {cars} cars/GPU on track.png"}[wl]
+
+
+# ----------------------------------------------------------------------------- CPU arms (oracle port)
+def cpu_units_per_s(wl, sample_cars, ticks, threads, seed=1):
+    """Times the oracle (oracle/*.c, a C restatement: kind 'port') on a bounded sample of the workload."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle
+    import ft_grandprix_b200 as ft
+    pyoracle.build()
+    t = ft.Track.bundled("track")
+    z = np.load(os.path.join(ROOT, "ft_grandprix_b200", "assets", "tracks.npz"))
+    shape = tuple(int(v) for v in z["track__shape"])
+    wall = np.unpackbits(z["track__bits"])[: shape[0] * shape[1]].reshape(shape)
+    ot = pyoracle.Track(wall)
+    xy, yaw, poses = make_poses(t.path, sample_cars, seed, level=(wl != "lidar"))
+    chunks = np.array_split(np.arange(sample_cars), threads)
+    if wl == "lidar":
+        def work(ix):
+            return ot.scan(poses[ix], threads=1)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, chunks))
+        dt = time.perf_counter() - t0
+        return sample_cars * 90 / dt, dt
+    model = pyoracle.Model()
+    state = [model.reset(xy[i, 0], xy[i, 1], yaw[i]) for i in range(sample_cars)]
+    qpos = np.stack([s[0] for s in state]); qvel = np.stack([s[1] for s in state]); warm = np.stack([s[2] for s in state])
+    ctrl = np.zeros((sample_cars, 2)); ranges = np.zeros((sample_cars, 90))
+    laps = [pyoracle.Lap(offset=10) for _ in range(sample_cars)]
+
+    def work(ix):
+        lo, hi = int(ix[0]), int(ix[-1]) + 1
+        for k in range(ticks):
+            if wl == "tick":
+                for i in range(lo, hi):
+                    laps[i].update(t.path, qpos[i, :2], k, 10, 0)
+                    r = pyoracle.driver(0, ranges[i])
+                    if r is not None:
+                        ctrl[i] = r
+                ranges[lo:hi] = ot.scan(qpos[lo:hi, :7], threads=1)
+            model.step_n(ot, qpos[lo:hi], qvel[lo:hi], warm[lo:hi], ctrl[lo:hi], nthreads=1)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(work, [c for c in chunks if len(c)]))
+    dt = time.perf_counter() - t0
+    return sample_cars * ticks / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    threads = os.cpu_count() or 1
+    sample_cars = {"lidar": 64 * threads, "tick": 16 * threads, "step": 16 * threads}[wl]
+    ticks = 1 if wl == "lidar" else 10
+    for _ in range(args.warmup):
+        cpu_units_per_s(wl, max(threads, sample_cars // 8), 1 if wl == "lidar" else 2, threads)
+    vals, dts = [], []
+    for _ in range(args.steps):
+        v, dt = cpu_units_per_s(wl, sample_cars, ticks, threads)
+        vals.append(v); dts.append(dt)
+    value = float(np.mean(vals))
+    metric, unit = ("lidar rays/s", "rays/s") if wl == "lidar" else ("car-steps/s", "car-steps/s")
+    sample = f"{sample_cars} cars x {ticks} tick(s) per step on track.png, C oracle (oracle/*.c), {threads} threads"
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(dts) * 1e3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(wl, args.cars), "sample": sample},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference = MuJoCo-on-CPU loop; mujoco is not installable here, so the arm times the C "
+                    "restatement of that loop (oracle/), not MuJoCo itself"}
+    if wl != "lidar":
+        line["rays_per_s"] = value * 90 if wl == "tick" else 0.0
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import ft_grandprix_b200 as ft
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl, cars = args.workload, args.cars
+    lib = ft._lib.load()
+    track = ft.Track.bundled("track")
+    fleet = ft.Fleet(track, cars, device=local, driver="nidc")
+    xy, yaw, poses = make_poses(track.path, cars, seed=(0 if wl == "lidar" else 1) + 1000 * rank, level=(wl != "lidar"))
+    fleet.reset(xy, yaw)
+    if wl == "lidar":
+        fleet.qpos[:, :7] = torch.from_numpy(poses).to(fleet.device)
+    torch.cuda.synchronize()
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=fleet.device)   # > 126 MB L2
+
+    def one_step():
+        if wl == "lidar":
+            fleet.lidar()
+        elif wl == "step":
+            fleet.step(1)
+        else:
+            fleet.tick(1)
+
+    stream = fleet.stream
+    with torch.cuda.stream(stream):
+        settle = args.settle if wl != "lidar" else 0
+        for k in range(settle):          # drive the fleet into its running regime (untimed)
+            one_step()
+        for _ in range(args.warmup):
+            flush.fill_(1)
+            one_step()
+    stream.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: K steps, each bracketed by CUDA events on the launching stream, L2 flushed between
+    launches0 = lib.ftgp_launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with torch.cuda.stream(stream):
+        for a, b in ev:
+            flush.fill_(1)
+            a.record(stream)
+            one_step()
+            b.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.ftgp_launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H inside the timed region
+    e2e_steps = max(3, min(args.steps, 20))
+    h2d = d2h = 0
+    if wl == "lidar":
+        import ctypes as C
+        qpos_h = torch.empty(cars, 34, dtype=torch.float64).pin_memory(); qpos_h.copy_(fleet.qpos.cpu())
+        out_h = torch.empty(cars, 90, dtype=torch.float32).pin_memory()
+        def e2e_step():
+            ft._lib.check(lib.ftgp_lidar_host(fleet.geom._ptr, C.c_void_p(qpos_h.data_ptr()), 34, None, cars,
+                                              C.c_void_p(out_h.data_ptr())), "ftgp_lidar_host")
+        h2d, d2h = cars * 7 * 8, cars * 90 * 4
+    else:
+        ctrl_h = torch.zeros(cars, 2, dtype=torch.float64).pin_memory()
+        ranges_h = torch.empty(cars, 90, dtype=torch.float32).pin_memory()
+        lap_h = torch.empty_like(fleet.lap, device="cpu").pin_memory()
+        def e2e_step():
+            with torch.cuda.stream(stream):
+                if wl == "step":
+                    fleet.ctrl.copy_(ctrl_h, non_blocking=True)
+                one_step()
+                ranges_h.copy_(fleet.ranges, non_blocking=True)
+                lap_h.copy_(fleet.lap, non_blocking=True)
+            stream.synchronize()
+        h2d = cars * 16 if wl == "step" else 0
+        d2h = cars * 90 * 4 + fleet.lap.numel() * 4
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks (max time), rank 0 prints
+    tt = torch.tensor([dev_ms, e2e_s * 1e3, float(launches)], dtype=torch.float64, device=fleet.device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, launches = float(tt[0]), float(tt[1]), int(tt[2])
+    units_per_step = cars * world * (90 if wl == "lidar" else 1)
+    value = units_per_step * args.steps / (dev_ms * 1e-3)
+    e2e_value = units_per_step * e2e_steps / (e2e_ms * 1e-3)
+    peak, peak_src = peaks()
+    per_unit = BYTES[wl] / (90 if wl == "lidar" else 1)
+    # dominant kernel of the step: its own launches are timed inside this same region
+    achieved = (value / world) * per_unit / 1e9
+    metric, unit = ("lidar rays/s", "rays/s") if wl == "lidar" else ("car-steps/s", "car-steps/s")
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64" if wl != "lidar" else "f32 traversal / f64 pose",
+            "data": "synthetic",
+            "config": {"workload": workload_name(wl, cars), "cars_per_gpu": cars, "beams": 90, "track": "track.png",
+                       "driver": "nidc (device)", "l2": "flushed (512 MiB write) between timed steps",
+                       "timing": "CUDA events on the launching stream per step, summed; max over ranks",
+                       "sharding": f"{world} x {cars} cars, no collective on the step path"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_unit": per_unit,
+                         "note": "latency/issue-bound path: algorithmic HBM traffic is far below peak by construction (SURVEY §8 d)"},
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "how": "C ABI with pinned host buffers, wall clock around H2D + kernels + D2H"},
+            "gpu_launches": launches, "clocks": clocks}
+    if wl != "lidar":
+        line["rays_per_s"] = value * 90 if wl == "tick" else 0.0
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            threads = 1
+            sc = {"lidar": 256, "tick": 32, "step": 32}[wl]
+            v, dt = cpu_units_per_s(wl, sc, 1 if wl == "lidar" else 20, threads)
+            line["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                                    "host_cores_available": os.cpu_count(),
+                                    "sample": f"{sc} cars x {1 if wl == 'lidar' else 20} tick(s), C oracle single thread ({dt:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("FTGP_WORKLOAD", "lidar"), choices=["tick", "lidar", "step"])
+    ap.add_argument("--cars", type=int, default=None)
+    ap.add_argument("--settle", type=int, default=200, help="untimed ticks before timing (tick/step workloads)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.cars is None:
+        args.cars = 4096 if args.workload == "lidar" else 65536
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,10 +46,9 @@ SIGNATURES = {
     "ftgp_lidar_host": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "ftgp_reset": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "ftgp_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
-    "ftgp_drivers": (_i, [_vp, _vp, _i, _vp, _i64, _vp]),
+    "ftgp_drivers": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp]),
     "ftgp_lap_update": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i, C.c_int32, C.c_int32, _vp]),
     "ftgp_tick": (_i, [C.POINTER(TickArgs), _i, _vp]),
-    "ftgp_tick_host": (_i, [C.POINTER(TickArgs), _i]),
 }
 
 _lib = None

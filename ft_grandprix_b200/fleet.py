@@ -1,0 +1,214 @@
+"""Fleet: the device-resident replacement for the reference's MjData + per-car VehicleState.
+
+Mirrors what `Mujoco.physics_thread` touches every tick (ft_grandprix/custom.py:1337-1426):
+
+    reference                                         here
+    ------------------------------------------------  ---------------------------------------
+    data.joint("car #i").qpos / .qvel                 fleet.qpos[i], fleet.qvel[i]   (fp64 rows)
+    data.sensordata[vehicle_state.sensors]            fleet.ranges[i]                (fp32[90])
+    data.ctrl[forward #i], data.ctrl[turn #i]         fleet.ctrl[i] = (speed, steering)
+    vehicle_state.{laps,completion,finished,...}      fleet.lap[i]  (int32 fields, LAP_FIELDS)
+    vehicle_state.times                               fleet.times[i] (lap durations in steps)
+    self.winners                                      fleet.lap[:, rank] / fleet.winners[world]
+    mujoco.mj_step(model, data)                       fleet.step()
+    driver.process_lidar(ranges)                      fleet.drive() (device) / fleet.drive_host()
+
+All arithmetic runs in libftgp.so (hand-written sm_100a CUDA behind include/ftgp.h); torch only
+owns the device memory and the stream.  There is no CPU fallback: constructing a Fleet without a
+CUDA device raises.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (DRIVER_FAST, DRIVER_LOBOTOMY, DRIVER_NIDC, LAP_FIELDS, MAX_LAPTIMES, NBEAMS, NQ, NU, NV)
+from .track import Geometry, Track
+from .vehicle import VehicleStateSnapshot
+
+TIMESTEP = 0.004                      # template/mushr.em.xml:30
+LAP = {name: k for k, name in enumerate(LAP_FIELDS)}
+DRIVER_KINDS = {"nidc": DRIVER_NIDC, "fast": DRIVER_FAST, "lobotomy": DRIVER_LOBOTOMY,
+                "ft_grandprix.nidc": DRIVER_NIDC, "ft_grandprix.fast": DRIVER_FAST,
+                "ft_grandprix.lobotomy": DRIVER_LOBOTOMY}
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+class Fleet:
+    def __init__(self, tracks, ncars, cars_per_world=1, device=0, track_id=None, driver="nidc",
+                 lap_target=10):
+        if not torch.cuda.is_available():
+            raise _lib.FtgpError("Fleet needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", int(device))
+        self.geom = tracks if isinstance(tracks, Geometry) else Geometry(tracks, device=int(device))
+        self.ncars, self.cars_per_world = int(ncars), int(cars_per_world)
+        if self.ncars % self.cars_per_world:
+            raise ValueError("ncars must be a multiple of cars_per_world")
+        self.nworlds = self.ncars // self.cars_per_world
+        self.lap_target = int(lap_target)
+        self.default_driver = DRIVER_KINDS[driver] if isinstance(driver, str) else int(driver)
+        dev, n = self.device, self.ncars
+        with torch.cuda.device(dev):
+            self.stream = torch.cuda.Stream(device=dev)
+        self.qpos = torch.zeros(n, NQ, dtype=torch.float64, device=dev)
+        self.qvel = torch.zeros(n, NV, dtype=torch.float64, device=dev)
+        self.warm = torch.zeros(n, NV, dtype=torch.float64, device=dev)
+        self.ctrl = torch.zeros(n, NU, dtype=torch.float64, device=dev)
+        self.ranges = torch.zeros(n, NBEAMS, dtype=torch.float32, device=dev)   # zeros on the first tick (B.11)
+        self.lap = torch.zeros(n, len(LAP_FIELDS), dtype=torch.int32, device=dev)
+        self.times = torch.zeros(n, MAX_LAPTIMES, dtype=torch.int32, device=dev)
+        self.winners = torch.zeros(self.nworlds, dtype=torch.int32, device=dev)
+        self.status = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.track_id = None if track_id is None else torch.as_tensor(track_id, dtype=torch.int32).to(dev).contiguous()
+        self.driver_kind = None
+        self.steps = 0
+        torch.cuda.synchronize(dev)
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def _s(self):
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def sync(self):
+        self.stream.synchronize()
+
+    def set_driver_kinds(self, kinds):
+        """Per-car built-in driver: names ('nidc', 'fast', 'lobotomy') or FTGP_DRIVER_* ints."""
+        k = [DRIVER_KINDS[x] if isinstance(x, str) else int(x) for x in kinds]
+        self.driver_kind = torch.tensor(k, dtype=torch.int32, device=self.device)
+
+    # ------------------------------------------------------------------ reset (custom.py:1089-1128,1232-1245)
+    def reset(self, xy, yaw):
+        xy = torch.as_tensor(np.asarray(xy, dtype=np.float64)).to(self.device).contiguous()
+        yaw = torch.as_tensor(np.asarray(yaw, dtype=np.float64)).to(self.device).contiguous()
+        if xy.shape != (self.ncars, 2) or yaw.shape != (self.ncars,):
+            raise ValueError("xy must be [ncars,2] and yaw [ncars]")
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        _lib.check(self.lib.ftgp_reset(_ptr(self.qpos), _ptr(self.qvel), _ptr(self.warm), _ptr(self.ctrl),
+                                       _ptr(xy), _ptr(yaw), self.ncars, self._s), "ftgp_reset")
+        with torch.cuda.stream(self.stream):
+            self.ranges.zero_(); self.lap.zero_(); self.times.zero_(); self.winners.zero_(); self.status.zero_()
+            # VehicleState(offset=(i+5)*2) with good_start=True (custom.py:96-118)
+            idx = torch.arange(self.ncars, device=self.device, dtype=torch.int32) % self.cars_per_world
+            self.lap[:, LAP["offset"]] = (idx + 5) * 2
+            self.lap[:, LAP["good_start"]] = 1
+        self.steps = 0
+        self.sync()
+        self._keep = (xy, yaw)
+
+    def reset_grid(self):
+        """The reference start grid: car i of each world at path[(i+5)*2] (custom.py:1232-1245)."""
+        xy = np.zeros((self.ncars, 2)); yaw = np.zeros(self.ncars)
+        tid = None if self.track_id is None else self.track_id.cpu().numpy()
+        for c in range(self.ncars):
+            t = self.geom.tracks[0 if tid is None else int(tid[c])]
+            x, y, a = t.start_pose(c % self.cars_per_world)
+            xy[c] = (x, y); yaw[c] = a
+        self.reset(xy, yaw)
+
+    # ------------------------------------------------------------------ the per-tick pieces
+    def lidar(self, visible=None, min_range=None):
+        """data.sensordata[vehicle_state.sensors] for every car (custom.py:1395)."""
+        _lib.check(self.lib.ftgp_lidar(self.geom._ptr, _ptr(self.qpos), NQ, _ptr(self.track_id), _ptr(visible),
+                                       self.ncars, self.cars_per_world, _ptr(self.ranges), _ptr(min_range),
+                                       self._s), "ftgp_lidar")
+        return self.ranges
+
+    def drive(self):
+        """Built-in batched drivers + control write (custom.py:1398-1423)."""
+        _lib.check(self.lib.ftgp_drivers(_ptr(self.ranges), _ptr(self.driver_kind), self.default_driver,
+                                         _ptr(self.lap), _ptr(self.ctrl), self.ncars, self._s), "ftgp_drivers")
+        return self.ctrl
+
+    def drive_host(self, drivers):
+        """Slow path for unmodified reference-style drivers: one Python object per car
+        with process_lidar(ranges) or process_lidar(ranges, state); exceptions are printed and leave
+        that car's ctrl unchanged (custom.py:1403-1411)."""
+        import inspect
+        self.sync()
+        ranges = self.ranges.cpu().numpy().astype(np.float64)
+        ctrl = self.ctrl.cpu().numpy()
+        snaps = None
+        for i, d in enumerate(drivers):
+            try:
+                if len(inspect.signature(d.process_lidar).parameters) >= 2:   # v2 driver (custom.py:103)
+                    if snaps is None:
+                        snaps = self.snapshots()
+                    sp, st = d.process_lidar(ranges[i].copy(), snaps[i])
+                else:
+                    sp, st = d.process_lidar(ranges[i].copy())
+                ctrl[i] = (float(sp), float(st))
+            except Exception as e:                                          # custom.py:1409-1411
+                print(f"Error in vehicle `{i}`: `{e}`")
+        self.ctrl.copy_(torch.from_numpy(ctrl))
+        return self.ctrl
+
+    def step(self, nsteps=1):
+        """mujoco.mj_step(model, data) (custom.py:1425)."""
+        _lib.check(self.lib.ftgp_step(self.geom._ptr, _ptr(self.qpos), _ptr(self.qvel), _ptr(self.warm),
+                                      _ptr(self.ctrl), _ptr(self.track_id), self.ncars, int(nsteps),
+                                      _ptr(self.status), self._s), "ftgp_step")
+        self.steps += int(nsteps)
+
+    def lap_update(self):
+        """Progress / lap state machine (custom.py:1340-1372)."""
+        _lib.check(self.lib.ftgp_lap_update(self.geom._ptr, _ptr(self.qpos), NQ, _ptr(self.track_id),
+                                            _ptr(self.lap), _ptr(self.times), _ptr(self.winners),
+                                            _ptr(self.status), self.ncars, self.cars_per_world, self.steps,
+                                            self.lap_target, self._s), "ftgp_lap_update")
+
+    def tick_args(self):
+        a = _lib.TickArgs()
+        a.geom = self.geom._ptr
+        a.qpos, a.qvel, a.warm, a.ctrl = (self.qpos.data_ptr(), self.qvel.data_ptr(), self.warm.data_ptr(),
+                                          self.ctrl.data_ptr())
+        a.ranges = self.ranges.data_ptr()
+        a.track_id = None if self.track_id is None else self.track_id.data_ptr()
+        a.driver_kind = None if self.driver_kind is None else self.driver_kind.data_ptr()
+        a.lap, a.times, a.winners, a.status = (self.lap.data_ptr(), self.times.data_ptr(),
+                                               self.winners.data_ptr(), self.status.data_ptr())
+        a.ncars = self.ncars
+        a.cars_per_world, a.default_driver = self.cars_per_world, self.default_driver
+        a.lap_target, a.steps = self.lap_target, self.steps
+        return a
+
+    def tick(self, nticks=1):
+        """nticks iterations of the physics loop (custom.py:1337-1426), all on device."""
+        a = self.tick_args()
+        _lib.check(self.lib.ftgp_tick(C.byref(a), int(nticks), self._s), "ftgp_tick")
+        self.steps += int(nticks)
+
+    # ------------------------------------------------------------------ v2 driver input (custom.py:149-160)
+    def snapshots(self):
+        self.sync()
+        qpos = self.qpos.cpu().numpy(); qvel = self.qvel.cpu().numpy(); lap = self.lap.cpu().numpy()
+        out = []
+        for i in range(self.ncars):
+            w, x, y, z = qpos[i, 3:7]
+            # quaternion_to_euler (custom.py:62-76)
+            roll = math.atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y))
+            t2 = max(-1.0, min(1.0, 2 * (w * y - z * x)))
+            pitch = math.asin(t2)
+            yaw = math.atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+            comp = int(lap[i, LAP["completion"]])
+            lap_completion = comp if lap[i, LAP["good_start"]] else comp - 100      # custom.py:132-140
+            laps = int(lap[i, LAP["laps"]])
+            out.append(VehicleStateSnapshot(laps=laps, velocity=qvel[i, 0:3], yaw=yaw, pitch=pitch, roll=roll,
+                                            lap_completion=lap_completion,
+                                            absolute_completion=laps * 100 + lap_completion,
+                                            time=self.steps / TIMESTEP))          # custom.py:1397 (sic)
+        return out
+
+    def state_dict(self):
+        self.sync()
+        return {k: getattr(self, k).cpu() for k in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "times",
+                                                     "winners", "status")} | {"steps": self.steps}
+
+    def load_state_dict(self, sd):
+        for k in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "times", "winners", "status"):
+            getattr(self, k).copy_(sd[k])
+        self.steps = int(sd["steps"])

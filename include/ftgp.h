@@ -115,13 +115,15 @@ int ftgp_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, cons
               const int32_t* track_id, int64_t ncars, int nsteps, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------ drivers */
-/* Device ports of the bundled drivers (nidc.py:116-131, fast.py:118-139, lobotomy.py):
- * kind: device int32[ncars] (FTGP_DRIVER_*) or NULL (= all `default_kind`).  Writes
- * ctrl[i] = (speed, steering) (custom.py:1418-1423).  active: device uint8[ncars] or NULL;
- * cars with active == 0 keep their ctrl (finished cars run LobotomyDriver -> (0,0) is
- * written instead when lobotomise_inactive != 0, custom.py:1437-1441). */
-int ftgp_drivers(const float* ranges, const int32_t* kind, int default_kind, double* ctrl,
-                 int64_t ncars, void* stream);
+/* Device ports of the bundled drivers (nidc.py:116-131, fast.py:118-139, lobotomy.py:1-3)
+ * followed by the control write ctrl[i] = (speed, steering) (custom.py:1418-1423).
+ * ranges: device float[ncars][90].  kind: device int32[ncars] (FTGP_DRIVER_*) or NULL
+ * (= every car runs `default_kind`).  lap: device lap state (see below) or NULL; a car
+ * whose FTGP_LAP_FINISHED field is set runs the lobotomy driver, as shadow() arranges
+ * (custom.py:1437).  A scan on which the Python driver would raise (NaN ->
+ * ValueError in int(np.ceil(nan))) leaves that car's ctrl untouched (custom.py:1409-1411). */
+int ftgp_drivers(const float* ranges, const int32_t* kind, int default_kind, const int32_t* lap,
+                 double* ctrl, int64_t ncars, void* stream);
 
 /* ------------------------------------------------------------------ lap logic */
 /* Replaces custom.py:1340-1372.  lap: device int32[ncars][FTGP_LAP_FIELDS] (see enum),

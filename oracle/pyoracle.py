@@ -102,11 +102,22 @@ class Track:
             raise ValueError(f"fto_centreline rc={rc}")
         return out
 
-    def scan(self, poses):
+    def scan(self, poses, threads=None):
+        """90-beam scan per pose; cars are independent, so they are spread over host threads
+        (ctypes releases the GIL around the C call)."""
         poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 7)
         out = np.zeros((len(poses), 90))
-        for i in range(len(poses)):
-            lib().fto_lidar_scan(self.ptr, _p(poses[i]), _p(out[i]))
+        L = lib()
+        def work(ix):
+            for i in ix:
+                L.fto_lidar_scan(self.ptr, _p(poses[i]), _p(out[i]))
+        threads = threads or min(os.cpu_count() or 1, 32)
+        if threads <= 1 or len(poses) < 64:
+            work(range(len(poses)))
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(work, np.array_split(np.arange(len(poses)), threads * 4)))
         return out
 
     def scan_world(self, poses, visible=None):
