@@ -54,9 +54,12 @@ __device__ __forceinline__ uint32_t mask_bit(const uint32_t* m, int bit) {
 
 // Intersect the ray (cell-local start (u,v), height z, per-metre increments du,dv,dz) with
 // the two triangles of one cell.  bits: b0 = (c,r), b1 = (c+1,r), b2 = (c,r+1), b3 = (c+1,r+1).
-// Returns the smallest parameter s >= smin at which it hits, or BIG.
+// Returns the smallest parameter s >= smin at which it hits, or BIG.  `unsure` is set when an
+// inside test landed within CELL_EPS of a triangle edge (or s within 1e-5 of smin): there the
+// fp32 decision is not trustworthy (a ray grazing a ridge by microns) and the caller re-runs
+// the cell in fp64 (cell_hit_exact).
 __device__ __forceinline__ float cell_hit(uint32_t bits, float u, float v, float z,
-                                          float du, float dv, float dz, float smin) {
+                                          float du, float dv, float dz, float smin, bool& unsure) {
     float h00 = (bits & 1u) ? HF_RANGE : 0.f, h10 = (bits & 2u) ? HF_RANGE : 0.f;
     float h01 = (bits & 4u) ? HF_RANGE : 0.f, h11 = (bits & 8u) ? HF_RANGE : 0.f;
     float best = BIG;
@@ -67,7 +70,10 @@ __device__ __forceinline__ float cell_hit(uint32_t bits, float u, float v, float
         if (fabsf(den) > 1e-15f) {
             float s = -num / den;
             float uu = u + s * du, vv = v + s * dv;
-            if (s >= smin && vv >= -CELL_EPS && vv <= uu + CELL_EPS && uu <= 1.f + CELL_EPS) best = s;
+            float m = fminf(fminf(vv, uu - vv), 1.f - uu);          // > 0 inside
+            if (s >= smin - 1e-5f && m >= -CELL_EPS) {
+                if (m <= CELL_EPS || s < smin + 1e-5f) unsure = true; else best = s;
+            }
         }
     }
     {   // triangle {(c,r), (c+1,r+1), (c,r+1)}: v >= u
@@ -77,10 +83,58 @@ __device__ __forceinline__ float cell_hit(uint32_t bits, float u, float v, float
         if (fabsf(den) > 1e-15f) {
             float s = -num / den;
             float uu = u + s * du, vv = v + s * dv;
-            if (s >= smin && s < best && uu >= -CELL_EPS && uu <= vv + CELL_EPS && vv <= 1.f + CELL_EPS) best = s;
+            float m = fminf(fminf(uu, vv - uu), 1.f - vv);
+            if (s >= smin - 1e-5f && m >= -CELL_EPS) {
+                if (m <= CELL_EPS || s < smin + 1e-5f) unsure = true; else if (s < best) best = s;
+            }
         }
     }
     return best;
+}
+
+// fp64 re-evaluation of one cell for a grazing ray: the ray is rebuilt from the car pose exactly as
+// the CPU restatement does, and the two triangles are tested without tolerance (hit point inside
+// the closed triangle, s >= 0).  Returns the absolute ray parameter or BIG.  Rare path (~1e-4 of cells).
+__device__ __noinline__ float cell_hit_exact(const TrackHeader* th, const double* __restrict__ pose7, int beam,
+                                             int ix, int iy, int ncol, int nrow, int cc, int rr, uint32_t bits) {
+    double q[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) q[k] = pose7[k];
+    double n = sqrt(q[3] * q[3] + q[4] * q[4] + q[5] * q[5] + q[6] * q[6]);
+    double w = q[3], x = q[4], y = q[5], z = q[6];
+    if (n < 1e-15) { w = 1; x = y = z = 0; } else { w /= n; x /= n; y /= n; z /= n; }
+    const double R0 = 1 - 2 * (y * y + z * z), R1 = 2 * (x * y - w * z), R2 = 2 * (x * z + w * y);
+    const double R3 = 2 * (x * y + w * z), R4 = 1 - 2 * (x * x + z * z), R5 = 2 * (y * z - w * x);
+    const double R6 = 2 * (x * z - w * y), R7 = 2 * (y * z + w * x), R8 = 1 - 2 * (x * x + y * y);
+    const double sb = c_beam_sc[beam][0], cb = c_beam_sc[beam][1];
+    const double rx = -0.0525, rz = 0.065, lr = 0.030;
+    const double dx = sb * R0 - cb * R1, dy = sb * R3 - cb * R4, dz = sb * R6 - cb * R7;
+    const double lx = rx - lr * sb, ly = lr * cb;
+    const double ox = q[0] + R0 * lx + R1 * ly + R2 * rz, oy = q[1] + R3 * lx + R4 * ly + R5 * rz,
+                 oz = q[2] + R6 * lx + R7 * ly + R8 * rz;
+    // chunk (ix, iy) is centred at (size_x * ix, size_y * (iy - (vc-1))); cell pitch = size / (n - 1)
+    const double cw = th->dsize_x / (ncol - 1), chh = th->dsize_y / (nrow - 1);
+    const double u = (ox - th->dsize_x * ix + 0.5 * th->dsize_x) / cw - cc;
+    const double v = (oy - th->dsize_y * (iy - (th->vc - 1)) + 0.5 * th->dsize_y) / chh - rr;
+    const double du = dx / cw, dv = dy / chh, zz = oz + 0.1;      // hfield geom z = -0.1 (mushr.em.xml:92)
+    const double H = 0.2 + 0.1;                                      // border_height + affordance (mushr.em.xml:55)
+    const double h00 = (bits & 1u) ? H : 0., h10 = (bits & 2u) ? H : 0., h01 = (bits & 4u) ? H : 0., h11 = (bits & 8u) ? H : 0.;
+    double best = 1e300;
+    {
+        double a = h10 - h00, b = h11 - h10, den = dz - a * du - b * dv, num = zz - h00 - a * u - b * v;
+        if (fabs(den) > 1e-15) {
+            double s = -num / den, uu = u + s * du, vv = v + s * dv;
+            if (s >= 0 && vv >= 0 && vv <= uu && uu <= 1) best = s;
+        }
+    }
+    {
+        double a = h11 - h01, b = h01 - h00, den = dz - a * du - b * dv, num = zz - h00 - a * u - b * v;
+        if (fabs(den) > 1e-15) {
+            double s = -num / den, uu = u + s * du, vv = v + s * dv;
+            if (s >= 0 && s < best && uu >= 0 && uu <= vv && vv <= 1) best = s;
+        }
+    }
+    return best < 1e300 ? (float)best : BIG;
 }
 
 // Vertical side face of a chunk's top box, crossed at parameter t.  axis 0: face normal to x
@@ -105,7 +159,8 @@ __device__ __forceinline__ bool face_hit(const uint32_t* m, int ncol, int nrow, 
 }
 
 // All hfield geoms + ground plane for one ray.  Returns distance or -1.
-__device__ float trace_walls(const uint32_t* __restrict__ sm, const TrackHeader* th, const Ray& ry) {
+__device__ float trace_walls(const uint32_t* __restrict__ sm, const TrackHeader* th, const Ray& ry,
+                             const double* __restrict__ pose7, int beam) {
     float best = BIG;
     // ground plane: hit only from the front side, inside the 300 m rendered square
     if (ry.dz < -1e-15f) {
@@ -214,7 +269,12 @@ __device__ float trace_walls(const uint32_t* __restrict__ sm, const TrackHeader*
                         int cc = major_x ? c : r, rr = major_x ? r : c;
                         uint32_t bits = mask_bits2(m, rr * ncol + cc) | (mask_bits2(m, (rr + 1) * ncol + cc) << 2);
                         if (bits == 0u && !floor_reach) continue;
-                        float s = cell_hit(bits, xa - (float)cc, ya - (float)rr, za, dfx, dfy, ry.dz, fmaxf(-ta, -1e-5f));
+                        bool unsure = false;
+                        float s = cell_hit(bits, xa - (float)cc, ya - (float)rr, za, dfx, dfy, ry.dz, -ta, unsure);
+                        if (unsure) {
+                            float sx = cell_hit_exact(th, pose7, beam, ix, iy, ncol, nrow, cc, rr, bits);
+                            s = sx < BIG ? sx - ta : BIG;
+                        }
                         if (s <= span + 1e-4f) found = fminf(found, s);
                     }
                     if (found < BIG || c == cend) break;
@@ -327,7 +387,7 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                 ry.fx0 = (float)(gxd - fgx); ry.fy0 = (float)(gyd - fgy);
                 ry.dgx = (float)(dwx[k] * inv_sx); ry.dgy = (float)(dwy[k] * inv_sy);
                 ry.lz = (float)(owz[k] - (double)HF_Z0); ry.dz = (float)dwz[k];
-                rng[k] = trace_walls(sm, th, ry);
+                rng[k] = trace_walls(sm, th, ry, qpos + car * stride, j);
             }
         }
         if (cpw > 1) {

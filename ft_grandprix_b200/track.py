@@ -100,7 +100,10 @@ class Track:
     def __del__(self):
         p = getattr(self, "_ptr", None)
         if p:
-            _lib.load().ftgp_track_destroy(p)
+            try:
+                _lib.load().ftgp_track_destroy(p)
+            except Exception:        # interpreter shutdown
+                pass
             self._ptr = None
 
 class Geometry:
@@ -122,5 +125,8 @@ class Geometry:
     def __del__(self):
         p = getattr(self, "_ptr", None)
         if p:
-            _lib.load().ftgp_geom_destroy(p)
+            try:
+                _lib.load().ftgp_geom_destroy(p)
+            except Exception:        # interpreter shutdown
+                pass
             self._ptr = None

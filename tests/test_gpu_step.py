@@ -1,0 +1,158 @@
+"""GPU: vehicle step and the fused tick against the CPU restatement, through the C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def ft():
+    import ft_grandprix_b200 as ft
+    return ft
+
+
+def _states(model, n, seed, max_pre=300, track=None):
+    """Diverse on-ground states: spawn like the reference, then drive the oracle for a random number of steps."""
+    rng = np.random.default_rng(seed)
+    Q, V, W, U = [], [], [], []
+    for i in range(n):
+        q, v, w = model.reset(rng.uniform(2, 38), -rng.uniform(2, 38), rng.uniform(-3, 3))
+        ctrl = np.array([rng.uniform(0, 5), rng.uniform(-0.8, 0.8)])
+        for k in range(int(rng.integers(0, max_pre))):
+            if k % 40 == 0:
+                ctrl = np.array([rng.uniform(0, 5), rng.uniform(-0.8, 0.8)])
+            model.step(None, q, v, w, ctrl)
+        Q.append(q); V.append(v); W.append(w); U.append(ctrl)
+    return np.array(Q), np.array(V), np.array(W), np.array(U)
+
+
+def _load(fleet, Q, V, W, U):
+    fleet.qpos.copy_(torch.from_numpy(Q)); fleet.qvel.copy_(torch.from_numpy(V))
+    fleet.warm.copy_(torch.from_numpy(W)); fleet.ctrl.copy_(torch.from_numpy(U))
+    torch.cuda.synchronize()
+
+
+def test_single_step_parity_1e5(ft, oracle):
+    """North star: single-step qpos/qvel within 1e-5 relative of the reference path (here: its restatement)."""
+    model = oracle.Model()
+    n = 256
+    Q, V, W, U = _states(model, n, seed=0)
+    t = ft.Track.bundled("track")
+    fleet = ft.Fleet(t, n)
+    fleet.geom_backup = fleet.geom
+    _load(fleet, Q, V, W, U)
+    # open ground (no walls): pure MuJoCo-restated dynamics
+    ft._lib.check(fleet.lib.ftgp_step(None, fleet.qpos.data_ptr(), fleet.qvel.data_ptr(), fleet.warm.data_ptr(),
+                                      fleet.ctrl.data_ptr(), None, n, 1, fleet.status.data_ptr(), fleet._s), "ftgp_step")
+    fleet.sync()
+    info = model.step_n(None, Q, V, W, U)
+    np.testing.assert_allclose(fleet.qpos.cpu().numpy(), Q, rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(fleet.qvel.cpu().numpy(), V, rtol=1e-5, atol=1e-9)
+    np.testing.assert_allclose(fleet.warm.cpu().numpy(), W, rtol=1e-5, atol=1e-6)
+    st = fleet.status.cpu().numpy()
+    assert ((st & 0xFF) == info[:, 0]).mean() > 0.99            # same Newton iteration counts
+    assert (((st >> 24) & 0xF) == info[:, 2]).all()             # same wheel-ground contact counts
+
+
+def test_trajectory_divergence_over_1000_ticks_is_reported(ft, oracle, capsys):
+    model = oracle.Model()
+    n = 32
+    Q, V, W, U = _states(model, n, seed=1, max_pre=1)
+    t = ft.Track.bundled("track")
+    fleet = ft.Fleet(t, n)
+    _load(fleet, Q, V, W, U)
+    div = []
+    for k in range(1000):
+        if k % 100 == 0:
+            rng = np.random.default_rng(k)
+            U = np.stack([rng.uniform(0.5, 4, n), rng.uniform(-0.5, 0.5, n)], 1)
+            fleet.ctrl.copy_(torch.from_numpy(U)); torch.cuda.synchronize()
+        ft._lib.check(fleet.lib.ftgp_step(None, fleet.qpos.data_ptr(), fleet.qvel.data_ptr(), fleet.warm.data_ptr(),
+                                          fleet.ctrl.data_ptr(), None, n, 1, None, fleet._s), "ftgp_step")
+        model.step_n(None, Q, V, W, U)
+        if k % 100 == 99:
+            fleet.sync()
+            div.append(float(np.abs(fleet.qpos.cpu().numpy()[:, :3] - Q[:, :3]).max()))
+    with capsys.disabled():
+        print("\n[report] max |xyz(GPU) - xyz(oracle)| every 100 ticks over 1000 ticks:", " ".join(f"{d:.1e}" for d in div))
+    assert div[-1] < 1e-3 and np.isfinite(div).all()
+
+
+def test_wall_contacts_match_oracle(ft, oracle, otracks):
+    """Cars pushed into walls: the framework's chassis-vs-hfield contact rule, GPU vs oracle."""
+    model = oracle.Model()
+    t = ft.Track.bundled("track")
+    n = 128
+    from conftest import random_poses
+    poses = random_poses(t.path, n, seed=4, level=True)
+    Q = np.zeros((n, 34)); V = np.zeros((n, 29)); W = np.zeros((n, 29)); U = np.tile([4.0, 0.0], (n, 1))
+    for i in range(n):
+        yaw = 2 * np.arctan2(poses[i, 6], poses[i, 3])
+        Q[i], V[i], W[i] = model.reset(poses[i, 0], poses[i, 1], yaw)
+    fleet = ft.Fleet(t, n)
+    _load(fleet, Q, V, W, U)
+    hits = 0
+    for k in range(700):
+        fleet.step(1)
+        info = model.step_n(otracks["track"], Q, V, W, U)
+        hits += int((info[:, 3] > 0).sum())
+        if k % 50 == 49:
+            fleet.sync()
+            st = fleet.status.cpu().numpy()
+            same = ((st >> 16) & 0xFF) == info[:, 3]
+            assert same.mean() > 0.95
+            # resynchronise so that one contact-timing difference cannot snowball
+            ok = np.abs(fleet.qpos.cpu().numpy() - Q).max(1) < 1e-6
+            assert ok.mean() > 0.9, ok.mean()
+            _load(fleet, Q, V, W, U)
+    assert hits > 100                                             # walls really were hit
+
+
+def test_full_tick_lockstep_short_race(ft, oracle, otracks, walls):
+    """Config-1/3 flavour: full tick (lap + nidc + lidar + step) on device vs the oracle pipeline fed the same
+    controls; ranges <= 1e-4 m, states <= 1e-5 rel, lap/finish results integer-exact."""
+    model = oracle.Model()
+    t = ft.Track.bundled("small-circle")
+    ot = otracks["small-circle"]
+    n = 40
+    fleet = ft.Fleet(t, n, driver="nidc", lap_target=1)
+    xy = np.array([t.start_pose(i % 40)[:2] for i in range(n)]); yaw = np.array([t.start_pose(i % 40)[2] for i in range(n)])
+    fleet.reset(xy, yaw)
+    fleet.lap[:, ft.fleet.LAP["offset"]] = torch.arange(n, dtype=torch.int32, device=fleet.device) * 2 + 10
+    torch.cuda.synchronize()
+    Q = np.zeros((n, 34)); V = np.zeros((n, 29)); W = np.zeros((n, 29)); U = np.zeros((n, 2))
+    for i in range(n):
+        Q[i], V[i], W[i] = model.reset(xy[i, 0], xy[i, 1], yaw[i])
+    laps = [oracle.Lap(offset=10 + 2 * i, max_times=16) for i in range(n)]
+    ranges = np.zeros((n, 90))
+    worst_r = worst_q = 0.0
+    for k in range(1500):
+        # oracle tick (custom.py:1337-1426)
+        for i in range(n):
+            laps[i].update(t.path, Q[i, :2], k, 1, 0)
+            r = oracle.driver(2 if laps[i].s.finished else 0, ranges[i])
+            if r is not None:
+                U[i] = r
+        new_ranges = ot.scan(Q[:, :7])
+        model.step_n(ot, Q, V, W, U)
+        fleet.tick(1)
+        if k % 25 == 0 or k == 1499:
+            fleet.sync()
+            g = fleet.ranges.cpu().numpy().astype(np.float64)
+            assert ((g < 0) == (new_ranges < 0)).all()
+            worst_r = max(worst_r, np.abs(g - new_ranges).max())
+            gq = fleet.qpos.cpu().numpy()
+            worst_q = max(worst_q, np.abs(gq - Q).max())
+            np.testing.assert_allclose(fleet.ctrl.cpu().numpy(), U, rtol=0, atol=1e-9)
+        # lock-step: the oracle's next driver call sees exactly what the device driver will see
+        fleet.sync()
+        ranges = fleet.ranges.cpu().numpy().astype(np.float64)
+        Q[:] = fleet.qpos.cpu().numpy(); V[:] = fleet.qvel.cpu().numpy(); W[:] = fleet.warm.cpu().numpy()
+    assert worst_r <= 1e-4 and worst_q <= 1e-6, (worst_r, worst_q)
+    lap = fleet.lap.cpu().numpy(); L = ft.fleet.LAP
+    for i in range(n):
+        s = laps[i].s
+        for f in ("completion", "laps", "start", "good_start", "finished", "ntimes", "off_track", "delta"):
+            assert lap[i, L[f]] == getattr(s, f), (i, f)
+    assert lap[:, L["completion"]].max() > 5                      # the cars really drove

@@ -1,0 +1,166 @@
+"""CPU: the mj_step restatement (oracle/step.c) checked against physical invariants, and the product's
+kernel source (csrc/mushr_step.cuh) compiled for the host and compared with it.
+
+The host build of the kernel source exists ONLY here (tests/host_harness): the GPU box runs the same
+source as a CUDA kernel, the product never links a CPU build of it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+P = lambda a: a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def model(oracle):
+    return oracle.Model()
+
+
+@pytest.fixture(scope="module")
+def host_kernel():
+    src = os.path.join(ROOT, "tests", "host_harness", "step_host.cpp")
+    out = os.path.join(ROOT, "tests", "host_harness", "libstep_host.so")
+    deps = [src] + [os.path.join(ROOT, "ft_grandprix_b200", "csrc", f) for f in ("mushr_step.cuh", "mushr_consts.h", "mushr_mesh.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", out, src])
+    return C.CDLL(out)
+
+
+def random_state(model, rng):
+    q = model.reset(0, 0, 0)[0]
+    q[0:3] = rng.normal(size=3)
+    q[3:7] = rng.normal(size=4); q[3:7] /= np.linalg.norm(q[3:7])
+    for a in (11, 18, 24, 30):
+        q[a:a + 4] = rng.normal(size=4); q[a:a + 4] /= np.linalg.norm(q[a:a + 4])
+    q[[7, 8, 9, 10, 15, 16, 17, 22, 23, 28, 29]] = rng.normal(size=11) * 0.3
+    return q
+
+
+def test_model_constants(model):
+    c = model.constants()
+    assert abs(c["body_mass"].sum() - 5.6328) < 1e-3                      # SURVEY A.1 total mass
+    assert abs(c["body_mass"][1] - (3.542137 + 1000 * np.pi * 0.03 ** 2 * 0.03)) < 1e-12
+    # ellipsoid inertia m/5 (b^2+c^2, a^2+c^2, a^2+b^2)
+    np.testing.assert_allclose(np.diag(c["body_inertia"][3]), 0.498952 / 5 * np.array([0.001, 0.0018, 0.001]), rtol=1e-12)
+    # translational invweight of a free body of mass m coupled to nothing would be 1/m; the car's is below 1/m_chassis
+    assert 1 / 5.64 < c["dof_invweight0"][0] < 0.5    # origin is off the CoM and the wheels slide in z: above 1/m_total
+    assert np.allclose(c["dof_invweight0"][0:3], c["dof_invweight0"][0]) and np.allclose(c["dof_invweight0"][10:13], c["dof_invweight0"][10])
+    assert 0.5 < c["meaninertia"] < 0.8
+
+
+def test_mass_matrix_spd_and_inverse_dynamics_consistency(model):
+    """CRB mass matrix is SPD; RNE with acceleration equals M qacc + bias (two independent recursions)."""
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        q = random_state(model, rng)
+        v, a = rng.normal(size=29), rng.normal(size=29)
+        M = model.mass_matrix(q)
+        assert np.abs(M - M.T).max() == 0 and np.linalg.eigvalsh(M).min() > 0
+        np.testing.assert_allclose(M @ a + model.bias(q, v), model.inverse(q, v, a), rtol=0, atol=1e-11)
+
+
+def test_bias_matches_lagrangian_finite_differences(model):
+    """qfrc_bias = C(q, v) + dV/dq: checked for the scalar joints (hinge/slide) with central differences of
+    the kinetic energy T = v^T M v / 2 and the gravitational potential, other joints at rest."""
+    rng = np.random.default_rng(1)
+    sj = [(7, 6), (8, 7), (9, 8), (10, 9), (15, 13), (16, 14), (17, 15), (22, 19), (23, 20), (28, 24), (29, 25)]   # (qadr, dadr)
+    q = random_state(model, rng)
+    v = np.zeros(29)
+    for _, d in sj:
+        v[d] = rng.normal()
+    bias = model.bias(q, v)
+    eps = 1e-6
+    def T(qq): return 0.5 * v @ model.mass_matrix(qq) @ v
+    def V(qq): return model.energy(qq, np.zeros(29)) - 0.5 * 500 * sum((qq[a] + 0.015) ** 2 for a in (8, 15, 22, 28))
+    # d/dt (dT/dv_i) - dT/dq_i + dV/dq_i with qacc = 0: sum_k dM_ij/dq_k v_k v_j - dT/dq_i + dV/dq_i
+    Mdot = np.zeros((29, 29))
+    for qa, d in sj:
+        qp, qm = q.copy(), q.copy(); qp[qa] += eps; qm[qa] -= eps
+        Mdot += (model.mass_matrix(qp) - model.mass_matrix(qm)) / (2 * eps) * v[d]
+    for qa, d in sj:
+        qp, qm = q.copy(), q.copy(); qp[qa] += eps; qm[qa] -= eps
+        want = (Mdot @ v)[d] - (T(qp) - T(qm)) / (2 * eps) + (V(qp) - V(qm)) / (2 * eps)
+        assert abs(bias[d] - want) < 1e-6 * max(1, abs(want)), (d, bias[d], want)
+
+
+def test_free_flight_conserves_momentum_and_falls_at_g(model):
+    q, v, w = model.reset(0, 0, 0)
+    q[2] = 5.0
+    v[0], v[5] = 1.0, 2.0
+    c = model.constants()
+    mass = c["body_mass"].sum()
+    for k in range(50):
+        rc, info = model.step(None, q, v, w, np.zeros(2))
+        assert rc == 0 and info[2] == 0            # no contacts
+    # vertical velocity of the free joint ~ -g t (origin is ~2 cm from the CoM and the body spins: small wobble)
+    assert abs(v[2] + 9.81 * 0.2) < 5e-3
+
+
+def test_settles_on_ground_and_reaches_servo_speed(model):
+    q, v, w = model.reset(1.0, 2.0, 0.3)
+    for k in range(2500):
+        rc, info = model.step(None, q, v, w, np.array([2.0, 0.0]))
+        assert rc == 0
+    assert info[2] == 4 and info[0] <= 3                                   # 4 wheel contacts, Newton converged fast
+    assert abs(q[2] - 0.0151) < 5e-4                                       # ride height (~0.0156 minus sag)
+    assert np.all(q[[8, 15, 22, 28]] > -0.002) and np.all(q[[8, 15, 22, 28]] < 0.002)   # suspensions on their stops
+    spin = v[[9, 15, 20, 25]]
+    # velocity servo kv=100, gear 0.04 on the mean spin, against 0.01 N m s wheel damping: 100 (u - 0.04 s) 0.01 = 0.01 s
+    assert np.allclose(spin, 2.0 / 0.05, rtol=2e-3)
+    assert abs(np.hypot(v[0], v[1]) - 0.03 * spin.mean()) < 2e-2          # rolling without slipping, r = 0.03
+    assert abs(np.arctan2(v[1], v[0]) - 0.3) < 0.03                       # straight along the spawn heading
+
+
+def test_ackermann_equality_holds(model):
+    q, v, w = model.reset(0, 0, 0)
+    for k in range(600):
+        model.step(None, q, v, w, np.array([1.0, 0.3]))
+    x = q[7]
+    assert abs(x - 0.3) < 2e-3
+    pl = x + 0.375 * x ** 2 + 0.140625 * x ** 3 - 0.0722656 * x ** 4
+    pr = x - 0.375 * x ** 2 + 0.140625 * x ** 3 + 0.0722656 * x ** 4
+    assert abs(q[9] - pl) < 2e-3 and abs(q[16] - pr) < 2e-3
+    assert v[5] > 0.3                                                       # it turns left
+
+
+def test_bad_state_resets_like_mujoco(model):
+    q, v, w = model.reset(3, 4, 1)
+    v[0] = 1e11
+    rc, _ = model.step(None, q, v, w, np.zeros(2))
+    assert rc == 1 and abs(q[1] - 2.0) < 1e-2 and abs(q[0]) < 1e-2          # back at qpos0 (0, 2, 0)
+
+
+def test_product_kernel_source_matches_oracle_constants(model, host_kernel):
+    d, w4, c2 = np.zeros(31), np.zeros(4), np.zeros(2)
+    host_kernel.hh_constants(P(d), P(w4), P(c2))
+    c = model.constants()
+    pad = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, -1, 20, 21, 22, 23, 24, -1, 25, 26, 27, 28]
+    for p, dof in enumerate(pad):
+        if dof >= 0:
+            assert abs(d[p] / c["dof_invweight0"][dof] - 1) < 1e-12
+    np.testing.assert_allclose(w4, c["body_invweight0"][[3, 5, 7, 9], 0], rtol=1e-12)
+    np.testing.assert_allclose(c2, [c["body_invweight0"][1, 0], c["meaninertia"]], rtol=1e-12)
+
+
+def test_product_kernel_source_single_step_parity(model, host_kernel):
+    """1e-5 relative bar (north star) -- the two implementations (generic dense vs block-arrow) agree to ~1e-13."""
+    rng = np.random.default_rng(3)
+    worst = 0
+    for car in range(6):
+        q, v, w = model.reset(rng.normal(), rng.normal(), rng.uniform(-3, 3))
+        for k in range(250):
+            ctrl = np.array([rng.uniform(0, 4), rng.uniform(-0.6, 0.6)]) if k % 25 == 0 else ctrl
+            qo, vo, wo = q.copy(), v.copy(), w.copy()
+            model.step(None, qo, vo, wo, ctrl)
+            qh, vh, wh = q.copy(), v.copy(), w.copy()
+            info = np.zeros(4, dtype=np.int32)
+            host_kernel.hh_step(P(qh), P(vh), P(wh), P(ctrl), 1, P(info))
+            np.testing.assert_allclose(qh, qo, rtol=1e-5, atol=1e-10)
+            np.testing.assert_allclose(vh, vo, rtol=1e-5, atol=1e-9)
+            worst = max(worst, np.abs(vh - vo).max())
+            q, v, w = qo, vo, wo
+    assert worst < 1e-10
