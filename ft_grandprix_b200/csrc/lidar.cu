@@ -299,27 +299,30 @@ __device__ float trace_walls(const uint32_t* __restrict__ sm, const TrackHeader*
 }
 
 // other car's lidar cylinder (mushr.em.xml:108): r = 0.03, half height 0.015, centred at
-// (rx, 0, rz - lh/2) in that car's frame.  lp/lv: ray in the cylinder frame.
-__device__ __forceinline__ float ray_cylinder(float px, float py, float pz, float vx, float vy, float vz,
-                                              float r, float hh) {
-    float best = BIG;
-    if (fabsf(vz) > 1e-15f) {
-#pragma unroll
-        for (int side = -1; side <= 1; side += 2) {
-            float s = ((float)side * hh - pz) / vz;
-            if (s >= 0.f) {
-                float x = px + s * vx, y = py + s * vy;
-                if (x * x + y * y <= r * r) best = fminf(best, s);
-            }
+// (rx, 0, rz - lh/2) in that car's frame.  p/v: ray in the cylinder frame.  fp64: the target is 3 cm
+// wide, so b^2 - a c cancels badly in fp32 for grazing rays (mju_rayGeom's cylinder branch restated).
+__device__ __forceinline__ double ray_cylinder(double px, double py, double pz, double vx, double vy, double vz,
+                                               double r, double hh) {
+    double best = -1.0;
+    const double a = vx * vx + vy * vy, b = px * vx + py * vy, c = px * px + py * py - r * r;
+    if (a > 1e-15) {
+        double det = b * b - a * c;
+        if (det >= 1e-15) {
+            det = sqrt(det);
+            const double x0 = (-b - det) / a, x1 = (-b + det) / a;
+            const double s = x0 >= 0 ? x0 : (x1 >= 0 ? x1 : -1.0);
+            if (s >= 0 && fabs(pz + s * vz) <= hh) best = s;
         }
     }
-    float a = vx * vx + vy * vy, b = px * vx + py * vy, c = px * px + py * py - r * r;
-    float det = b * b - a * c;
-    if (det >= 1e-15f && a > 0.f) {
-        det = sqrtf(det);
-        float x0 = (-b - det) / a, x1 = (-b + det) / a;
-        float s = x0 >= 0.f ? x0 : (x1 >= 0.f ? x1 : -1.f);
-        if (s >= 0.f && fabsf(pz + s * vz) <= hh) best = fminf(best, s);
+    if (fabs(vz) > 1e-15) {
+#pragma unroll
+        for (int side = -1; side <= 1; side += 2) {
+            const double s = ((double)side * hh - pz) / vz;
+            if (s >= 0) {
+                const double x = px + s * vx, y = py + s * vy;
+                if (x * x + y * y <= r * r && (best < 0 || s < best)) best = s;
+            }
+        }
     }
     return best;
 }
@@ -401,15 +404,15 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                 for (int k = 0; k < 3; k++) {
                     if (lane + 32 * k >= FTGP_NBEAMS) continue;
                     // ray in the other car's frame, relative to its cylinder centre
-                    double ex = owx[k] - Q.p[0], ey = owy[k] - Q.p[1], ez = owz[k] - Q.p[2];
-                    float px = (float)(Q.R[0] * ex + Q.R[3] * ey + Q.R[6] * ez - rx);
-                    float py = (float)(Q.R[1] * ex + Q.R[4] * ey + Q.R[7] * ez);
-                    float pz = (float)(Q.R[2] * ex + Q.R[5] * ey + Q.R[8] * ez - (rz - 0.015 / 2));
-                    float vx = (float)(Q.R[0] * dwx[k] + Q.R[3] * dwy[k] + Q.R[6] * dwz[k]);
-                    float vy = (float)(Q.R[1] * dwx[k] + Q.R[4] * dwy[k] + Q.R[7] * dwz[k]);
-                    float vz = (float)(Q.R[2] * dwx[k] + Q.R[5] * dwy[k] + Q.R[8] * dwz[k]);
-                    float s = ray_cylinder(px, py, pz, vx, vy, vz, 0.03f, 0.015f);
-                    if (s < BIG && (rng[k] < 0.f || s < rng[k])) rng[k] = s;
+                    const double ex = owx[k] - Q.p[0], ey = owy[k] - Q.p[1], ez = owz[k] - Q.p[2];
+                    const double px = Q.R[0] * ex + Q.R[3] * ey + Q.R[6] * ez - rx;
+                    const double py = Q.R[1] * ex + Q.R[4] * ey + Q.R[7] * ez;
+                    const double pz = Q.R[2] * ex + Q.R[5] * ey + Q.R[8] * ez - (rz - 0.015 / 2);
+                    const double vx = Q.R[0] * dwx[k] + Q.R[3] * dwy[k] + Q.R[6] * dwz[k];
+                    const double vy = Q.R[1] * dwx[k] + Q.R[4] * dwy[k] + Q.R[7] * dwz[k];
+                    const double vz = Q.R[2] * dwx[k] + Q.R[5] * dwy[k] + Q.R[8] * dwz[k];
+                    const double s = ray_cylinder(px, py, pz, vx, vy, vz, 0.03, 0.015);
+                    if (s >= 0 && (rng[k] < 0.f || (float)s < rng[k])) rng[k] = (float)s;
                 }
             }
         }
