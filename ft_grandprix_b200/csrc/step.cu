@@ -9,6 +9,8 @@
 // pre-step pose -> mj_step (the reference's one-tick sensor lag is kept).
 #include "common.h"
 #include "mushr_consts.h"
+#include "mushr_step_warp.cuh"
+#include <cstdlib>
 
 namespace ftgp {
 using namespace mushr;
@@ -29,61 +31,114 @@ static int ensure_model(int device) {
 // chassis-vs-wall contacts (this framework's definition, identical to oracle/step.c wall_contacts()):
 // each chassis hull vertex below the hfield surface gives one condim-3 contact against the surface
 // triangle's plane.  Reads the compiled track from global memory (L2-resident, ~50 KB).
-struct Walls {
+struct WallHit { double dist, nrm[3], t1[3], t2[3], pnt[3]; };
+
+__device__ bool wall_probe(const uint32_t* blob, const TrackHeader* th, const double* R1, const double* p1, int v, WallHit& h) {
+    const double hull[MUSHR_CHASSIS_NHULL][3] = MUSHR_CHASSIS_HULL;
+    const uint16_t* index = reinterpret_cast<const uint16_t*>(blob + th->index_off);
+    const uint32_t* chunks = blob + th->chunks_off;
+    double p[3];
+    mat_vec3(p, R1, hull[v]);
+    for (int a = 0; a < 3; a++) p[a] += p1[a];
+    const int i = (int)floor(p[0] / th->dsize_x + 0.5), j = (int)floor(-p[1] / th->dsize_y + 0.5);
+    if (i < 0 || i >= th->hc || j < 0 || j >= th->vc) return false;
+    const uint32_t cid = index[(th->vc - 1 - j) * th->hc + i];
+    if (cid == EMPTY_CHUNK) return false;
+    const uint32_t* m = chunks + cid * CHUNK_WORDS;
+    const int ncol = m[13] & 0xFF, nrow = (m[13] >> 8) & 0xFF;
+    const double sx = 0.5 * th->dsize_x, sy = 0.5 * th->dsize_y;
+    const double dx = 2 * sx / (ncol - 1), dy = 2 * sy / (nrow - 1);
+    const double u = (p[0] - th->dsize_x * i + sx) / dx, vv = (p[1] + th->dsize_y * j + sy) / dy;
+    int cc = (int)floor(u), rr = (int)floor(vv);
+    cc = cc < 0 ? 0 : (cc > ncol - 2 ? ncol - 2 : cc); rr = rr < 0 ? 0 : (rr > nrow - 2 ? nrow - 2 : rr);
+    const double fu = u - cc, fv = vv - rr;
+    auto bit = [&](int r_, int c_) { int b = r_ * ncol + c_; return (double)((m[b >> 5] >> (b & 31)) & 1u) * 0.3; };
+    const double z00 = bit(rr, cc), z10 = bit(rr, cc + 1), z01 = bit(rr + 1, cc), z11 = bit(rr + 1, cc + 1);
+    double gx, gy, z;
+    if (fv <= fu) { gx = (z10 - z00) / dx; gy = (z11 - z10) / dy; z = z00 + (z10 - z00) * fu + (z11 - z10) * fv; }
+    else { gx = (z11 - z01) / dx; gy = (z01 - z00) / dy; z = z00 + (z11 - z01) * fu + (z01 - z00) * fv; }
+    const double nn = sqrt(gx * gx + gy * gy + 1);
+    h.nrm[0] = -gx / nn; h.nrm[1] = -gy / nn; h.nrm[2] = 1 / nn;
+    const double hh = -0.1 + z;
+    if (hh <= -0.1 + 1e-12 && h.nrm[2] > 0.999999) return false;
+    h.dist = (p[2] - hh) * h.nrm[2];
+    if (h.dist >= 0) return false;
+    // frame (mju_makeFrame)
+    h.t1[0] = h.t1[1] = h.t1[2] = 0;
+    if (h.nrm[1] < 0.5 && h.nrm[1] > -0.5) h.t1[1] = 1; else h.t1[2] = 1;
+    const double d = dot3(h.nrm, h.t1);
+    for (int a = 0; a < 3; a++) h.t1[a] -= d * h.nrm[a];
+    const double tn = sqrt(dot3(h.t1, h.t1));
+    for (int a = 0; a < 3; a++) h.t1[a] /= tn;
+    cross3(h.t2, h.nrm, h.t1);
+    for (int a = 0; a < 3; a++) h.pnt[a] = p[a] - h.nrm[a] * h.dist * 0.5;
+    return true;
+}
+
+struct Walls {                                  // thread-per-car flavour
     const uint32_t* blob; const TrackHeader* th;
     __device__ void operator()(const ModelConsts& mc, const Kin& k, Rows& r) const {
         if (!blob) return;
-        const double hull[MUSHR_CHASSIS_NHULL][3] = MUSHR_CHASSIS_HULL;
-        const uint16_t* index = reinterpret_cast<const uint16_t*>(blob + th->index_off);
-        const uint32_t* chunks = blob + th->chunks_off;
         for (int v = 0; v < MUSHR_CHASSIS_NHULL && r.ncon < MAXCON; v++) {
-            double p[3];
-            mat_vec3(p, k.R1, hull[v]);
-            for (int a = 0; a < 3; a++) p[a] += k.p1[a];
-            const int i = (int)floor(p[0] / th->dsize_x + 0.5), j = (int)floor(-p[1] / th->dsize_y + 0.5);
-            if (i < 0 || i >= th->hc || j < 0 || j >= th->vc) continue;
-            const uint32_t cid = index[(th->vc - 1 - j) * th->hc + i];
-            if (cid == EMPTY_CHUNK) continue;
-            const uint32_t* m = chunks + cid * CHUNK_WORDS;
-            const int ncol = m[13] & 0xFF, nrow = (m[13] >> 8) & 0xFF;
-            const double sx = 0.5 * th->dsize_x, sy = 0.5 * th->dsize_y;
-            const double dx = 2 * sx / (ncol - 1), dy = 2 * sy / (nrow - 1);
-            const double u = (p[0] - th->dsize_x * i + sx) / dx, vv = (p[1] + th->dsize_y * j + sy) / dy;
-            int cc = (int)floor(u), rr = (int)floor(vv);
-            cc = cc < 0 ? 0 : (cc > ncol - 2 ? ncol - 2 : cc); rr = rr < 0 ? 0 : (rr > nrow - 2 ? nrow - 2 : rr);
-            const double fu = u - cc, fv = vv - rr;
-            auto bit = [&](int r_, int c_) { int b = r_ * ncol + c_; return (double)((m[b >> 5] >> (b & 31)) & 1u) * 0.3; };
-            const double z00 = bit(rr, cc), z10 = bit(rr, cc + 1), z01 = bit(rr + 1, cc), z11 = bit(rr + 1, cc + 1);
-            double gx, gy, z;
-            if (fv <= fu) { gx = (z10 - z00) / dx; gy = (z11 - z10) / dy; z = z00 + (z10 - z00) * fu + (z11 - z10) * fv; }
-            else { gx = (z11 - z01) / dx; gy = (z01 - z00) / dy; z = z00 + (z11 - z01) * fu + (z01 - z00) * fv; }
-            const double nn = sqrt(gx * gx + gy * gy + 1);
-            double nrm[3] = {-gx / nn, -gy / nn, 1 / nn};
-            const double h = -0.1 + z;
-            if (h <= -0.1 + 1e-12 && nrm[2] > 0.999999) continue;
-            const double dist = (p[2] - h) * nrm[2];
-            if (dist >= 0) continue;
+            WallHit h;
+            if (!wall_probe(blob, th, k.R1, k.p1, v, h)) continue;
             Contact& c = r.con[r.ncon++];
-            c.dist = dist; c.mu = 1.0; c.dmin = 0.9; c.wheel = -1; c.tran = mc.chassis_invweight0;
-            // frame (mju_makeFrame)
-            double t1[3] = {0, 0, 0};
-            if (nrm[1] < 0.5 && nrm[1] > -0.5) t1[1] = 1; else t1[2] = 1;
-            const double d = dot3(nrm, t1);
-            for (int a = 0; a < 3; a++) t1[a] -= d * nrm[a];
-            const double tn = sqrt(dot3(t1, t1));
-            for (int a = 0; a < 3; a++) t1[a] /= tn;
-            double t2[3];
-            cross3(t2, nrm, t1);
+            c.dist = h.dist; c.mu = 1.0; c.dmin = 0.9; c.wheel = -1; c.tran = mc.chassis_invweight0;
             double off[3];
-            for (int a = 0; a < 3; a++) off[a] = p[a] - nrm[a] * dist * 0.5 - k.com[a];
+            for (int a = 0; a < 3; a++) off[a] = h.pnt[a] - k.com[a];
             for (int col = 0; col < 9; col++) {
                 double jp[3] = {0, 0, 0};
                 if (col < 6) { cross3(jp, k.cdof[col], off); for (int a = 0; a < 3; a++) jp[a] += k.cdof[col][3 + a]; }
-                c.J[0][col] = dot3(nrm, jp); c.J[1][col] = dot3(t1, jp); c.J[2][col] = dot3(t2, jp);
+                c.J[0][col] = dot3(h.nrm, jp); c.J[1][col] = dot3(h.t1, jp); c.J[2][col] = dot3(h.t2, jp);
             }
         }
     }
 };
+
+struct WallsWarp {                              // warp-per-car flavour: lane v probes hull vertex v
+    const uint32_t* blob; const TrackHeader* th;
+    __device__ int operator()(const ModelConsts& mc, WarpShared& S, const double* com, int T, int ncon) const {
+        if (!blob) return ncon;
+        WallHit h;
+        const bool hit = T < MUSHR_CHASSIS_NHULL && wall_probe(blob, th, S.R1, S.p1, T, h);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const int slot = ncon + __popc(m & ((1u << T) - 1));
+        if (hit && slot < MAXCON) {
+            S.cdist[slot] = h.dist; S.cmu[slot] = 1.0; S.cdmin[slot] = 0.9; S.ctran[slot] = mc.chassis_invweight0; S.cwheel[slot] = -1;
+            for (int a = 0; a < 3; a++) { S.cpnt[slot][a] = h.pnt[a]; S.cframe[slot][a] = h.nrm[a]; S.cframe[slot][3 + a] = h.t1[a]; S.cframe[slot][6 + a] = h.t2[a]; }
+        }
+        const int n = ncon + __popc(m);
+        return n > MAXCON ? MAXCON : n;
+    }
+};
+
+__global__ void __launch_bounds__(128)
+step_warp_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
+                 double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
+                 const int32_t* __restrict__ lap, int64_t ncars, int nsteps, int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    WarpShared* SS = reinterpret_cast<WarpShared*>(smraw);
+    const int T = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t car = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (car >= ncars) return;
+    WarpShared& S = SS[wib];
+    WallsWarp walls{nullptr, nullptr};
+    const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
+    if (blob && !shadowed) {
+        const GeomHeader* gh = reinterpret_cast<const GeomHeader*>(blob);
+        int tid = track_id ? track_id[car] : 0;
+        if (tid < 0 || tid >= gh->ntracks) tid = 0;
+        walls.blob = blob; walls.th = reinterpret_cast<const TrackHeader*>(blob + gh->track_off[tid]);
+    }
+    int st = 0;
+    for (int s = 0; s < nsteps; s++) {
+        StepInfo info;
+        step_car_warp(S, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, T, info);
+        __syncwarp();
+        st = (info.iters & 0xFF) | (info.reset ? 0x100 : (st & 0x100)) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24);
+    }
+    if (status && T == 0) status[car] = st;
+}
 
 __global__ void __launch_bounds__(64)
 step_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
@@ -121,9 +176,25 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     int dev = 0;
     FTGP_CUDA(cudaGetDevice(&dev));
     int rc = ensure_model(dev); if (rc) return rc;
-    const int threads = 64;
-    step_kernel<<<(unsigned)((ncars + threads - 1) / threads), threads, 0, stream>>>(
-        g ? g->d_blob : nullptr, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status);
+    // FTGP_STEP_IMPL=thread selects the round-1 thread-per-car kernel (kept as the in-library A/B reference)
+    static int impl = -1;
+    if (impl < 0) { const char* e = getenv("FTGP_STEP_IMPL"); impl = (e && e[0] == 't') ? 1 : 0; }
+    const uint32_t* blob = g ? g->d_blob : nullptr;
+    if (impl == 1) {
+        const int threads = 64;
+        step_kernel<<<(unsigned)((ncars + threads - 1) / threads), threads, 0, stream>>>(
+            blob, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status);
+    } else {
+        const int warps = 4;
+        const size_t smem = warps * sizeof(WarpShared);
+        static bool attr[16] = {false};
+        if (dev < 16 && !attr[dev]) {
+            FTGP_CUDA(cudaFuncSetAttribute(step_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr[dev] = true;
+        }
+        step_warp_kernel<<<(unsigned)((ncars + warps - 1) / warps), warps * 32, smem, stream>>>(
+            blob, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status);
+    }
     count_launch();
     FTGP_CUDA(cudaGetLastError());
     return FTGP_OK;
