@@ -174,7 +174,8 @@ FT_HDN void arrow_mul(const Arrow& A, const double* x, double* y) {
         for (int j = 0; j < NR; j++) { double s = 0; for (int l = 0; l < NC; l++) s += A.B[w][l][j] * xc[l]; y[j] += s; }
     }
 }
-// in-place Cholesky: W_w = L_w L_w^T, B_w <- Y_w = L_w^{-1} B_w, R <- chol(R - sum_w Y_w^T Y_w)
+// in-place Cholesky: W_w = L_w L_w^T, B_w <- Y_w = L_w^{-1} B_w, R <- chol(R - sum_w Y_w^T Y_w).
+// The diagonals of the factors hold 1 / L_jj (every later use divides by them).
 FT_HDN void arrow_factor(Arrow& A) {
     for (int w = 0; w < 4; w++) {
         double* L = A.W[w];
@@ -182,8 +183,8 @@ FT_HDN void arrow_factor(Arrow& A) {
             double d = L[tri(j, j)];
             for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)];
             if (d < MINVAL) d = MINVAL;
-            d = sqrt(d); L[tri(j, j)] = d;
-            double id = 1.0 / d;
+            const double id = 1.0 / sqrt(d);
+            L[tri(j, j)] = id;
             for (int i = j + 1; i < NC; i++) {
                 double s = L[tri(i, j)];
                 for (int k = 0; k < j; k++) s -= L[tri(i, k)] * L[tri(j, k)];
@@ -194,7 +195,7 @@ FT_HDN void arrow_factor(Arrow& A) {
             for (int l = 0; l < NC; l++) {
                 double s = A.B[w][l][c];
                 for (int k = 0; k < l; k++) s -= L[tri(l, k)] * A.B[w][k][c];
-                A.B[w][l][c] = s / L[tri(l, l)];
+                A.B[w][l][c] = s * L[tri(l, l)];
             }
         for (int i = 0; i < NR; i++)
             for (int j = 0; j <= i; j++) {
@@ -208,8 +209,8 @@ FT_HDN void arrow_factor(Arrow& A) {
         double d = L[tri(j, j)];
         for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)];
         if (d < MINVAL) d = MINVAL;
-        d = sqrt(d); L[tri(j, j)] = d;
-        double id = 1.0 / d;
+        const double id = 1.0 / sqrt(d);
+        L[tri(j, j)] = id;
         for (int i = j + 1; i < NR; i++) {
             double s = L[tri(i, j)];
             for (int k = 0; k < j; k++) s -= L[tri(i, k)] * L[tri(j, k)];
@@ -224,17 +225,17 @@ FT_HDN void arrow_solve(const Arrow& A, double* x) {
         for (int l = 0; l < NC; l++) {
             double s = xc[l];
             for (int k = 0; k < l; k++) s -= L[tri(l, k)] * xc[k];
-            xc[l] = s / L[tri(l, l)];
+            xc[l] = s * L[tri(l, l)];
         }
         for (int j = 0; j < NR; j++) { double s = 0; for (int l = 0; l < NC; l++) s += A.B[w][l][j] * xc[l]; x[j] -= s; }
     }
     const double* L = A.R;
-    for (int i = 0; i < NR; i++) { double s = x[i]; for (int k = 0; k < i; k++) s -= L[tri(i, k)] * x[k]; x[i] = s / L[tri(i, i)]; }
-    for (int i = NR - 1; i >= 0; i--) { double s = x[i]; for (int k = i + 1; k < NR; k++) s -= L[tri(k, i)] * x[k]; x[i] = s / L[tri(i, i)]; }
+    for (int i = 0; i < NR; i++) { double s = x[i]; for (int k = 0; k < i; k++) s -= L[tri(i, k)] * x[k]; x[i] = s * L[tri(i, i)]; }
+    for (int i = NR - 1; i >= 0; i--) { double s = x[i]; for (int k = i + 1; k < NR; k++) s -= L[tri(k, i)] * x[k]; x[i] = s * L[tri(i, i)]; }
     for (int w = 0; w < 4; w++) {                       // backward: x_w = L_w^{-T} (z_w - Y_w x_r)
         const double* Lw = A.W[w]; double* xc = x + NR + NC * w;
         for (int l = 0; l < NC; l++) { double s = 0; for (int j = 0; j < NR; j++) s += A.B[w][l][j] * x[j]; xc[l] -= s; }
-        for (int l = NC - 1; l >= 0; l--) { double s = xc[l]; for (int k = l + 1; k < NC; k++) s -= Lw[tri(k, l)] * xc[k]; xc[l] = s / Lw[tri(l, l)]; }
+        for (int l = NC - 1; l >= 0; l--) { double s = xc[l]; for (int k = l + 1; k < NC; k++) s -= Lw[tri(k, l)] * xc[k]; xc[l] = s * Lw[tri(l, l)]; }
     }
 }
 
@@ -467,8 +468,9 @@ FT_HD double impedance(double dmin, double dmax, double width, double mid, doubl
     double x = fabs(pos / width);
     if (x >= 1) return dmax;
     if (x == 0) return dmin;
-    double y;
-    if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
+    double y;                                           // power == 2 for every solimp of this model
+    if (power == 2.0) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
+    else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
     else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
     return dmin + y * (dmax - dmin);
 }
@@ -655,7 +657,7 @@ FT_HDN double rows_cost(const Rows& r, const double* x, double* qfrc, Arrow* H) 
 
 // line-search evaluation: total cost and its first two derivatives at qacc + alpha * search
 struct LsPoint { double alpha, cost, d0, d1; };
-struct LsCtx { const Rows* r; const double* x; const double* s; double qg0, qg1, qg2; };
+struct LsCtx { const Rows* r; const double* x; const double* s; double qg0, qg1, qg2; double cdx[MAXCON][3], cds[MAXCON][3]; };
 
 FT_HDN void ls_eval(const LsCtx& c, LsPoint& pt, double alpha) {
     const Rows& r = *c.r; const double* x = c.x; const double* s = c.s;
@@ -683,8 +685,7 @@ FT_HDN void ls_eval(const LsCtx& c, LsPoint& pt, double alpha) {
     }
     for (int cc = 0; cc < r.ncon; cc++) {
         const Contact& ct = r.con[cc];
-        double dx[3], ds[3];
-        contact_dots(ct, x, dx); contact_dots(ct, s, ds);
+        const double* dx = c.cdx[cc]; const double* ds = c.cds[cc];
         const double D = r.con_D[cc];
         for (int rr = 0; rr < 4; rr++) {
             const double sg = (rr & 1) ? -1.0 : 1.0; const int ta = 1 + (rr >> 1);
@@ -707,6 +708,7 @@ FT_HDN double line_search(const Rows& r, const Arrow& M, Solver& s, const double
     LsCtx c; c.r = &r; c.x = s.qacc; c.s = s.search;
     c.qg0 = s.gauss; c.qg1 = 0; c.qg2 = 0;
     for (int p = 0; p < NP; p++) { c.qg1 += s.search[p] * (s.Ma[p] - qfrc_smooth[p]); c.qg2 += 0.5 * s.search[p] * s.Mv[p]; }
+    for (int cc = 0; cc < r.ncon; cc++) { contact_dots(r.con[cc], s.qacc, c.cdx[cc]); contact_dots(r.con[cc], s.search, c.cds[cc]); }
     const double gtol = SOLVER_TOL * LS_TOL * snorm / scale;
     LsPoint p0, p1, p2, pm, a1, a2;
     int it = 0;

@@ -25,20 +25,25 @@ struct WarpShared {
     double q[NQ];
     double R1[9], p1[3], p2[3], xi1[3];
     double pw[4][3], ps[4][3];
-    double axis[NP][3];
-    double cdof[NP][6];
-    double inert[10][10];      // 0 car body, 1 steering wheel, 2+w wheel, 6+w softener
-    double cfrc[10][6];
+    union {                    // the position-stage scratch is dead before H is first written
+        struct {
+            double axis[NP][3];
+            double cdof[NP][6];
+            double inert[10][10];      // 0 car body, 1 steering wheel, 2+w wheel, 6+w softener
+            double cfrc[10][6];
+        };
+        Arrow H;
+    };
     double cframe[MAXCON][9], cpnt[MAXCON][3], cdist[MAXCON], cmu[MAXCON], cdmin[MAXCON], ctran[MAXCON];
     int cwheel[MAXCON];
     double J[MAXCON][3][9];
     double conD[MAXCON], conAref[MAXCON][4], conK[MAXCON][5], conF[MAXCON][3];
     double eqD[2], eqDer[2], eqF[2];
-    Arrow M, H;
+    Arrow M;
     double X[32], V[32];
 };
 
-__device__ __forceinline__ double warp_sum(double v) {
+__device__ __noinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -46,11 +51,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ double dot6(const double* a, const double* b) {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5];
 }
-__device__ __forceinline__ double rcp_pivot(double d) { return 1.0 / (d < MINVAL ? MINVAL : d); }
+__device__ __forceinline__ double rcp_pivot(double d) { return __drcp_rn(d < MINVAL ? MINVAL : d); }
 
 // ---- cooperative block-arrow algebra (A in shared memory; x vectors in shared memory, padded, 32 entries)
 // y_p = (A x)_p for lane p
-__device__ __forceinline__ double arrow_mul_w(const Arrow& A, const double* x, int p) {
+__device__ __noinline__ double arrow_mul_w(const Arrow& A, const double* x, int p) {
     double s = 0;
     if (p < NR) {
 #pragma unroll
@@ -69,52 +74,38 @@ __device__ __forceinline__ double arrow_mul_w(const Arrow& A, const double* x, i
     return s;
 }
 
-// in-place LDL^T of a lower-triangular packed n x n block with `nl` cooperating lanes (t = 0..nl-1);
-// on exit the diagonal holds 1/d_k and the strict lower part the unit-lower factor.
+// in-place LDL^T of a lower-triangular packed N x N block in shared memory; lane t (< N) owns row t.
+// On exit the diagonal holds 1/d_k and the strict lower part the unit-lower factor.
 template <int N>
-__device__ __forceinline__ void ldl_block(double* A, int t, int nl) {
+__device__ __forceinline__ void ldl_block(double* A, int t) {
 #pragma unroll
-    for (int k = 0; k < N; k++) {
+    for (int k = 0; k < N - 1; k++) {
         const double inv = rcp_pivot(A[tri(k, k)]);
-        // read phase: trailing entries (i, m), k < m <= i < N, spread over the lanes
-        constexpr int MAXE = (N - 1) * N / 2;
-        double upd[(MAXE + 7) / 8 > 0 ? (MAXE + 7) / 8 : 1];
-        double col = 0;
-        const int ne = (N - 1 - k) * (N - k) / 2;
+        const bool act = t > k && t < N;
+        double aik = 0, upd[N];
+        if (act) {
+            aik = A[tri(t, k)];
+            const double s = aik * inv;
 #pragma unroll
-        for (int r = 0; r < (MAXE + 7) / 8; r++) {
-            const int e = t + r * nl;
-            upd[r] = 0;
-            if (e < ne && r * nl < ne) {
-                // e -> (a, b) with 0 <= b <= a < N-1-k : i = k+1+a, m = k+1+b
-                int a = 0;
-                while ((a + 1) * (a + 2) / 2 <= e) a++;
-                const int b = e - a * (a + 1) / 2;
-                upd[r] = A[tri(k + 1 + a, k)] * A[tri(k + 1 + b, k)] * inv;
-            }
+            for (int m = k + 1; m < N; m++) upd[m] = (m <= t) ? s * A[tri(m, k)] : 0.0;
         }
-        if (t < N - 1 - k) col = A[tri(k + 1 + t, k)] * inv;
         __syncwarp();
+        if (act) {
 #pragma unroll
-        for (int r = 0; r < (MAXE + 7) / 8; r++) {
-            const int e = t + r * nl;
-            if (e < ne && r * nl < ne) {
-                int a = 0;
-                while ((a + 1) * (a + 2) / 2 <= e) a++;
-                const int b = e - a * (a + 1) / 2;
-                A[tri(k + 1 + a, k + 1 + b)] -= upd[r];
-            }
+            for (int m = k + 1; m < N; m++) if (m <= t) A[tri(t, m)] -= upd[m];
+            A[tri(t, k)] = aik * inv;
         }
-        if (t < N - 1 - k) A[tri(k + 1 + t, k)] = col;
-        if (t == 0) A[tri(k, k)] = inv;
+        if (t == k) A[tri(k, k)] = inv;
         __syncwarp();
     }
+    if (t == N - 1) A[tri(N - 1, N - 1)] = rcp_pivot(A[tri(N - 1, N - 1)]);
+    __syncwarp();
 }
 
 // A <- factor: W_w = L D L^T (diag holds 1/d), B_w <- Y_w = L_w^{-1} B_w, R <- LDL^T(R - sum_w Y_w^T D_w^{-1} Y_w)
-__device__ __forceinline__ void arrow_factor_w(Arrow& A, int T) {
+__device__ __noinline__ void arrow_factor_w(Arrow& A, int T) {
     const int g = T >> 3, t = T & 7;
-    ldl_block<NC>(A.W[g], t, 8);
+    ldl_block<NC>(A.W[g], t);
     if (t < NR) {                                   // column t of the border, forward substitution in registers
         double y[NC];
 #pragma unroll
@@ -140,11 +131,11 @@ __device__ __forceinline__ void arrow_factor_w(Arrow& A, int T) {
         A.R[T] = s;
     }
     __syncwarp();
-    ldl_block<NR>(A.R, T, 32);
+    ldl_block<NR>(A.R, T);
 }
 
 // X <- A^{-1} X (X in shared memory)
-__device__ __forceinline__ void arrow_solve_w(const Arrow& A, double* X, int T) {
+__device__ __noinline__ void arrow_solve_w(const Arrow& A, double* X, int T) {
     const int g = T >> 3, t = T & 7;
     if (t == 0) {                                   // z_w = L_w^{-1} x_w
         double z[NC];
@@ -215,7 +206,7 @@ __device__ __forceinline__ void arrow_solve_w(const Arrow& A, double* X, int T) 
     __syncwarp();
 }
 
-__device__ __forceinline__ void arrow_copy_w(Arrow& dst, const Arrow& src, int T) {
+__device__ __noinline__ void arrow_copy_w(Arrow& dst, const Arrow& src, int T) {
     double* d = reinterpret_cast<double*>(&dst); const double* s = reinterpret_cast<const double*>(&src);
     constexpr int n = sizeof(Arrow) / sizeof(double);
     for (int i = T; i < n; i += 32) d[i] = s[i];
@@ -244,7 +235,7 @@ struct LaneRows {
 // Evaluates all rows at acceleration x (own entry xp; the full vector must already be in S.X).
 // Returns the lane's cost share; fp = lane's entry of J^T force; hd = quadratic-row weight to add on H's diagonal.
 // Contact lanes also publish K (J^T D J weights) and F (frame forces) in shared memory.
-__device__ __forceinline__ double eval_rows_w(WarpShared& S, const LaneRows& r, int p, int T, int ncon, double xp,
+__device__ __noinline__ double eval_rows_w(WarpShared& S, const LaneRows& r, int p, int T, int ncon, double xp,
                                               double& fp, double& hd, double* cjar3, double& eqjar) {
     double cost = 0; fp = 0; hd = 0;
     if (r.frf > 0) {
@@ -315,7 +306,7 @@ __device__ __forceinline__ double eval_rows_w(WarpShared& S, const LaneRows& r, 
 }
 
 // H = M + J^T D J for the rows that eval_rows_w found quadratic (hd per lane, K per contact)
-__device__ __forceinline__ void assemble_H_w(WarpShared& S, const LaneRows& r, int p, int T, int ncon, double hd) {
+__device__ __noinline__ void assemble_H_w(WarpShared& S, const LaneRows& r, int p, int T, int ncon, double hd) {
     arrow_copy_w(S.H, S.M, T);
     // contact blocks
     if (T < 21) {                                    // root-root (i, j < 6)
@@ -360,6 +351,37 @@ __device__ __forceinline__ void assemble_H_w(WarpShared& S, const LaneRows& r, i
 }
 
 struct LsTot { double alpha, cost, d0, d1; };
+struct LsLane { const LaneRows* r; double x, search, eqjar, eqjv, cj3[3], cs3[3], qg0, qg1, qg2; bool contact; };
+
+// line-search point: total cost and derivatives at qacc + a * search (all lanes call; sums are warp-wide)
+__device__ __noinline__ LsTot ls_eval_w(const LsLane& L, double a) {
+    const LaneRows& r = *L.r;
+    const double x = L.x, search = L.search;
+    double q0 = 0, q1 = 0, q2 = 0;
+    if (r.frf > 0) {
+        const double jar = x - r.frAref, jv = search, xx = jar + a * jv;
+        if (xx <= -r.frRf) { q0 += r.frf * (-0.5 * r.frRf - jar); q1 += -r.frf * jv; }
+        else if (xx >= r.frRf) { q0 += r.frf * (-0.5 * r.frRf + jar); q1 += r.frf * jv; }
+        else { q0 += 0.5 * r.frD * jar * jar; q1 += r.frD * jar * jv; q2 += 0.5 * r.frD * jv * jv; }
+    }
+    if (r.limSign) {
+        const double jar = r.limSign * x - r.limAref, jv = r.limSign * search;
+        if (jar + a * jv < 0) { q0 += 0.5 * r.limD * jar * jar; q1 += r.limD * jar * jv; q2 += 0.5 * r.limD * jv * jv; }
+    }
+    if (r.eqw >= 0) { q0 += 0.5 * r.eqD * L.eqjar * L.eqjar; q1 += r.eqD * L.eqjar * L.eqjv; q2 += 0.5 * r.eqD * L.eqjv * L.eqjv; }
+    if (L.contact) {
+        for (int rr = 0; rr < 4; rr++) {
+            const double sg = (rr & 1) ? -1.0 : 1.0; const int ta = 1 + (rr >> 1);
+            const double jar = L.cj3[0] + sg * r.cmu * L.cj3[ta] - r.cAref[rr], jv = L.cs3[0] + sg * r.cmu * L.cs3[ta];
+            if (jar + a * jv < 0) { q0 += 0.5 * r.cD * jar * jar; q1 += r.cD * jar * jv; q2 += 0.5 * r.cD * jv * jv; }
+        }
+    }
+    q0 = warp_sum(q0) + L.qg0; q1 = warp_sum(q1) + L.qg1; q2 = warp_sum(q2) + L.qg2;
+    LsTot t;
+    t.alpha = a; t.cost = a * a * q2 + a * q1 + q0; t.d0 = 2 * a * q2 + q1; t.d1 = 2 * q2;
+    if (t.d1 <= 0) t.d1 = MINVAL;
+    return t;
+}
 
 // one car, one warp.  status bits as in ftgp.h.
 template <class WallFn>
@@ -660,16 +682,19 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
     }
     const double scale = 1.0 / (mc.meaninertia * NV);
     double cost, gauss, grad, search;
-    // Newton direction at x
-    auto direction = [&]() {
+    // cost, constraint forces and gradient at x
+    auto evaluate = [&]() {
         S.X[T] = x;
         __syncwarp();
         double c = eval_rows_w(S, r, p, T, ncon, x, fp, hd, cj3, eqjar);
         const double g = 0.5 * (Ma - qfs) * (x - qas);
         gauss = warp_sum(g);
         cost = warp_sum(c) + gauss;
-        assemble_H_w(S, r, p, T, ncon, hd);
         grad = (p < NP) ? Ma - qfs - fp : 0.0;
+    };
+    // Newton direction: search = -H^{-1} grad, H = M + J^T D J over the rows evaluate() found quadratic
+    auto solve_direction = [&]() {
+        assemble_H_w(S, r, p, T, ncon, hd);
         arrow_factor_w(S.H, T);
         S.X[T] = grad;
         __syncwarp();
@@ -677,7 +702,8 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
         search = -S.X[T];
         __syncwarp();
     };
-    direction();
+    evaluate();
+    solve_direction();
     int iter = 0;
     while (iter < SOLVER_ITER) {
         // ---- exact line search (PrimalSearch)
@@ -703,33 +729,11 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
                 __syncwarp();
                 const double qg0 = gauss, qg1 = warp_sum(search * (Ma - qfs)), qg2 = warp_sum(0.5 * search * Mv);
                 const double gtol = SOLVER_TOL * LS_TOL * snorm / scale;
-                auto ev = [&](double a) {
-                    double q0 = 0, q1 = 0, q2 = 0;
-                    if (r.frf > 0) {
-                        const double jar = x - r.frAref, jv = search, xx = jar + a * jv;
-                        if (xx <= -r.frRf) { q0 += r.frf * (-0.5 * r.frRf - jar); q1 += -r.frf * jv; }
-                        else if (xx >= r.frRf) { q0 += r.frf * (-0.5 * r.frRf + jar); q1 += r.frf * jv; }
-                        else { q0 += 0.5 * r.frD * jar * jar; q1 += r.frD * jar * jv; q2 += 0.5 * r.frD * jv * jv; }
-                    }
-                    if (r.limSign) {
-                        const double jar = r.limSign * x - r.limAref, jv = r.limSign * search;
-                        if (jar + a * jv < 0) { q0 += 0.5 * r.limD * jar * jar; q1 += r.limD * jar * jv; q2 += 0.5 * r.limD * jv * jv; }
-                    }
-                    if (r.eqw >= 0) { q0 += 0.5 * r.eqD * eqjar * eqjar; q1 += r.eqD * eqjar * eqjv; q2 += 0.5 * r.eqD * eqjv * eqjv; }
-                    if (T < ncon) {
-#pragma unroll
-                        for (int rr = 0; rr < 4; rr++) {
-                            const double sg = (rr & 1) ? -1.0 : 1.0; const int ta = 1 + (rr >> 1);
-                            const double jar = cj3[0] + sg * r.cmu * cj3[ta] - r.cAref[rr], jv = cs3[0] + sg * r.cmu * cs3[ta];
-                            if (jar + a * jv < 0) { q0 += 0.5 * r.cD * jar * jar; q1 += r.cD * jar * jv; q2 += 0.5 * r.cD * jv * jv; }
-                        }
-                    }
-                    q0 = warp_sum(q0) + qg0; q1 = warp_sum(q1) + qg1; q2 = warp_sum(q2) + qg2;
-                    LsTot t;
-                    t.alpha = a; t.cost = a * a * q2 + a * q1 + q0; t.d0 = 2 * a * q2 + q1; t.d1 = 2 * q2;
-                    if (t.d1 <= 0) t.d1 = MINVAL;
-                    return t;
-                };
+                LsLane L;
+                L.r = &r; L.x = x; L.search = search; L.eqjar = eqjar; L.eqjv = eqjv;
+                L.cj3[0] = cj3[0]; L.cj3[1] = cj3[1]; L.cj3[2] = cj3[2]; L.cs3[0] = cs3[0]; L.cs3[1] = cs3[1]; L.cs3[2] = cs3[2];
+                L.qg0 = qg0; L.qg1 = qg1; L.qg2 = qg2; L.contact = T < ncon;
+                auto ev = [&](double a) { return ls_eval_w(L, a); };
                 LsTot p0 = ev(0), p1 = ev(p0.alpha - p0.d0 / p0.d1), p2, pm, a1, a2;
                 if (p0.cost < p1.cost) p1 = p0;
                 bool done = fabs(p1.d0) < gtol;
@@ -772,10 +776,13 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
         }
         if (alpha == 0) break;
         const double oldcost = cost;
-        direction();
+        evaluate();
         const double gn = warp_sum(grad * grad);
         iter++;
+        // MuJoCo factorises H before this test; the direction is unused when the test ends the loop,
+        // so the factorisation is skipped then (same qacc, one block-arrow LDL^T less per step)
         if (scale * (oldcost - cost) < SOLVER_TOL || scale * sqrt(gn) < SOLVER_TOL) break;
+        solve_direction();
     }
     info.iters = iter;
     if (__any_sync(FULL, bad_value(x))) {                 // mj_checkAcc

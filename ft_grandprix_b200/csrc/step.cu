@@ -112,7 +112,7 @@ struct WallsWarp {                              // warp-per-car flavour: lane v 
     }
 };
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 step_warp_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
                  double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
                  const int32_t* __restrict__ lap, int64_t ncars, int nsteps, int32_t* __restrict__ status) {
@@ -176,20 +176,25 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     int dev = 0;
     FTGP_CUDA(cudaGetDevice(&dev));
     int rc = ensure_model(dev); if (rc) return rc;
-    // FTGP_STEP_IMPL=thread selects the round-1 thread-per-car kernel (kept as the in-library A/B reference)
+    // Two implementations of the same arithmetic (both parity-tested): thread-per-car (default: fewer issue
+    // slots per car, local-memory bound) and warp-per-car (FTGP_STEP_IMPL=warp: state in registers / shared
+    // memory, instruction-fetch bound).  Measured on B200 at 65,536 cars: 3.8 ms vs 9.3 ms per step.
     static int impl = -1;
-    if (impl < 0) { const char* e = getenv("FTGP_STEP_IMPL"); impl = (e && e[0] == 't') ? 1 : 0; }
+    if (impl < 0) { const char* e = getenv("FTGP_STEP_IMPL"); impl = (e && e[0] == 'w') ? 0 : 1; }
     const uint32_t* blob = g ? g->d_blob : nullptr;
     if (impl == 1) {
-        const int threads = 64;
+        static int threads = 0;
+        if (!threads) { const char* e = getenv("FTGP_STEP_BLOCK"); threads = e ? atoi(e) : 64; if (threads < 32 || threads > 64) threads = 64; }
         step_kernel<<<(unsigned)((ncars + threads - 1) / threads), threads, 0, stream>>>(
             blob, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status);
     } else {
-        const int warps = 4;
+        static int warps = 0;
+        if (!warps) { const char* e = getenv("FTGP_STEP_WARPS"); warps = e ? atoi(e) : 4; if (warps < 1 || warps > 4) warps = 4; }
         const size_t smem = warps * sizeof(WarpShared);
         static bool attr[16] = {false};
         if (dev < 16 && !attr[dev]) {
             FTGP_CUDA(cudaFuncSetAttribute(step_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FTGP_CUDA(cudaFuncSetAttribute(step_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             attr[dev] = true;
         }
         step_warp_kernel<<<(unsigned)((ncars + warps - 1) / warps), warps * 32, smem, stream>>>(
