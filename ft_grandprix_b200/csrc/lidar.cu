@@ -158,146 +158,6 @@ __device__ __forceinline__ bool face_hit(const uint32_t* m, int ncol, int nrow, 
     return zt < prof;
 }
 
-// All hfield geoms + ground plane for one ray.  Returns distance or -1.
-__device__ float trace_walls(const uint32_t* __restrict__ sm, const TrackHeader* th, const Ray& ry,
-                             const double* __restrict__ pose7, int beam) {
-    float best = BIG;
-    // ground plane: hit only from the front side, inside the 300 m rendered square
-    if (ry.dz < -1e-15f) {
-        float tp = -(ry.lz + HF_Z0 - PLANE_Z) / ry.dz;
-        if (tp >= 0.f) {
-            float px = ((float)ry.ix0 + ry.fx0 - 0.5f + tp * ry.dgx) * th->size_x;
-            float py = ((float)(ry.iy0 - (th->vc - 1)) + ry.fy0 - 0.5f + tp * ry.dgy) * th->size_y;
-            if (fabsf(px) <= PLANE_HALF && fabsf(py) <= PLANE_HALF) best = tp;
-        }
-    }
-    // parameter interval in which the ray is inside the walls' height slab [0, 0.3]
-    float tz0 = 0.f, tz1 = BIG;
-    if (fabsf(ry.dz) > 1e-15f) {
-        float a = (0.f - ry.lz) / ry.dz, b = (HF_RANGE - ry.lz) / ry.dz;
-        tz0 = fmaxf(0.f, fminf(a, b)); tz1 = fmaxf(a, b);
-    } else if (ry.lz < 0.f || ry.lz > HF_RANGE) tz1 = -1.f;
-    float tend = fminf(tz1, best);
-    if (tend < tz0) return best < BIG ? best : -1.f;
-
-    // clip against the chunk grid [0,hc] x [0,vc]
-    const int hc = th->hc, vc = th->vc;
-    float gx = (float)ry.ix0 + ry.fx0, gy = (float)ry.iy0 + ry.fy0;
-    float tg0 = 0.f, tg1 = tend;
-    int enter_axis = -1;
-    const float inv_dgx = fabsf(ry.dgx) > 1e-20f ? 1.f / ry.dgx : 0.f;
-    const float inv_dgy = fabsf(ry.dgy) > 1e-20f ? 1.f / ry.dgy : 0.f;
-    if (inv_dgx != 0.f) {
-        float a = (0.f - gx) * inv_dgx, b = ((float)hc - gx) * inv_dgx;
-        float lo = fminf(a, b), hi = fmaxf(a, b);
-        if (lo > tg0) { tg0 = lo; enter_axis = 0; }
-        tg1 = fminf(tg1, hi);
-    } else if (gx < 0.f || gx >= (float)hc) tg1 = -1.f;
-    if (inv_dgy != 0.f) {
-        float a = (0.f - gy) * inv_dgy, b = ((float)vc - gy) * inv_dgy;
-        float lo = fminf(a, b), hi = fmaxf(a, b);
-        if (lo > tg0) { tg0 = lo; enter_axis = 1; }
-        tg1 = fminf(tg1, hi);
-    } else if (gy < 0.f || gy >= (float)vc) tg1 = -1.f;
-    if (tg1 < tg0) return best < BIG ? best : -1.f;
-    float ts = tg0;
-    if (tz0 > ts) { ts = tz0; enter_axis = -1; }   // dropping into the slab from above: no side face
-    if (ts > tend) return best < BIG ? best : -1.f;
-
-    const int stepx = ry.dgx >= 0.f ? 1 : -1, stepy = ry.dgy >= 0.f ? 1 : -1;
-    // chunk containing the start point (relative to the origin cell to keep fp32 exact)
-    float relx = ry.fx0 + ts * ry.dgx, rely = ry.fy0 + ts * ry.dgy;
-    int ix = ry.ix0 + (int)floorf(relx), iy = ry.iy0 + (int)floorf(rely);
-    if (enter_axis == 0) ix = stepx > 0 ? 0 : hc - 1;
-    if (enter_axis == 1) iy = stepy > 0 ? 0 : vc - 1;
-    ix = min(max(ix, 0), hc - 1); iy = min(max(iy, 0), vc - 1);
-
-    const uint16_t* index = reinterpret_cast<const uint16_t*>(sm + th->index_off);
-    const uint32_t* chunks = sm + th->chunks_off;
-    float t0 = ts;
-    int entry_axis = enter_axis;
-    for (int guard = 0; guard < 512; guard++) {
-        // exit of this chunk
-        float tmx = inv_dgx != 0.f ? ((float)(ix - ry.ix0 + (stepx > 0 ? 1 : 0)) - ry.fx0) * inv_dgx : BIG;
-        float tmy = inv_dgy != 0.f ? ((float)(iy - ry.iy0 + (stepy > 0 ? 1 : 0)) - ry.fy0) * inv_dgy : BIG;
-        int exit_axis = tmx <= tmy ? 0 : 1;
-        float t1 = fminf(tmx, tmy);
-        uint32_t cid = index[iy * hc + ix];
-        if (cid != EMPTY_CHUNK) {
-            const uint32_t* m = chunks + cid * CHUNK_WORDS;
-            const int ncol = m[13] & 0xFF, nrow = (m[13] >> 8) & 0xFF;
-            const float nx = (float)(ncol - 1), ny = (float)(nrow - 1);
-            // fine-cell coordinates inside this chunk: f(t) = fo + t * df
-            const float fxo = ((float)(ry.ix0 - ix) + ry.fx0) * nx, dfx = ry.dgx * nx;
-            const float fyo = ((float)(ry.iy0 - iy) + ry.fy0) * ny, dfy = ry.dgy * ny;
-            const float inv_h = 1.f / HF_RANGE;
-            // entry side face
-            if (entry_axis >= 0 && t0 <= tend) {
-                bool far_side = entry_axis == 0 ? stepx < 0 : stepy < 0;
-                float along = entry_axis == 0 ? fyo + t0 * dfy : fxo + t0 * dfx;
-                if (face_hit(m, ncol, nrow, entry_axis, far_side, along, (ry.lz + t0 * ry.dz) * inv_h))
-                    return fminf(best, t0);
-            }
-            float ta = fmaxf(t0, tz0), tb = fminf(t1, tend);
-            if (ta <= tb) {
-                // re-origin at ta
-                const float xa = fxo + ta * dfx, ya = fyo + ta * dfy, za = ry.lz + ta * ry.dz;
-                const float span = tb - ta;
-                const bool floor_reach = fminf(za, za + span * ry.dz) <= 0.f;
-                const bool major_x = fabsf(dfx) >= fabsf(dfy);
-                const float dM = major_x ? dfx : dfy, dm = major_x ? dfy : dfx;
-                const float Ma = major_x ? xa : ya, ma = major_x ? ya : xa;
-                const int nM = major_x ? ncol - 1 : nrow - 1, nm = major_x ? nrow - 1 : ncol - 1;
-                const int sg = dM >= 0.f ? 1 : -1;
-                const float inv_dM = fabsf(dM) > 1e-20f ? 1.f / dM : 0.f;
-                float Mb = Ma + span * dM;
-                int c = (int)floorf(Ma - (float)sg * 1e-3f), cend = (int)floorf(Mb + (float)sg * 1e-3f);
-                c = min(max(c, 0), nM - 1); cend = min(max(cend, 0), nM - 1);
-                float found = BIG;
-                for (;;) {
-                    // parameter interval (relative to ta) spent in major-cell c
-                    float s0 = 0.f, s1 = span;
-                    if (inv_dM != 0.f) {
-                        float e0 = ((float)(c + (sg > 0 ? 0 : 1)) - Ma) * inv_dM;
-                        float e1 = ((float)(c + (sg > 0 ? 1 : 0)) - Ma) * inv_dM;
-                        s0 = fmaxf(s0, e0); s1 = fminf(s1, e1);
-                    }
-                    float m0 = ma + s0 * dm, m1 = ma + s1 * dm;
-                    int rlo = (int)floorf(fminf(m0, m1) - 1e-3f), rhi = (int)floorf(fmaxf(m0, m1) + 1e-3f);
-                    rlo = min(max(rlo, 0), nm - 1); rhi = min(max(rhi, 0), nm - 1);
-                    for (int r = rlo; r <= rhi; r++) {
-                        int cc = major_x ? c : r, rr = major_x ? r : c;
-                        uint32_t bits = mask_bits2(m, rr * ncol + cc) | (mask_bits2(m, (rr + 1) * ncol + cc) << 2);
-                        if (bits == 0u && !floor_reach) continue;
-                        bool unsure = false;
-                        float s = cell_hit(bits, xa - (float)cc, ya - (float)rr, za, dfx, dfy, ry.dz, -ta, unsure);
-                        if (unsure) {
-                            float sx = cell_hit_exact(th, pose7, beam, ix, iy, ncol, nrow, cc, rr, bits);
-                            s = sx < BIG ? sx - ta : BIG;
-                        }
-                        if (s <= span + 1e-4f) found = fminf(found, s);
-                    }
-                    if (found < BIG || c == cend) break;
-                    c += sg;
-                }
-                if (found < BIG) return fminf(best, fmaxf(ta + found, 0.f));
-            }
-            // exit side face
-            if (t1 <= tend) {
-                bool far_side = exit_axis == 0 ? stepx > 0 : stepy > 0;
-                float along = exit_axis == 0 ? fyo + t1 * dfy : fxo + t1 * dfx;
-                if (face_hit(m, ncol, nrow, exit_axis, far_side, along, (ry.lz + t1 * ry.dz) * inv_h))
-                    return fminf(best, t1);
-            }
-        }
-        if (t1 >= tend) break;
-        if (exit_axis == 0) ix += stepx; else iy += stepy;
-        if (ix < 0 || ix >= hc || iy < 0 || iy >= vc) break;
-        t0 = t1; entry_axis = exit_axis;
-    }
-    return best < BIG ? best : -1.f;
-}
-
 // other car's lidar cylinder (mushr.em.xml:108): r = 0.03, half height 0.015, centred at
 // (rx, 0, rz - lh/2) in that car's frame.  p/v: ray in the cylinder frame.  fp64: the target is 3 cm
 // wide, so b^2 - a c cancels badly in fp32 for grazing rays (mju_rayGeom's cylinder branch restated).
@@ -327,27 +187,46 @@ __device__ __forceinline__ double ray_cylinder(double px, double py, double pz, 
     return best;
 }
 
-struct Pose { double p[3], R[9]; };
+// ---------------------------------------------------------------------------------------------------
+// Traversal as a per-lane state machine.  A warp owns a batch of cars (whole worlds) and a pool of
+// 90 x ncars rays; every lane runs IDLE -> CHUNK (one Amanatides-Woo step over the 0.5 m chunk grid)
+// -> SWEEP (one major-axis column of 19x19 cells inside a non-empty chunk) -> ... -> IDLE, and an idle
+// lane pulls the next ray of the pool.  Each loop iteration executes each of the three short code
+// blocks at most once for the whole warp, so lanes never wait for another lane's inner loop
+// (the first version traced beams l, l+32, l+64 per lane with nested loops: 6.5 of 32 lanes active).
+enum { ST_IDLE = 0, ST_CHUNK = 1, ST_SWEEP = 2 };
+constexpr int BATCH = 8;              // max cars per warp batch (a batch holds whole worlds: cars_per_world 1, 2, 4 or 8)
+constexpr int FRAME_DOUBLES = 12;     // p[3], R[9]
 
-__device__ __forceinline__ void load_pose(const double* __restrict__ qpos, int64_t stride, int64_t car,
-                                          int lane, Pose& P) {
-    double v = lane < 7 ? qpos[car * stride + lane] : 0.0;
-    double q[7];
-#pragma unroll
-    for (int k = 0; k < 7; k++) q[k] = __shfl_sync(0xffffffffu, v, k);
-    double n = sqrt(q[3] * q[3] + q[4] * q[4] + q[5] * q[5] + q[6] * q[6]);
-    double w = q[3], x = q[4], y = q[5], z = q[6];
-    if (n < 1e-15) { w = 1; x = y = z = 0; } else { w /= n; x /= n; y /= n; z /= n; }
-    P.p[0] = q[0]; P.p[1] = q[1]; P.p[2] = q[2];
-    P.R[0] = 1 - 2 * (y * y + z * z); P.R[1] = 2 * (x * y - w * z); P.R[2] = 2 * (x * z + w * y);
-    P.R[3] = 2 * (x * y + w * z); P.R[4] = 1 - 2 * (x * x + z * z); P.R[5] = 2 * (y * z - w * x);
-    P.R[6] = 2 * (x * z - w * y); P.R[7] = 2 * (y * z + w * x); P.R[8] = 1 - 2 * (x * x + y * y);
+struct Lane {
+    // ray
+    int ix0, iy0; float fx0, fy0, dgx, dgy, lz, dz;
+    float inv_dgx, inv_dgy; int stepx, stepy;
+    float tz0, tend, best;
+    // chunk DDA
+    int ix, iy; float t0; int entry_axis;
+    // current chunk
+    const uint32_t* m; int ncol, nrow; float fxo, dfx, fyo, dfy, t1; int exit_axis; bool nonempty;
+    // sweep
+    float ta, span, xa, ya, za, dM, dm, Ma, ma, inv_dM; int nM, nm, sg, c, cend; bool floor_reach, major_x;
+    // bookkeeping
+    int rid, state; bool need_advance;
+    const TrackHeader* th;
+};
+
+__device__ __forceinline__ void finish(Lane& L, float val, float* __restrict__ ranges, float* __restrict__ min_range,
+                                       int64_t base_car) {
+    const int car = L.rid / FTGP_NBEAMS, beam = L.rid - car * FTGP_NBEAMS;
+    ranges[(base_car + car) * FTGP_NBEAMS + beam] = val;
+    if (min_range && val >= 0.f) atomicMin(reinterpret_cast<unsigned int*>(min_range + base_car + car), __float_as_uint(val));
+    L.state = ST_IDLE; L.need_advance = false;
 }
 
 __global__ void __launch_bounds__(512)
 lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* __restrict__ qpos,
              int64_t stride, const int32_t* __restrict__ track_id, const uint8_t* __restrict__ visible,
-             int64_t ncars, int cpw, float* __restrict__ ranges, float* __restrict__ min_range) {
+             const int32_t* __restrict__ lap, int64_t ncars, int cpw, int bsz, float* __restrict__ ranges,
+             float* __restrict__ min_range) {
     extern __shared__ __align__(16) uint32_t sm[];
     {
         const uint4* src = reinterpret_cast<const uint4*>(blob);
@@ -357,79 +236,268 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
     }
     __syncthreads();
     const GeomHeader* gh = reinterpret_cast<const GeomHeader*>(sm);
-    const int lane = threadIdx.x & 31;
-    const int64_t warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    double* frames = reinterpret_cast<double*>(sm + ((lidar_words + 3) & ~3)) + (size_t)wib * BATCH * FRAME_DOUBLES;
+    int* meta = reinterpret_cast<int*>(reinterpret_cast<double*>(sm + ((lidar_words + 3) & ~3)) +
+                                       (size_t)warps_per_block * BATCH * FRAME_DOUBLES) + wib * BATCH;
     const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
+    const int64_t nbatch = (ncars + bsz - 1) / bsz;
     const double rx = -0.0525, rz = 0.065, lr = 0.030;   // mushr.em.xml:101-103
+    const unsigned lt = (1u << lane) - 1u;
 
-    for (int64_t car = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); car < ncars; car += nwarps) {
-        int tid = track_id ? track_id[car] : 0;
-        if (tid < 0 || tid >= gh->ntracks) tid = 0;
-        const TrackHeader* th = reinterpret_cast<const TrackHeader*>(sm + gh->track_off[tid]);
-        Pose P;
-        load_pose(qpos, stride, car, lane, P);
-        const double inv_sx = 1.0 / th->dsize_x, inv_sy = 1.0 / th->dsize_y;
-        float rng[3];
-        double dwx[3], dwy[3], dwz[3], owx[3], owy[3], owz[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int j = lane + 32 * k;
-            rng[k] = -1.f;
-            if (j < FTGP_NBEAMS) {
-                const double sb = c_beam_sc[j][0], cb = c_beam_sc[j][1];
-                // site +Z axis in the car frame = (sin b, -cos b, 0); origin = lidar axis - lr * dir
-                dwx[k] = sb * P.R[0] - cb * P.R[1]; dwy[k] = sb * P.R[3] - cb * P.R[4]; dwz[k] = sb * P.R[6] - cb * P.R[7];
-                const double lx = rx - lr * sb, ly = lr * cb;
-                owx[k] = P.p[0] + P.R[0] * lx + P.R[1] * ly + P.R[2] * rz;
-                owy[k] = P.p[1] + P.R[3] * lx + P.R[4] * ly + P.R[5] * rz;
-                owz[k] = P.p[2] + P.R[6] * lx + P.R[7] * ly + P.R[8] * rz;
-                const double gxd = owx[k] * inv_sx + 0.5, gyd = owy[k] * inv_sy + 0.5 + (double)(th->vc - 1);
-                const double fgx = floor(gxd), fgy = floor(gyd);
-                Ray ry;
-                ry.ix0 = (int)fgx; ry.iy0 = (int)fgy;
-                ry.fx0 = (float)(gxd - fgx); ry.fy0 = (float)(gyd - fgy);
-                ry.dgx = (float)(dwx[k] * inv_sx); ry.dgy = (float)(dwy[k] * inv_sy);
-                ry.lz = (float)(owz[k] - (double)HF_Z0); ry.dz = (float)dwz[k];
-                rng[k] = trace_walls(sm, th, ry, qpos + car * stride, j);
-            }
+    for (int64_t batch = (int64_t)blockIdx.x * warps_per_block + wib; batch < nbatch; batch += nwarps) {
+        const int64_t base_car = batch * bsz;
+        const int nb = (int)min((int64_t)bsz, ncars - base_car);
+        __syncwarp();
+        if (lane < nb) {            // pose frame of each car of the batch: position + rotation matrix, fp64
+            const double* q = qpos + (base_car + lane) * stride;
+            double w = q[3], x = q[4], y = q[5], z = q[6];
+            const double n = sqrt(w * w + x * x + y * y + z * z);
+            if (n < 1e-15) { w = 1; x = y = z = 0; } else { w /= n; x /= n; y /= n; z /= n; }
+            double* F = frames + lane * FRAME_DOUBLES;
+            F[0] = q[0]; F[1] = q[1]; F[2] = q[2];
+            F[3] = 1 - 2 * (y * y + z * z); F[4] = 2 * (x * y - w * z); F[5] = 2 * (x * z + w * y);
+            F[6] = 2 * (x * y + w * z); F[7] = 1 - 2 * (x * x + z * z); F[8] = 2 * (y * z - w * x);
+            F[9] = 2 * (x * z - w * y); F[10] = 2 * (y * z + w * x); F[11] = 1 - 2 * (x * x + y * y);
+            int tid = track_id ? track_id[base_car + lane] : 0;
+            if (tid < 0 || tid >= gh->ntracks) tid = 0;
+            // bit 8: other cars do not see this car (shadowed, custom.py:1455-1464); bit 9: its own rangefinders are
+            // switched off (mjSENS_USER after shadow(), custom.py:1438): the ranges row keeps its stale values
+            int flags = tid;
+            if (visible && !visible[base_car + lane]) flags |= 0x100;
+            if (lap && lap[(base_car + lane) * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED]) flags |= 0x300;
+            meta[lane] = flags;
+            if (min_range) min_range[base_car + lane] = INFINITY;
         }
-        if (cpw > 1) {
-            const int64_t w0 = (car / cpw) * cpw;
-            for (int64_t oc = w0; oc < w0 + cpw && oc < ncars; oc++) {
-                if (oc == car) continue;                       // bodyexclude: own root body
-                if (visible && !visible[oc]) continue;         // shadowed car: alpha 0 material
-                Pose Q;
-                load_pose(qpos, stride, oc, lane, Q);
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    if (lane + 32 * k >= FTGP_NBEAMS) continue;
-                    // ray in the other car's frame, relative to its cylinder centre
-                    const double ex = owx[k] - Q.p[0], ey = owy[k] - Q.p[1], ez = owz[k] - Q.p[2];
-                    const double px = Q.R[0] * ex + Q.R[3] * ey + Q.R[6] * ez - rx;
-                    const double py = Q.R[1] * ex + Q.R[4] * ey + Q.R[7] * ez;
-                    const double pz = Q.R[2] * ex + Q.R[5] * ey + Q.R[8] * ez - (rz - 0.015 / 2);
-                    const double vx = Q.R[0] * dwx[k] + Q.R[3] * dwy[k] + Q.R[6] * dwz[k];
-                    const double vy = Q.R[1] * dwx[k] + Q.R[4] * dwy[k] + Q.R[7] * dwz[k];
-                    const double vz = Q.R[2] * dwx[k] + Q.R[5] * dwy[k] + Q.R[8] * dwz[k];
-                    const double s = ray_cylinder(px, py, pz, vx, vy, vz, 0.03, 0.015);
-                    if (s >= 0 && (rng[k] < 0.f || (float)s < rng[k])) rng[k] = (float)s;
+        __syncwarp();
+        const int nrays = nb * FTGP_NBEAMS;
+        int next = 0;
+        Lane L;
+        L.state = ST_IDLE; L.need_advance = false;
+        for (;;) {
+            const unsigned idle = __ballot_sync(0xffffffffu, L.state == ST_IDLE);
+            const bool refill = next < nrays && (__popc(idle) >= 8 || idle == 0xffffffffu);
+            if (!refill && idle == 0xffffffffu) break;
+            if (refill) {
+                const int r = next + __popc(idle & lt);
+                next += __popc(idle);
+                if (L.state == ST_IDLE && r < nrays) {
+                    // ---------------- ray set-up (fp64 pose math, then fp32 cell-relative coordinates)
+                    const int car = r / FTGP_NBEAMS, j = r - car * FTGP_NBEAMS;
+                    const int flags = meta[car];
+                    if (!(flags & 0x200)) {
+                        L.rid = r;
+                        const double* F = frames + car * FRAME_DOUBLES;
+                        const TrackHeader* th = reinterpret_cast<const TrackHeader*>(sm + gh->track_off[flags & 0xFF]);
+                        L.th = th;
+                        const double sb = c_beam_sc[j][0], cb = c_beam_sc[j][1];
+                        // site +Z axis in the car frame = (sin b, -cos b, 0); origin = lidar axis - lr * dir
+                        const double dwx = sb * F[3] - cb * F[4], dwy = sb * F[6] - cb * F[7], dwz = sb * F[9] - cb * F[10];
+                        const double lx = rx - lr * sb, ly = lr * cb;
+                        const double owx = F[0] + F[3] * lx + F[4] * ly + F[5] * rz;
+                        const double owy = F[1] + F[6] * lx + F[7] * ly + F[8] * rz;
+                        const double owz = F[2] + F[9] * lx + F[10] * ly + F[11] * rz;
+                        const double inv_sx = 1.0 / th->dsize_x, inv_sy = 1.0 / th->dsize_y;
+                        const double gxd = owx * inv_sx + 0.5, gyd = owy * inv_sy + 0.5 + (double)(th->vc - 1);
+                        const double fgx = floor(gxd), fgy = floor(gyd);
+                        L.ix0 = (int)fgx; L.iy0 = (int)fgy;
+                        L.fx0 = (float)(gxd - fgx); L.fy0 = (float)(gyd - fgy);
+                        L.dgx = (float)(dwx * inv_sx); L.dgy = (float)(dwy * inv_sy);
+                        L.lz = (float)(owz + 0.1); L.dz = (float)dwz;
+                        float best = BIG;
+                        // other cars of the same world: their lidar cylinder (mushr.em.xml:108)
+                        if (cpw > 1) {
+                            const int w0 = (car / cpw) * cpw;
+                            for (int oc = w0; oc < w0 + cpw && oc < nb; oc++) {
+                                if (oc == car || (meta[oc] & 0x100)) continue;      // bodyexclude / invisible
+                                const double* Q = frames + oc * FRAME_DOUBLES;
+                                const double ex = owx - Q[0], ey = owy - Q[1], ez = owz - Q[2];
+                                const double px = Q[3] * ex + Q[6] * ey + Q[9] * ez - rx;
+                                const double py = Q[4] * ex + Q[7] * ey + Q[10] * ez;
+                                const double pz = Q[5] * ex + Q[8] * ey + Q[11] * ez - (rz - 0.015 / 2);
+                                const double vx = Q[3] * dwx + Q[6] * dwy + Q[9] * dwz;
+                                const double vy = Q[4] * dwx + Q[7] * dwy + Q[10] * dwz;
+                                const double vz = Q[5] * dwx + Q[8] * dwy + Q[11] * dwz;
+                                const double sc = ray_cylinder(px, py, pz, vx, vy, vz, 0.03, 0.015);
+                                if (sc >= 0 && (float)sc < best) best = (float)sc;
+                            }
+                        }
+                        // ground plane: hit only from the front side, inside the 300 m rendered square
+                        if (L.dz < -1e-15f) {
+                            float tp = -(L.lz + HF_Z0 - PLANE_Z) / L.dz;
+                            if (tp >= 0.f) {
+                                float ppx = ((float)L.ix0 + L.fx0 - 0.5f + tp * L.dgx) * th->size_x;
+                                float ppy = ((float)(L.iy0 - (th->vc - 1)) + L.fy0 - 0.5f + tp * L.dgy) * th->size_y;
+                                if (fabsf(ppx) <= PLANE_HALF && fabsf(ppy) <= PLANE_HALF) best = fminf(best, tp);
+                            }
+                        }
+                        L.best = best;
+                        // parameter interval in which the ray is inside the walls' height slab [0, 0.3]
+                        float tz0 = 0.f, tz1 = BIG;
+                        if (fabsf(L.dz) > 1e-15f) {
+                            float a = (0.f - L.lz) / L.dz, b2 = (HF_RANGE - L.lz) / L.dz;
+                            tz0 = fmaxf(0.f, fminf(a, b2)); tz1 = fmaxf(a, b2);
+                        } else if (L.lz < 0.f || L.lz > HF_RANGE) tz1 = -1.f;
+                        const float tend = fminf(tz1, best);
+                        L.tz0 = tz0; L.tend = tend;
+                        bool go = tend >= tz0;
+                        // clip against the chunk grid [0,hc] x [0,vc]
+                        const int hc = th->hc, vc = th->vc;
+                        const float gx = (float)L.ix0 + L.fx0, gy = (float)L.iy0 + L.fy0;
+                        float tg0 = 0.f, tg1 = tend;
+                        int enter_axis = -1;
+                        L.inv_dgx = fabsf(L.dgx) > 1e-20f ? 1.f / L.dgx : 0.f;
+                        L.inv_dgy = fabsf(L.dgy) > 1e-20f ? 1.f / L.dgy : 0.f;
+                        if (L.inv_dgx != 0.f) {
+                            float a = (0.f - gx) * L.inv_dgx, b2 = ((float)hc - gx) * L.inv_dgx;
+                            float lo = fminf(a, b2), hi = fmaxf(a, b2);
+                            if (lo > tg0) { tg0 = lo; enter_axis = 0; }
+                            tg1 = fminf(tg1, hi);
+                        } else if (gx < 0.f || gx >= (float)hc) tg1 = -1.f;
+                        if (L.inv_dgy != 0.f) {
+                            float a = (0.f - gy) * L.inv_dgy, b2 = ((float)vc - gy) * L.inv_dgy;
+                            float lo = fminf(a, b2), hi = fmaxf(a, b2);
+                            if (lo > tg0) { tg0 = lo; enter_axis = 1; }
+                            tg1 = fminf(tg1, hi);
+                        } else if (gy < 0.f || gy >= (float)vc) tg1 = -1.f;
+                        if (tg1 < tg0) go = false;
+                        float ts = tg0;
+                        if (tz0 > ts) { ts = tz0; enter_axis = -1; }   // dropping into the slab from above: no side face
+                        if (ts > tend) go = false;
+                        if (!go) finish(L, best < BIG ? best : -1.f, ranges, min_range, base_car);
+                        else {
+                            L.stepx = L.dgx >= 0.f ? 1 : -1; L.stepy = L.dgy >= 0.f ? 1 : -1;
+                            // chunk containing the start point (relative to the origin cell to keep fp32 exact)
+                            const float relx = L.fx0 + ts * L.dgx, rely = L.fy0 + ts * L.dgy;
+                            int ix = L.ix0 + (int)floorf(relx), iy = L.iy0 + (int)floorf(rely);
+                            if (enter_axis == 0) ix = L.stepx > 0 ? 0 : hc - 1;
+                            if (enter_axis == 1) iy = L.stepy > 0 ? 0 : vc - 1;
+                            L.ix = min(max(ix, 0), hc - 1); L.iy = min(max(iy, 0), vc - 1);
+                            L.t0 = ts; L.entry_axis = enter_axis;
+                            L.state = ST_CHUNK;
+                        }
+                    }
                 }
             }
-        }
-        float* out = ranges + car * FTGP_NBEAMS;
-        float mn = BIG;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int j = lane + 32 * k;
-            if (j < FTGP_NBEAMS) {
-                out[j] = rng[k];
-                if (rng[k] >= 0.f) mn = fminf(mn, rng[k]);
+            // ---------------- one step over the chunk grid
+            if (L.state == ST_CHUNK) {
+                const TrackHeader* th = L.th;
+                const int hc = th->hc;
+                const float tmx = L.inv_dgx != 0.f ? ((float)(L.ix - L.ix0 + (L.stepx > 0 ? 1 : 0)) - L.fx0) * L.inv_dgx : BIG;
+                const float tmy = L.inv_dgy != 0.f ? ((float)(L.iy - L.iy0 + (L.stepy > 0 ? 1 : 0)) - L.fy0) * L.inv_dgy : BIG;
+                L.exit_axis = tmx <= tmy ? 0 : 1;
+                L.t1 = fminf(tmx, tmy);
+                const uint16_t* index = reinterpret_cast<const uint16_t*>(sm + th->index_off);
+                const uint32_t cid = index[L.iy * hc + L.ix];
+                L.nonempty = cid != EMPTY_CHUNK;
+                L.need_advance = true;
+                if (L.nonempty) {
+                    const uint32_t* m = sm + th->chunks_off + cid * CHUNK_WORDS;
+                    L.m = m;
+                    L.ncol = m[13] & 0xFF; L.nrow = (m[13] >> 8) & 0xFF;
+                    const float nx = (float)(L.ncol - 1), ny = (float)(L.nrow - 1);
+                    // fine-cell coordinates inside this chunk: f(t) = fo + t * df
+                    L.fxo = ((float)(L.ix0 - L.ix) + L.fx0) * nx; L.dfx = L.dgx * nx;
+                    L.fyo = ((float)(L.iy0 - L.iy) + L.fy0) * ny; L.dfy = L.dgy * ny;
+                    const float inv_h = 1.f / HF_RANGE;
+                    bool done = false;
+                    if (L.entry_axis >= 0 && L.t0 <= L.tend) {       // entry side face
+                        const bool far_side = L.entry_axis == 0 ? L.stepx < 0 : L.stepy < 0;
+                        const float along = L.entry_axis == 0 ? L.fyo + L.t0 * L.dfy : L.fxo + L.t0 * L.dfx;
+                        if (face_hit(m, L.ncol, L.nrow, L.entry_axis, far_side, along, (L.lz + L.t0 * L.dz) * inv_h)) {
+                            finish(L, fminf(L.best, L.t0), ranges, min_range, base_car); done = true;
+                        }
+                    }
+                    if (!done) {
+                        float ta = fmaxf(L.t0, L.tz0), tb = fminf(L.t1, L.tend);
+                        if (ta <= tb) {
+                            const float za0 = L.lz + ta * L.dz;
+                            L.floor_reach = fminf(za0, za0 + (tb - ta) * L.dz) <= 0.f;
+                            if (!L.floor_reach) {
+                                // only cells with a wall vertex can be hit: clip to the chunk's wall bounding box (+1 cell)
+                                const uint32_t bb = m[14];
+                                const float xlo = (float)(bb & 0xFF) - 1.01f, xhi = (float)((bb >> 8) & 0xFF) + 1.01f;
+                                const float ylo = (float)((bb >> 16) & 0xFF) - 1.01f, yhi = (float)(bb >> 24) + 1.01f;
+                                if (fabsf(L.dfx) > 1e-20f) {
+                                    const float i = 1.f / L.dfx, a = (xlo - L.fxo) * i, b2 = (xhi - L.fxo) * i;
+                                    ta = fmaxf(ta, fminf(a, b2)); tb = fminf(tb, fmaxf(a, b2));
+                                } else if (L.fxo < xlo || L.fxo > xhi) tb = -BIG;
+                                if (fabsf(L.dfy) > 1e-20f) {
+                                    const float i = 1.f / L.dfy, a = (ylo - L.fyo) * i, b2 = (yhi - L.fyo) * i;
+                                    ta = fmaxf(ta, fminf(a, b2)); tb = fminf(tb, fmaxf(a, b2));
+                                } else if (L.fyo < ylo || L.fyo > yhi) tb = -BIG;
+                            }
+                            if (ta <= tb) {
+                                // re-origin at ta
+                                L.ta = ta; L.span = tb - ta;
+                                L.xa = L.fxo + ta * L.dfx; L.ya = L.fyo + ta * L.dfy; L.za = L.lz + ta * L.dz;
+                                L.major_x = fabsf(L.dfx) >= fabsf(L.dfy);
+                                L.dM = L.major_x ? L.dfx : L.dfy; L.dm = L.major_x ? L.dfy : L.dfx;
+                                L.Ma = L.major_x ? L.xa : L.ya; L.ma = L.major_x ? L.ya : L.xa;
+                                L.nM = L.major_x ? L.ncol - 1 : L.nrow - 1; L.nm = L.major_x ? L.nrow - 1 : L.ncol - 1;
+                                L.sg = L.dM >= 0.f ? 1 : -1;
+                                L.inv_dM = fabsf(L.dM) > 1e-20f ? 1.f / L.dM : 0.f;
+                                const float Mb = L.Ma + L.span * L.dM;
+                                int c = (int)floorf(L.Ma - (float)L.sg * 1e-3f), cend = (int)floorf(Mb + (float)L.sg * 1e-3f);
+                                L.c = min(max(c, 0), L.nM - 1); L.cend = min(max(cend, 0), L.nM - 1);
+                                L.state = ST_SWEEP; L.need_advance = false;
+                            }
+                        }
+                    }
+                }
             }
-        }
-        if (min_range) {
-            // warp-level min-reduction (non-negative floats order like their bit patterns)
-            unsigned r = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
-            if (lane == 0) min_range[car] = r == __float_as_uint(BIG) ? INFINITY : __uint_as_float(r);
+            // ---------------- one major-axis column of cells inside the current chunk
+            if (L.state == ST_SWEEP) {
+                float s0 = 0.f, s1 = L.span;
+                if (L.inv_dM != 0.f) {
+                    const float e0 = ((float)(L.c + (L.sg > 0 ? 0 : 1)) - L.Ma) * L.inv_dM;
+                    const float e1 = ((float)(L.c + (L.sg > 0 ? 1 : 0)) - L.Ma) * L.inv_dM;
+                    s0 = fmaxf(s0, e0); s1 = fminf(s1, e1);
+                }
+                const float m0 = L.ma + s0 * L.dm, m1 = L.ma + s1 * L.dm;
+                int rlo = (int)floorf(fminf(m0, m1) - 1e-3f), rhi = (int)floorf(fmaxf(m0, m1) + 1e-3f);
+                rlo = min(max(rlo, 0), L.nm - 1); rhi = min(max(rhi, 0), L.nm - 1);
+                float found = BIG;
+                for (int r = rlo; r <= rhi; r++) {
+                    const int cc = L.major_x ? L.c : r, rr = L.major_x ? r : L.c;
+                    const uint32_t bits = mask_bits2(L.m, rr * L.ncol + cc) | (mask_bits2(L.m, (rr + 1) * L.ncol + cc) << 2);
+                    if (bits == 0u && !L.floor_reach) continue;
+                    bool unsure = false;
+                    float s = cell_hit(bits, L.xa - (float)cc, L.ya - (float)rr, L.za, L.dfx, L.dfy, L.dz, -L.ta, unsure);
+                    if (unsure) {
+                        const int car = L.rid / FTGP_NBEAMS;
+                        const float sx = cell_hit_exact(L.th, qpos + (base_car + car) * stride, L.rid - car * FTGP_NBEAMS,
+                                                        L.ix, L.iy, L.ncol, L.nrow, cc, rr, bits);
+                        s = sx < BIG ? sx - L.ta : BIG;
+                    }
+                    if (s <= L.span + 1e-4f) found = fminf(found, s);
+                }
+                if (found < BIG) finish(L, fminf(L.best, fmaxf(L.ta + found, 0.f)), ranges, min_range, base_car);
+                else if (L.c == L.cend) { L.state = ST_CHUNK; L.need_advance = true; }
+                else L.c += L.sg;
+            }
+            // ---------------- leave the current chunk
+            if (L.need_advance) {
+                L.need_advance = false;
+                bool done = false;
+                if (L.nonempty && L.t1 <= L.tend) {                  // exit side face
+                    const bool far_side = L.exit_axis == 0 ? L.stepx > 0 : L.stepy > 0;
+                    const float along = L.exit_axis == 0 ? L.fyo + L.t1 * L.dfy : L.fxo + L.t1 * L.dfx;
+                    if (face_hit(L.m, L.ncol, L.nrow, L.exit_axis, far_side, along, (L.lz + L.t1 * L.dz) * (1.f / HF_RANGE))) {
+                        finish(L, fminf(L.best, L.t1), ranges, min_range, base_car); done = true;
+                    }
+                }
+                if (!done) {
+                    if (L.t1 >= L.tend) finish(L, L.best < BIG ? L.best : -1.f, ranges, min_range, base_car);
+                    else {
+                        if (L.exit_axis == 0) L.ix += L.stepx; else L.iy += L.stepy;
+                        if (L.ix < 0 || L.ix >= L.th->hc || L.iy < 0 || L.iy >= L.th->vc)
+                            finish(L, L.best < BIG ? L.best : -1.f, ranges, min_range, base_car);
+                        else { L.t0 = L.t1; L.entry_axis = L.exit_axis; L.state = ST_CHUNK; }
+                    }
+                }
+            }
         }
     }
 }
@@ -448,10 +516,12 @@ static int ensure_beams(int device) {
 }
 
 int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const int32_t* track_id,
-                 const uint8_t* visible, int64_t ncars, int cpw, float* ranges, float* min_range,
+                 const uint8_t* visible, const int32_t* lap, int64_t ncars, int cpw, float* ranges, float* min_range,
                  cudaStream_t stream) {
+    if (cpw > BATCH || BATCH % cpw) { set_error("ftgp_lidar: cars_per_world must be 1, 2, 4 or 8"); return FTGP_ERR_UNSUPPORTED; }
     GeomHeader gh; memcpy(&gh, g->h_blob.data(), sizeof gh);
-    size_t smem = (size_t)((gh.lidar_words + 3) / 4) * 16;
+    const int threads = 512;
+    size_t smem = (size_t)((gh.lidar_words + 3) / 4) * 16 + (size_t)(threads / 32) * BATCH * (FRAME_DOUBLES * 8 + 4);
     static int sm_count[16] = {0};
     int dev = g->device;
     if (dev < 16 && sm_count[dev] == 0) {
@@ -460,15 +530,17 @@ int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const i
     }
     if (smem > 227 * 1024) { set_error("geometry blob (%zu B) exceeds shared memory", smem); return FTGP_ERR_UNSUPPORTED; }
     int rc = ensure_beams(dev); if (rc) return rc;
-    const int threads = 512;
     int per_sm = (int)std::min<size_t>(4, (227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    int64_t need = (ncars + (threads / 32) - 1) / (threads / 32);
     int nsm = dev < 16 ? sm_count[dev] : 148;
+    // cars per warp batch: 8 for big fleets (best lane utilisation), fewer when the fleet would not fill the GPU
+    int bsz = BATCH;
+    while (bsz > cpw && (ncars + bsz - 1) / bsz < (int64_t)nsm * per_sm * (threads / 32) * 2) bsz >>= 1;
+    int64_t need = ((ncars + bsz - 1) / bsz + (threads / 32) - 1) / (threads / 32);
     int grid = (int)std::min<int64_t>(need, (int64_t)nsm * per_sm);
     if (grid < 1) return FTGP_OK;
-    lidar_kernel<<<grid, threads, smem, stream>>>(g->d_blob, gh.lidar_words, qpos, stride, track_id, visible,
-                                                  ncars, cpw, ranges, min_range);
+    lidar_kernel<<<grid, threads, smem, stream>>>(g->d_blob, gh.lidar_words, qpos, stride, track_id, visible, lap,
+                                                  ncars, cpw, bsz, ranges, min_range);
     count_launch();
     FTGP_CUDA(cudaGetLastError());
     return FTGP_OK;
@@ -485,7 +557,7 @@ extern "C" int ftgp_lidar(const ftgp_geom* g, const double* qpos, int64_t qpos_s
     }
     if (ncars == 0) return FTGP_OK;
     FTGP_CUDA(cudaSetDevice(g->device));
-    return launch_lidar(g, qpos, qpos_stride, track_id, visible, ncars, cars_per_world, ranges, min_range,
+    return launch_lidar(g, qpos, qpos_stride, track_id, visible, nullptr, ncars, cars_per_world, ranges, min_range,
                         (cudaStream_t)stream);
 }
 
@@ -511,7 +583,7 @@ extern "C" int ftgp_lidar_host(const ftgp_geom* g, const double* qpos, int64_t q
     FTGP_CUDA(cudaMemcpy2DAsync(base, 7 * sizeof(double), qpos, qpos_stride * sizeof(double), 7 * sizeof(double),
                                 ncars, cudaMemcpyHostToDevice, s));
     if (track_id) FTGP_CUDA(cudaMemcpyAsync(base + o_tid, track_id, b_tid, cudaMemcpyHostToDevice, s));
-    int rc = launch_lidar(g, (const double*)base, 7, track_id ? (const int32_t*)(base + o_tid) : nullptr, nullptr,
+    int rc = launch_lidar(g, (const double*)base, 7, track_id ? (const int32_t*)(base + o_tid) : nullptr, nullptr, nullptr,
                           ncars, 1, (float*)(base + o_rng), nullptr, s);
     if (rc) return rc;
     FTGP_CUDA(cudaMemcpyAsync(ranges, base + o_rng, b_rng, cudaMemcpyDeviceToHost, s));

@@ -206,7 +206,8 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
 }
 
 int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const int32_t* track_id,
-                 const uint8_t* visible, int64_t ncars, int cpw, float* ranges, float* min_range, cudaStream_t stream);
+                 const uint8_t* visible, const int32_t* lap, int64_t ncars, int cpw, float* ranges, float* min_range,
+                 cudaStream_t stream);
 int launch_drivers(const float* ranges, const int32_t* kind, int default_kind, const int32_t* lap, double* ctrl,
                    int64_t ncars, cudaStream_t stream);
 int launch_lap(const ftgp_geom* g, const double* qpos, int64_t stride, const int32_t* track_id, int32_t* lap,
@@ -239,7 +240,7 @@ extern "C" int ftgp_tick(const ftgp_tick_args* a, int nticks, void* stream) {
         // custom.py:1395-1423 driver on the ranges of the previous mj_step, control write
         if ((rc = launch_drivers(a->ranges, a->driver_kind, a->default_driver, a->lap, a->ctrl, a->ncars, s))) return rc;
         // custom.py:1425 mj_step: rangefinders are evaluated from the pre-step pose, then the state advances
-        if ((rc = launch_lidar(a->geom, a->qpos, FTGP_NQ, a->track_id, nullptr, a->ncars, a->cars_per_world, a->ranges,
+        if ((rc = launch_lidar(a->geom, a->qpos, FTGP_NQ, a->track_id, nullptr, a->lap, a->ncars, a->cars_per_world, a->ranges,
                                nullptr, s))) return rc;
         if ((rc = launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, 1, a->status, s))) return rc;
     }

@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <algorithm>
 #include "common.h"
 
 namespace ftgp {
@@ -236,7 +237,18 @@ extern "C" ftgp_geom* ftgp_geom_create(const ftgp_track* const* tracks, const do
         th.chunks_off = (int)blob.size();
         for (int c = 0; c < th.nchunks; c++) {
             for (int wd = 0; wd < 13; wd++) blob.push_back(t->masks[(size_t)c * 13 + wd]);
-            blob.push_back((uint32_t)t->dims[2 * c] | ((uint32_t)t->dims[2 * c + 1] << 8));
+            const int ncol = t->dims[2 * c], nrow = t->dims[2 * c + 1];
+            blob.push_back((uint32_t)ncol | ((uint32_t)nrow << 8));
+            int cmin = 255, cmax = 0, rmin = 255, rmax = 0;
+            for (int r = 0; r < nrow; r++)
+                for (int cc = 0; cc < ncol; cc++) {
+                    const int bit = r * ncol + cc;
+                    if ((t->masks[(size_t)c * 13 + (bit >> 5)] >> (bit & 31)) & 1u) {
+                        cmin = std::min(cmin, cc); cmax = std::max(cmax, cc); rmin = std::min(rmin, r); rmax = std::max(rmax, r);
+                    }
+                }
+            if (cmin > cmax) { cmin = 200; cmax = 100; rmin = 200; rmax = 100; }      // no wall vertex: empty box
+            blob.push_back((uint32_t)cmin | ((uint32_t)cmax << 8) | ((uint32_t)rmin << 16) | ((uint32_t)rmax << 24));
         }
         memcpy(&blob[thdr_off[k]], &th, sizeof th);
     }
