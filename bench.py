@@ -327,7 +327,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("FTGP_WORKLOAD", "lidar"), choices=["tick", "lidar", "step"])
+    ap.add_argument("--workload", default=os.environ.get("FTGP_WORKLOAD", "tick"), choices=["tick", "lidar", "step"])
     ap.add_argument("--cars", type=int, default=None)
     ap.add_argument("--settle", type=int, default=200, help="untimed ticks before timing (tick/step workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
