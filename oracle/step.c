@@ -29,7 +29,7 @@
 #define NV FTO_NV
 #define NQ FTO_NQ
 #define NEQ 2
-#define MAXCON 24
+#define MAXCON 8            /* framework rule: at most 8 contacts per car (4 wheel-ground first, then chassis-wall in hull-vertex order) */
 #define MAXEFC (NEQ + 23 + 7 + 4 * MAXCON)
 
 enum { J_FREE, J_BALL, J_SLIDE, J_HINGE };
@@ -614,8 +614,10 @@ static void hfield_plane_at(const fto_track* t, double x, double y, double* nrm,
     double dx = 2 * c->size[0] / (c->ncol - 1), dy = 2 * c->size[1] / (c->nrow - 1);
     double u = (x - c->pos[0] + c->size[0]) / dx, v = (y - c->pos[1] + c->size[1]) / dy;
     int cc = (int)floor(u), rr = (int)floor(v);
-    if (cc < 0) cc = 0; if (cc > c->ncol - 2) cc = c->ncol - 2;
-    if (rr < 0) rr = 0; if (rr > c->nrow - 2) rr = c->nrow - 2;
+    if (cc < 0) cc = 0;
+    if (cc > c->ncol - 2) cc = c->ncol - 2;
+    if (rr < 0) rr = 0;
+    if (rr > c->nrow - 2) rr = c->nrow - 2;
     double fu = u - cc, fv = v - rr;
     double z00 = c->data[rr * c->ncol + cc] * c->size[2], z10 = c->data[rr * c->ncol + cc + 1] * c->size[2];
     double z01 = c->data[(rr + 1) * c->ncol + cc] * c->size[2], z11 = c->data[(rr + 1) * c->ncol + cc + 1] * c->size[2];
@@ -951,7 +953,8 @@ int fto_step(const fto_model* m, const fto_track* t, double* qpos, double* qvel,
         double tv = 0;
         for (int w = 0; w < 4; w++) tv += 0.25 * qvel[thr[w]];
         double f_fwd = 100.0 * ctrl[0] - 100.0 * (0.04 * tv);
-        if (f_fwd > 500) f_fwd = 500; if (f_fwd < -500) f_fwd = -500;
+        if (f_fwd > 500) f_fwd = 500;
+        if (f_fwd < -500) f_fwd = -500;
         act[6] += f_turn;
         for (int w = 0; w < 4; w++) act[thr[w]] += 0.04 * 0.25 * f_fwd;
     }
