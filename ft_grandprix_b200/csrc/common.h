@@ -29,8 +29,9 @@ void count_launch(int n = 1);
 // chunk record: words 0..12 = 400 vertex bits (bit r*ncol + c set = wall vertex,
 // hfield row r = 0 at the -Y edge, i.e. the PNG chunk's bottom pixel row),
 // word 13 = ncol | nrow << 8; word 14 = bounding box of the wall vertices: cmin | cmax << 8 | rmin << 16 | rmax << 24
+// words 15..27 = the same 400 vertex bits transposed (bit c * nrow + r), for rays that cross fewer columns than rows
 // (cmin > cmax when the chunk has no wall vertex left, i.e. an all-wall chunk whose elevation normalises to 0)
-constexpr int CHUNK_WORDS = 15;   // 13 mask words, dims, wall-vertex bounding box
+constexpr int CHUNK_WORDS = 28;   // 13 mask words (row-major), dims, wall bounding box, 13 mask words (column-major)
 constexpr uint16_t EMPTY_CHUNK = 0xFFFF;
 
 struct TrackHeader {

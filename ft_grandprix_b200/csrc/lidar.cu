@@ -48,6 +48,11 @@ __device__ __forceinline__ uint32_t mask_bits2(const uint32_t* m, int bit) {
     uint32_t lo = m[w], hi = m[min(w + 1, 12)];
     return __funnelshift_r(lo, hi, s) & 3u;
 }
+// n (<= 20) consecutive vertex bits starting at `bit`
+__device__ __forceinline__ uint32_t mask_line(const uint32_t* m, int bit, int n) {
+    int w = bit >> 5, sh = bit & 31;
+    return __funnelshift_r(m[w], m[min(w + 1, 12)], sh) & ((1u << n) - 1u);
+}
 __device__ __forceinline__ uint32_t mask_bit(const uint32_t* m, int bit) {
     return (m[bit >> 5] >> (bit & 31)) & 1u;
 }
@@ -225,21 +230,25 @@ __device__ __forceinline__ void finish(Lane& L, float val, float* __restrict__ r
 __global__ void __launch_bounds__(512)
 lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* __restrict__ qpos,
              int64_t stride, const int32_t* __restrict__ track_id, const uint8_t* __restrict__ visible,
-             const int32_t* __restrict__ lap, int64_t ncars, int cpw, int bsz, float* __restrict__ ranges,
+             const int32_t* __restrict__ lap, int64_t ncars, int cpw, int bsz, int stage, float* __restrict__ ranges,
              float* __restrict__ min_range) {
     extern __shared__ __align__(16) uint32_t sm[];
-    {
+    // the compiled tracks are staged into shared memory when they fit (one or two tracks); otherwise they are
+    // read through L1/L2 from the global blob
+    if (stage) {
         const uint4* src = reinterpret_cast<const uint4*>(blob);
         uint4* dst = reinterpret_cast<uint4*>(sm);
         int n4 = (lidar_words + 3) >> 2;
         for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const GeomHeader* gh = reinterpret_cast<const GeomHeader*>(sm);
+    const uint32_t* geo = stage ? sm : blob;
+    uint32_t* scratch = stage ? sm + ((lidar_words + 3) & ~3) : sm;
+    const GeomHeader* gh = reinterpret_cast<const GeomHeader*>(geo);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
-    double* frames = reinterpret_cast<double*>(sm + ((lidar_words + 3) & ~3)) + (size_t)wib * BATCH * FRAME_DOUBLES;
-    int* meta = reinterpret_cast<int*>(reinterpret_cast<double*>(sm + ((lidar_words + 3) & ~3)) +
+    double* frames = reinterpret_cast<double*>(scratch) + (size_t)wib * BATCH * FRAME_DOUBLES;
+    int* meta = reinterpret_cast<int*>(reinterpret_cast<double*>(scratch) +
                                        (size_t)warps_per_block * BATCH * FRAME_DOUBLES) + wib * BATCH;
     const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
     const int64_t nbatch = (ncars + bsz - 1) / bsz;
@@ -289,7 +298,7 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                     if (!(flags & 0x200)) {
                         L.rid = r;
                         const double* F = frames + car * FRAME_DOUBLES;
-                        const TrackHeader* th = reinterpret_cast<const TrackHeader*>(sm + gh->track_off[flags & 0xFF]);
+                        const TrackHeader* th = reinterpret_cast<const TrackHeader*>(geo + gh->track_off[flags & 0xFF]);
                         L.th = th;
                         const double sb = c_beam_sc[j][0], cb = c_beam_sc[j][1];
                         // site +Z axis in the car frame = (sin b, -cos b, 0); origin = lidar axis - lr * dir
@@ -388,12 +397,12 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                 const float tmy = L.inv_dgy != 0.f ? ((float)(L.iy - L.iy0 + (L.stepy > 0 ? 1 : 0)) - L.fy0) * L.inv_dgy : BIG;
                 L.exit_axis = tmx <= tmy ? 0 : 1;
                 L.t1 = fminf(tmx, tmy);
-                const uint16_t* index = reinterpret_cast<const uint16_t*>(sm + th->index_off);
+                const uint16_t* index = reinterpret_cast<const uint16_t*>(geo + th->index_off);
                 const uint32_t cid = index[L.iy * hc + L.ix];
                 L.nonempty = cid != EMPTY_CHUNK;
                 L.need_advance = true;
                 if (L.nonempty) {
-                    const uint32_t* m = sm + th->chunks_off + cid * CHUNK_WORDS;
+                    const uint32_t* m = geo + th->chunks_off + cid * CHUNK_WORDS;
                     L.m = m;
                     L.ncol = m[13] & 0xFF; L.nrow = (m[13] >> 8) & 0xFF;
                     const float nx = (float)(L.ncol - 1), ny = (float)(L.nrow - 1);
@@ -432,7 +441,9 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                                 // re-origin at ta
                                 L.ta = ta; L.span = tb - ta;
                                 L.xa = L.fxo + ta * L.dfx; L.ya = L.fyo + ta * L.dfy; L.za = L.lz + ta * L.dz;
-                                L.major_x = fabsf(L.dfx) >= fabsf(L.dfy);
+                                // iterate over the lines of the SLOW axis (rows if |dy| <= |dx|, columns otherwise); the run of
+                                // cells a line covers along the fast axis is tested at once against the line-pair occupancy bits
+                                L.major_x = fabsf(L.dfx) < fabsf(L.dfy);          // true: lines are columns (transposed masks)
                                 L.dM = L.major_x ? L.dfx : L.dfy; L.dm = L.major_x ? L.dfy : L.dfx;
                                 L.Ma = L.major_x ? L.xa : L.ya; L.ma = L.major_x ? L.ya : L.xa;
                                 L.nM = L.major_x ? L.ncol - 1 : L.nrow - 1; L.nm = L.major_x ? L.nrow - 1 : L.ncol - 1;
@@ -458,11 +469,22 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                 const float m0 = L.ma + s0 * L.dm, m1 = L.ma + s1 * L.dm;
                 int rlo = (int)floorf(fminf(m0, m1) - 1e-3f), rhi = (int)floorf(fmaxf(m0, m1) + 1e-3f);
                 rlo = min(max(rlo, 0), L.nm - 1); rhi = min(max(rhi, 0), L.nm - 1);
+                // vertex bits of lines c and c+1 along the fast axis (row-major masks for rows, transposed for columns)
+                const uint32_t* mk = L.major_x ? L.m + 15 : L.m;
+                const int nline = L.major_x ? L.nrow : L.ncol;          // vertices per line
+                const uint32_t lineA = mask_line(mk, L.c * nline, nline), lineB = mask_line(mk, (L.c + 1) * nline, nline);
+                uint32_t occ = lineA | lineB;
+                occ |= occ >> 1;                                        // cell k has a wall vertex among its 4 corners
+                const uint32_t range = (2u << rhi) - (1u << rlo);       // cells rlo..rhi
+                uint32_t cand = L.floor_reach ? range : (occ & range);
                 float found = BIG;
-                for (int r = rlo; r <= rhi; r++) {
-                    const int cc = L.major_x ? L.c : r, rr = L.major_x ? r : L.c;
-                    const uint32_t bits = mask_bits2(L.m, rr * L.ncol + cc) | (mask_bits2(L.m, (rr + 1) * L.ncol + cc) << 2);
-                    if (bits == 0u && !L.floor_reach) continue;
+                while (cand && found == BIG) {
+                    const int k = L.dm >= 0.f ? __ffs(cand) - 1 : 31 - __clz(cand);
+                    cand &= ~(1u << k);
+                    const uint32_t a2 = (lineA >> k) & 3u, b2 = (lineB >> k) & 3u;
+                    // corner bits b0 = (c,r), b1 = (c+1,r), b2 = (c,r+1), b3 = (c+1,r+1)
+                    const uint32_t bits = L.major_x ? ((a2 & 1u) | ((b2 & 1u) << 1) | ((a2 & 2u) << 1) | ((b2 & 2u) << 2)) : (a2 | (b2 << 2));
+                    const int cc = L.major_x ? L.c : k, rr = L.major_x ? k : L.c;
                     bool unsure = false;
                     float s = cell_hit(bits, L.xa - (float)cc, L.ya - (float)rr, L.za, L.dfx, L.dfy, L.dz, -L.ta, unsure);
                     if (unsure) {
@@ -521,14 +543,16 @@ int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const i
     if (cpw > BATCH || BATCH % cpw) { set_error("ftgp_lidar: cars_per_world must be 1, 2, 4 or 8"); return FTGP_ERR_UNSUPPORTED; }
     GeomHeader gh; memcpy(&gh, g->h_blob.data(), sizeof gh);
     const int threads = 512;
-    size_t smem = (size_t)((gh.lidar_words + 3) / 4) * 16 + (size_t)(threads / 32) * BATCH * (FRAME_DOUBLES * 8 + 4);
+    const size_t scratch = (size_t)(threads / 32) * BATCH * (FRAME_DOUBLES * 8 + 4);
+    const size_t blob_bytes = (size_t)((gh.lidar_words + 3) / 4) * 16;
+    const int stage = blob_bytes + scratch <= 200 * 1024;
+    const size_t smem = (stage ? blob_bytes : 0) + scratch;
     static int sm_count[16] = {0};
     int dev = g->device;
     if (dev < 16 && sm_count[dev] == 0) {
         FTGP_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
         FTGP_CUDA(cudaFuncSetAttribute(lidar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
-    if (smem > 227 * 1024) { set_error("geometry blob (%zu B) exceeds shared memory", smem); return FTGP_ERR_UNSUPPORTED; }
     int rc = ensure_beams(dev); if (rc) return rc;
     int per_sm = (int)std::min<size_t>(4, (227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
@@ -540,7 +564,7 @@ int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const i
     int grid = (int)std::min<int64_t>(need, (int64_t)nsm * per_sm);
     if (grid < 1) return FTGP_OK;
     lidar_kernel<<<grid, threads, smem, stream>>>(g->d_blob, gh.lidar_words, qpos, stride, track_id, visible, lap,
-                                                  ncars, cpw, bsz, ranges, min_range);
+                                                  ncars, cpw, bsz, stage, ranges, min_range);
     count_launch();
     FTGP_CUDA(cudaGetLastError());
     return FTGP_OK;

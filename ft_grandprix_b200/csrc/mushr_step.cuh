@@ -155,6 +155,13 @@ struct Arrow {
     double B[4][NC][NR];   // borders: chain slot l (row) x root dof (col)
 };
 FT_HD int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+FT_HD double inv_sqrt(double d) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(d);
+#else
+    return 1.0 / sqrt(d);
+#endif
+}
 
 // y = A x in padded space
 FT_HDN void arrow_mul(const Arrow& A, const double* x, double* y) {
@@ -183,7 +190,7 @@ FT_HDN void arrow_factor(Arrow& A) {
             double d = L[tri(j, j)];
             for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)];
             if (d < MINVAL) d = MINVAL;
-            const double id = 1.0 / sqrt(d);
+            const double id = inv_sqrt(d);
             L[tri(j, j)] = id;
             for (int i = j + 1; i < NC; i++) {
                 double s = L[tri(i, j)];
@@ -209,7 +216,7 @@ FT_HDN void arrow_factor(Arrow& A) {
         double d = L[tri(j, j)];
         for (int k = 0; k < j; k++) d -= L[tri(j, k)] * L[tri(j, k)];
         if (d < MINVAL) d = MINVAL;
-        const double id = 1.0 / sqrt(d);
+        const double id = inv_sqrt(d);
         L[tri(j, j)] = id;
         for (int i = j + 1; i < NR; i++) {
             double s = L[tri(i, j)];
@@ -746,15 +753,20 @@ FT_HDN double line_search(const Rows& r, const Arrow& M, Solver& s, const double
 }
 
 // gradient + Newton direction at the current point: grad = Ma - qfrc_smooth - J^T f ; search = -H^{-1} grad
-FT_HDN void newton_direction(const Rows& r, const Arrow& M, Solver& s, const double* qfrc_smooth, const double* qacc_smooth,
-                             Arrow& H, double* qfrc_con) {
+// cost, constraint force J^T f and gradient at the current point
+FT_HDN void newton_evaluate(const Rows& r, Solver& s, const double* qfrc_smooth, const double* qacc_smooth, double* qfrc_con) {
     for (int p = 0; p < NP; p++) qfrc_con[p] = 0;
-    H = M;
-    double cc = rows_cost<true, true>(r, s.qacc, qfrc_con, &H);
+    double cc = rows_cost<true, false>(r, s.qacc, qfrc_con, nullptr);
     double g = 0;
     for (int p = 0; p < NP; p++) g += (s.Ma[p] - qfrc_smooth[p]) * (s.qacc[p] - qacc_smooth[p]);
     s.gauss = 0.5 * g; s.cost = cc + s.gauss;
-    for (int p = 0; p < NP; p++) { s.grad[p] = s.Ma[p] - qfrc_smooth[p] - qfrc_con[p]; s.search[p] = s.grad[p]; }
+    for (int p = 0; p < NP; p++) s.grad[p] = s.Ma[p] - qfrc_smooth[p] - qfrc_con[p];
+}
+// Newton direction: search = -H^{-1} grad with H = M + J^T D J over the quadratic rows at the current point
+FT_HDN void newton_direction(const Rows& r, const Arrow& M, Solver& s, Arrow& H) {
+    H = M;
+    rows_cost<false, true>(r, s.qacc, nullptr, &H);
+    for (int p = 0; p < NP; p++) s.search[p] = s.grad[p];
     arrow_factor(H);
     arrow_solve(H, s.search);
     for (int p = 0; p < NP; p++) s.search[p] = -s.search[p];
@@ -830,18 +842,22 @@ FT_HDN void step_car(const ModelConsts& mc, double* qpos, double* qvel, double* 
         else for (int p = 0; p < NP; p++) s.qacc[p] = wa[p];
     }
     const double scale = 1.0 / (mc.meaninertia * NV);
-    newton_direction(r, M, s, qfrc_smooth, qacc_smooth, H, qfrc_con);
+    newton_evaluate(r, s, qfrc_smooth, qacc_smooth, qfrc_con);
+    newton_direction(r, M, s, H);
     int iter = 0;
     while (iter < SOLVER_ITER) {
         const double alpha = line_search(r, M, s, qfrc_smooth, scale);
         if (alpha == 0) break;
         for (int p = 0; p < NP; p++) { s.qacc[p] += alpha * s.search[p]; s.Ma[p] += alpha * s.Mv[p]; }
         const double oldcost = s.cost;
-        newton_direction(r, M, s, qfrc_smooth, qacc_smooth, H, qfrc_con);
+        newton_evaluate(r, s, qfrc_smooth, qacc_smooth, qfrc_con);
         double gn = 0;
         for (int p = 0; p < NP; p++) gn += s.grad[p] * s.grad[p];
         iter++;
+        // MuJoCo factorises H before this test; the direction is unused when the test ends the loop, so the
+        // factorisation is skipped then (same qacc, one block-arrow Cholesky less per step)
         if (scale * (oldcost - s.cost) < SOLVER_TOL || scale * sqrt(gn) < SOLVER_TOL) break;
+        newton_direction(r, M, s, H);
     }
     info.iters = iter;
     bool badacc = false;

@@ -249,6 +249,13 @@ extern "C" ftgp_geom* ftgp_geom_create(const ftgp_track* const* tracks, const do
                 }
             if (cmin > cmax) { cmin = 200; cmax = 100; rmin = 200; rmax = 100; }      // no wall vertex: empty box
             blob.push_back((uint32_t)cmin | ((uint32_t)cmax << 8) | ((uint32_t)rmin << 16) | ((uint32_t)rmax << 24));
+            uint32_t mt[13] = {0};                                   // transposed copy
+            for (int r = 0; r < nrow; r++)
+                for (int cc = 0; cc < ncol; cc++) {
+                    const int bit = r * ncol + cc;
+                    if ((t->masks[(size_t)c * 13 + (bit >> 5)] >> (bit & 31)) & 1u) { const int bt = cc * nrow + r; mt[bt >> 5] |= 1u << (bt & 31); }
+                }
+            for (int wd = 0; wd < 13; wd++) blob.push_back(mt[wd]);
         }
         memcpy(&blob[thdr_off[k]], &th, sizeof th);
     }

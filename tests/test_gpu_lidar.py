@@ -202,3 +202,20 @@ def test_reset_matches_reference_spawn(ft):
         np.testing.assert_allclose(q[i], want, atol=1e-15)
     assert fleet.lap[:, ft.fleet.LAP["offset"]].cpu().tolist() == [(i + 5) * 2 for i in range(8)]
     assert float(fleet.ranges.abs().sum()) == 0.0       # zeros on the first tick
+
+
+def test_lidar_four_tracks_geometry_read_from_global_memory(ft, otracks):
+    """All four bundled tracks in one geometry do not fit in shared memory: the kernel reads them through L2."""
+    names = ["track", "circle", "small-circle", "inkscape"]
+    tracks = [ft.Track.bundled(nm) for nm in names]
+    n = 512
+    tid = np.arange(n) % 4
+    poses = np.zeros((n, 7))
+    for k, t in enumerate(tracks):
+        poses[tid == k] = random_poses(t.path, n, seed=20 + k)[tid == k]
+    got, fleet = _scan_gpu(ft, tracks, poses, track_id=tid)
+    assert fleet.geom.nbytes > 200 * 1024
+    want = np.zeros((n, 90))
+    for k, nm in enumerate(names):
+        want[tid == k] = otracks[nm].scan(poses[tid == k])
+    _check(got, want)
