@@ -156,3 +156,63 @@ def test_full_tick_lockstep_short_race(ft, oracle, otracks, walls):
         for f in ("completion", "laps", "start", "good_start", "finished", "ntimes", "off_track", "delta"):
             assert lap[i, L[f]] == getattr(s, f), (i, f)
     assert lap[:, L["completion"]].max() > 5                      # the cars really drove
+
+
+def test_sharded_fleet_is_bit_identical_to_unsharded(ft):
+    """SURVEY §4/§8 e: cars are independent, so cutting a fleet into k contiguous shards (what each GPU rank does)
+    must reproduce the unsharded run bit for bit -- state, ranges and lap results."""
+    from ft_grandprix_b200.sharding import shard_range
+    from conftest import random_poses
+    t = ft.Track.bundled("track")
+    n, ticks = 6144, 40
+    poses = random_poses(t.path, n, seed=9, level=True)
+    xy = poses[:, :2]; yaw = 2 * np.arctan2(poses[:, 6], poses[:, 3])
+    whole = ft.Fleet(t, n)
+    whole.reset(xy, yaw); whole.tick(ticks); whole.sync()
+    for k in (3,):
+        for r in range(k):
+            lo, hi = shard_range(n, k, r)
+            part = ft.Fleet(t, hi - lo)
+            part.reset(xy[lo:hi], yaw[lo:hi]); part.tick(ticks); part.sync()
+            for name in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "times"):
+                a, b = getattr(part, name).cpu().numpy(), getattr(whole, name)[lo:hi].cpu().numpy()
+                assert np.array_equal(a, b), (name, r)
+
+
+def test_config1_single_car_nidc_on_track(ft, oracle, otracks):
+    """BASELINE config 1: one car, bundled nidc driver, template track.png, from the reference start grid slot
+    (path[10], heading path[11] - path[10]); device tick vs the oracle pipeline in lock-step for 2,500 ticks
+    (10 s simulated)."""
+    model = oracle.Model()
+    t = ft.Track.bundled("track")
+    ot = otracks["track"]
+    fleet = ft.Fleet(t, 1, driver="nidc")
+    fleet.reset_grid()
+    x, y, yaw = t.start_pose(0)
+    Q = np.zeros((1, 34)); V = np.zeros((1, 29)); W = np.zeros((1, 29)); U = np.zeros((1, 2))
+    Q[0], V[0], W[0] = model.reset(x, y, yaw)
+    np.testing.assert_array_equal(fleet.qpos.cpu().numpy(), Q)
+    lap = oracle.Lap(offset=10, max_times=16)
+    ranges = np.zeros((1, 90))
+    worst_r = worst_q = 0.0
+    for k in range(2500):
+        lap.update(t.path, Q[0, :2], k, 10, 0)
+        r = oracle.driver(0, ranges[0])
+        if r is not None:
+            U[0] = r
+        new_ranges = ot.scan(Q[:, :7], threads=1)
+        model.step_n(ot, Q, V, W, U)
+        fleet.tick(1); fleet.sync()
+        g = fleet.ranges.cpu().numpy().astype(np.float64)
+        assert ((g < 0) == (new_ranges < 0)).all()
+        worst_r = max(worst_r, np.abs(g - new_ranges).max())
+        gq = fleet.qpos.cpu().numpy()
+        worst_q = max(worst_q, np.abs(gq - Q).max())
+        ranges = g
+        Q[:] = gq; V[:] = fleet.qvel.cpu().numpy(); W[:] = fleet.warm.cpu().numpy()
+    assert worst_r <= 1e-4 and worst_q <= 1e-6, (worst_r, worst_q)
+    L = ft.fleet.LAP
+    got = fleet.lap.cpu().numpy()[0]
+    for f in ("completion", "laps", "start", "good_start", "finished", "ntimes", "off_track"):
+        assert got[L[f]] == getattr(lap.s, f), f
+    assert np.hypot(*(Q[0, :2] - np.array([x, y]))) > 5.0         # it drove away from the grid
