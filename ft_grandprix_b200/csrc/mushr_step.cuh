@@ -799,7 +799,11 @@ FT_HDN void step_car(const ModelConsts& mc, double* qpos, double* qvel, double* 
     double v[NP], wa[NP];
     for (int p = 0; p < NP; p++) { int d = p2d(p); v[p] = d >= 0 ? qvel[d] : 0.0; wa[p] = d >= 0 ? warm[d] : 0.0; }
     // ---- position stage
-    Kin k;
+    // the position-stage scratch (Kin) is dead before the solver state (H, Solver) is first written: share the storage
+    struct SolverState { Arrow H; Solver s; };
+    constexpr size_t SCRATCH = sizeof(Kin) > sizeof(SolverState) ? sizeof(Kin) : sizeof(SolverState);
+    double scratch[SCRATCH / sizeof(double)];
+    Kin& k = *reinterpret_cast<Kin*>(scratch);
     kinematics(mc, qpos, k);
     Arrow M;
     mass_matrix(k, M);
@@ -826,12 +830,14 @@ FT_HDN void step_car(const ModelConsts& mc, double* qpos, double* qvel, double* 
         f = f > 500.0 ? 500.0 : (f < -500.0 ? -500.0 : f);
         for (int w = 0; w < 4; w++) qfrc_smooth[NR + NC * w + 2] += 0.04 * 0.25 * f;
     }
-    Arrow H = M;
+    SolverState& so = *reinterpret_cast<SolverState*>(scratch);
+    Arrow& H = so.H;
+    H = M;
     arrow_factor(H);
     for (int p = 0; p < NP; p++) qacc_smooth[p] = qfrc_smooth[p];
     arrow_solve(H, qacc_smooth);
     // ---- Newton: warm start if its cost beats qacc_smooth's (mj_fwdConstraint)
-    Solver s;
+    Solver& s = so.s;
     double qfrc_con[NP];
     {
         arrow_mul(M, wa, s.Ma);
