@@ -204,15 +204,44 @@ def run_gpu(args):
     torch.cuda.synchronize()
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=fleet.device)   # > 126 MB L2
 
-    def one_step():
+    def one_step(kev=None):
+        """One pass of the hot path.  The tick is issued as its four kernels in the order of ftgp_tick / custom.py:1337-1426
+        (lap update, driver, rangefinders from the pre-step pose, mj_step) so that the two heavy kernels can be bracketed
+        by their own CUDA events (kev = [lidar0, lidar1, step0, step1]) on the launching stream."""
         if wl == "lidar":
+            if kev: kev[0].record(stream)
             fleet.lidar()
+            if kev: kev[1].record(stream)
         elif wl == "step":
+            if kev: kev[2].record(stream)
             fleet.step(1)
+            if kev: kev[3].record(stream)
         else:
-            fleet.tick(1)
+            fleet.lap_update()
+            fleet.drive()
+            if kev: kev[0].record(stream)
+            fleet.lidar()
+            if kev: kev[1].record(stream); kev[2].record(stream)
+            fleet.step(1)
+            if kev: kev[3].record(stream)
 
     stream = fleet.stream
+    if wl == "tick" and args.fused_check:
+        # the fused C entry point and the four separate calls are the same kernels in the same order
+        sd = fleet.state_dict()
+        fleet.tick(3); fleet.sync()
+        a = {k: v.clone() for k, v in fleet.state_dict().items() if hasattr(v, "clone")}
+        fleet.load_state_dict(sd); torch.cuda.synchronize()
+        for _ in range(3):
+            one_step()
+        fleet.sync()
+        b = fleet.state_dict()
+        assert all(torch.equal(a[k], b[k]) for k in a), "ftgp_tick differs from the four separate calls"
+        fleet.load_state_dict(sd); torch.cuda.synchronize()
+    # clocks / throttle reasons are sampled from the warm-up on (nvidia-smi needs a few hundred ms to start reporting;
+    # settle + warm-up + timed steps are the same load)
+    sampler = ClockSampler(local)
+    sampler.start()
     with torch.cuda.stream(stream):
         settle = args.settle if wl != "lidar" else 0
         for k in range(settle):          # drive the fleet into its running regime (untimed)
@@ -230,20 +259,21 @@ def run_gpu(args):
 
     # ---- device-resident timing: K steps, each bracketed by CUDA events on the launching stream, L2 flushed between
     launches0 = lib.ftgp_launch_count()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kevs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     with torch.cuda.stream(stream):
-        for a, b in ev:
+        for (a, b), kev in zip(ev, kevs):
             flush.fill_(1)
             a.record(stream)
-            one_step()
+            one_step(kev)
             b.record(stream)
     barrier()
     clocks = sampler.stop()
     launches = lib.ftgp_launch_count() - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    lidar_ms = np.mean([k[0].elapsed_time(k[1]) for k in kevs]) if wl != "step" else None
+    step_ms = np.mean([k[2].elapsed_time(k[3]) for k in kevs]) if wl != "lidar" else None
 
     # ---- end to end through the C ABI with HOST buffers (pinned): H2D + kernels + D2H inside the timed region
     e2e_steps = max(3, min(args.steps, 20))
@@ -287,9 +317,23 @@ def run_gpu(args):
     value = units_per_step * args.steps / (dev_ms * 1e-3)
     e2e_value = units_per_step * e2e_steps / (e2e_ms * 1e-3)
     peak, peak_src = peaks()
-    per_unit = BYTES[wl] / (90 if wl == "lidar" else 1)
-    # dominant kernel of the step: its own launches are timed inside this same region
-    achieved = (value / world) * per_unit / 1e9
+    # roofline of the dominant kernel (step_kernel in the tick, else the only kernel): algorithmic bytes of ONE launch
+    # (1,488 B per car-step, 416 B per 90-ray scan) / its own CUDA-event duration in this timed region
+    dom = "lidar_kernel" if wl == "lidar" else "step_kernel"
+    dom_ms = lidar_ms if wl == "lidar" else step_ms
+    per_unit = (BYTES["lidar"] if wl == "lidar" else BYTES["step"])
+    achieved = cars * per_unit / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(dom)
+    kernels = {}
+    if lidar_ms is not None:
+        kernels["lidar_kernel"] = {"ms": float(lidar_ms), "rays_per_s": cars * 90 / (lidar_ms * 1e-3), "ns_per_ray": lidar_ms * 1e6 / (cars * 90),
+                                   "algorithmic_GBps": cars * BYTES["lidar"] / (lidar_ms * 1e-3) / 1e9}
+    if step_ms is not None:
+        kernels["step_kernel"] = {"ms": float(step_ms), "car_steps_per_s": cars / (step_ms * 1e-3),
+                                  "algorithmic_GBps": cars * BYTES["step"] / (step_ms * 1e-3) / 1e9}
     metric, unit = ("lidar rays/s", "rays/s") if wl == "lidar" else ("car-steps/s", "car-steps/s")
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -300,12 +344,13 @@ def run_gpu(args):
                        "timing": "CUDA events on the launching stream per step, summed; max over ranks",
                        "sharding": f"{world} x {cars} cars, no collective on the step path"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_unit": per_unit,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": dom, "kernel_ms": float(dom_ms),
+                         "algorithmic_bytes_per_launch": cars * per_unit, "algorithmic_bytes_per_unit": per_unit,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/)" if traffic else None,
                          "note": "latency/issue-bound path: algorithmic HBM traffic is far below peak by construction (SURVEY §8 d)"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "how": "C ABI with pinned host buffers, wall clock around H2D + kernels + D2H"},
-            "gpu_launches": launches, "clocks": clocks}
+            "gpu_launches": launches, "clocks": clocks, "kernels": kernels}
     if wl != "lidar":
         line["rays_per_s"] = value * 90 if wl == "tick" else 0.0
     if rank == 0:
@@ -331,6 +376,7 @@ def main():
     ap.add_argument("--cars", type=int, default=None)
     ap.add_argument("--settle", type=int, default=200, help="untimed ticks before timing (tick/step workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused-check", action="store_true", help="assert that ftgp_tick == the four separate calls, bit for bit")
     args = ap.parse_args()
     if args.cars is None:
         args.cars = 4096 if args.workload == "lidar" else 65536

@@ -42,7 +42,7 @@ SIGNATURES = {
     "ftgp_geom_destroy": (None, [_vp]),
     "ftgp_geom_device": (_i, [_vp]),
     "ftgp_geom_bytes": (_i64, [_vp]),
-    "ftgp_lidar": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "ftgp_lidar": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "ftgp_lidar_host": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "ftgp_reset": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "ftgp_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),

@@ -574,14 +574,14 @@ int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const i
 using namespace ftgp;
 
 extern "C" int ftgp_lidar(const ftgp_geom* g, const double* qpos, int64_t qpos_stride,
-                          const int32_t* track_id, const uint8_t* visible, int64_t ncars,
+                          const int32_t* track_id, const uint8_t* visible, const int32_t* lap, int64_t ncars,
                           int cars_per_world, float* ranges, float* min_range, void* stream) {
     if (!g || !qpos || !ranges || ncars < 0 || qpos_stride < 7 || cars_per_world < 1) {
         set_error("ftgp_lidar: bad argument"); return FTGP_ERR_ARG;
     }
     if (ncars == 0) return FTGP_OK;
     FTGP_CUDA(cudaSetDevice(g->device));
-    return launch_lidar(g, qpos, qpos_stride, track_id, visible, nullptr, ncars, cars_per_world, ranges, min_range,
+    return launch_lidar(g, qpos, qpos_stride, track_id, visible, lap, ncars, cars_per_world, ranges, min_range,
                         (cudaStream_t)stream);
 }
 

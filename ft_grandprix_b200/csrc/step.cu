@@ -229,7 +229,6 @@ extern "C" int ftgp_tick(const ftgp_tick_args* a, int nticks, void* stream) {
     if (!a || !a->geom || !a->qpos || !a->qvel || !a->warm || !a->ctrl || !a->ranges || !a->lap || !a->times ||
         a->ncars < 0 || a->cars_per_world < 1 || nticks < 0) { set_error("ftgp_tick: bad argument"); return FTGP_ERR_ARG; }
     if (a->ncars == 0) return FTGP_OK;
-    if (a->cars_per_world != 1) { set_error("ftgp_tick: multi-car worlds need car-car contacts (not built yet)"); return FTGP_ERR_UNSUPPORTED; }
     FTGP_CUDA(cudaSetDevice(a->geom->device));
     cudaStream_t s = (cudaStream_t)stream;
     for (int t = 0; t < nticks; t++) {

@@ -111,9 +111,11 @@ class Fleet:
         self.reset(xy, yaw)
 
     # ------------------------------------------------------------------ the per-tick pieces
-    def lidar(self, visible=None, min_range=None):
-        """data.sensordata[vehicle_state.sensors] for every car (custom.py:1395)."""
+    def lidar(self, visible=None, min_range=None, shadow_finished=True):
+        """data.sensordata[vehicle_state.sensors] for every car (custom.py:1395).  Finished cars are shadowed as in
+        the reference (stale ranges, invisible to the others) unless shadow_finished is False."""
         _lib.check(self.lib.ftgp_lidar(self.geom._ptr, _ptr(self.qpos), NQ, _ptr(self.track_id), _ptr(visible),
+                                       _ptr(self.lap) if shadow_finished else None,
                                        self.ncars, self.cars_per_world, _ptr(self.ranges), _ptr(min_range),
                                        self._s), "ftgp_lidar")
         return self.ranges

@@ -89,10 +89,13 @@ int64_t ftgp_geom_bytes(const ftgp_geom* g);
  * int32[ncars] or NULL (all on track 0).  cars_per_world > 1: consecutive cars share a
  * world and see each other's lidar cylinder (mushr.em.xml:108); visible: device
  * uint8[ncars] or NULL (0 = shadowed car, custom.py:1455-1464).
+ * lap: device lap state (FTGP_LAP_* rows, see below) or NULL; a car whose FTGP_LAP_FINISHED field
+ * is set has been shadow()ed (custom.py:1436-1464): its rangefinders are switched off (its
+ * ranges row keeps the stale values) and the other cars no longer see it.
  * ranges: device float[ncars][90].  min_range: device float[ncars] or NULL (smallest
  * non-negative range of the scan, +inf if none). */
 int ftgp_lidar(const ftgp_geom* g, const double* qpos, int64_t qpos_stride,
-               const int32_t* track_id, const uint8_t* visible, int64_t ncars,
+               const int32_t* track_id, const uint8_t* visible, const int32_t* lap, int64_t ncars,
                int cars_per_world, float* ranges, float* min_range, void* stream);
 /* host-buffer variant (same arguments in host memory) */
 int ftgp_lidar_host(const ftgp_geom* g, const double* qpos, int64_t qpos_stride,
@@ -152,7 +155,9 @@ typedef struct {
 } ftgp_tick_args;
 /* One iteration of physics_thread (custom.py:1337-1426) for the whole fleet:
  * lap update -> built-in driver on last tick's ranges -> ctrl -> [rangefinders from the
- * pre-step pose || mj_step] ; the same one-tick sensor lag as the reference. */
+ * pre-step pose, mj_step] ; the same one-tick sensor lag as the reference.
+ * cars_per_world > 1: the cars of a world see each other's lidar cylinder and are ranked
+ * together, but car-car CONTACTS are not generated yet (they pass through each other). */
 int ftgp_tick(const ftgp_tick_args* a, int nticks, void* stream);
 
 #ifdef __cplusplus
