@@ -387,7 +387,12 @@ __device__ __noinline__ LsTot ls_eval_w(const LsLane& L, double a) {
 template <class WallFn>
 __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __restrict__ qpos_g, double* __restrict__ qvel_g,
                               double* __restrict__ warm_g, const double* __restrict__ ctrl_g, const WallFn& walls,
-                              int T, StepInfo& info) {
+                              int T, bool live, StepInfo& info) {
+    // Every warp of the CTA passes the same BLOCK_SYNC points: the warps then run the same code region at the same
+    // time, which is what keeps this 200 KB kernel inside the 32 KB instruction cache (measured: 4 independent warps
+    // per CTA 9.3 ms, 16 loosely aligned warps 7.3 ms at 65,536 cars).  `live` is false for the padding warps of
+    // the last CTA: they run the step of the last car but write nothing.
+#define BLOCK_SYNC() __syncthreads()
     const unsigned FULL = 0xffffffffu;
     const int p = T;                                     // padded dof of this lane (31 = spare lane)
     const bool chain = p >= NR && p < NP;
@@ -408,6 +413,7 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
         __syncwarp();
     }
     S.V[T] = v;
+    BLOCK_SYNC();
     // ---- leaders: kinematics
     const bool root_leader = T == 0, wheel_leader = chain && l == 0;
     double Rw[9], R2[9];                                 // leader-private orientations (wheel / steering wheel)
@@ -493,6 +499,7 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
         inert_com_diag(S.inert[6 + w], is, is, is, I3, dd, SOFT_MASS);
     }
     __syncwarp();
+    BLOCK_SYNC();
     // ---- mass-matrix row of this lane (mj_crb)
     if (p < NP) {
         double Ib[10];
@@ -580,6 +587,7 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
     ncon = walls(mc, S, com, T, ncon);                  // chassis-vs-wall contacts appended (warp-cooperative)
     info.ncon_wall = ncon - info.ncon_wheel;
     __syncwarp();
+    BLOCK_SYNC();
     // ---- contact Jacobians: item = (contact, column)
     for (int it = T; it < ncon * 9; it += 32) {
         const int c = it / 9, col = it % 9, wh = S.cwheel[c];
@@ -657,6 +665,7 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
         }
     }
     __syncwarp();
+    BLOCK_SYNC();
     // ---- qacc_smooth = M^{-1} qfrc_smooth
     arrow_copy_w(S.H, S.M, T);
     arrow_factor_w(S.H, T);
@@ -665,6 +674,7 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
     arrow_solve_w(S.H, S.X, T);
     const double qas = S.X[T];
     __syncwarp();
+    BLOCK_SYNC();
     // ---- warm start vs smooth start
     double x, Ma, fp, hd, cj3[3] = {0, 0, 0}, eqjar = 0;
     {
@@ -702,13 +712,16 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
         search = -S.X[T];
         __syncwarp();
     };
+    BLOCK_SYNC();
     evaluate();
     solve_direction();
     int iter = 0;
-    while (iter < SOLVER_ITER) {
+    bool active = true;
+    // the loop is CTA-uniform: a warp whose car has converged idles through the remaining rounds
+    while (__syncthreads_or(active && iter < SOLVER_ITER)) {
         // ---- exact line search (PrimalSearch)
         double alpha = 0;
-        {
+        if (active && iter < SOLVER_ITER) {
             const double snorm = sqrt(warp_sum(search * search));
             if (snorm >= MINVAL) {
                 S.X[T] = search;
@@ -774,23 +787,26 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
                 if (alpha != 0) { x += alpha * search; Ma += alpha * Mv; }
             }
         }
-        if (alpha == 0) break;
-        const double oldcost = cost;
-        evaluate();
-        const double gn = warp_sum(grad * grad);
-        iter++;
-        // MuJoCo factorises H before this test; the direction is unused when the test ends the loop,
-        // so the factorisation is skipped then (same qacc, one block-arrow LDL^T less per step)
-        if (scale * (oldcost - cost) < SOLVER_TOL || scale * sqrt(gn) < SOLVER_TOL) break;
-        solve_direction();
+        else active = false;
+        if (active) {
+            if (alpha == 0) active = false;
+            else {
+                const double oldcost = cost;
+                evaluate();
+                const double gn = warp_sum(grad * grad);
+                iter++;
+                // MuJoCo factorises H before this test; the direction is unused when the test ends the loop,
+                // so the factorisation is skipped then (same qacc, one block-arrow LDL^T less per step)
+                if (scale * (oldcost - cost) < SOLVER_TOL || scale * sqrt(gn) < SOLVER_TOL) active = false;
+            }
+        }
+        BLOCK_SYNC();
+        if (active) solve_direction();
     }
     info.iters = iter;
-    if (__any_sync(FULL, bad_value(x))) {                 // mj_checkAcc
-        for (int i = T; i < NQ; i += 32) qpos_g[i] = (i == 1) ? 2.0 : ((i == 3 || i == 11 || i == 18 || i == 24 || i == 30) ? 1.0 : 0.0);
-        if (d >= 0) { qvel_g[d] = 0; warm_g[d] = 0; }
-        info.reset = 1;
-        return;
-    }
+    const bool badacc = __any_sync(FULL, bad_value(x));   // mj_checkAcc -> mj_resetData
+    if (badacc) info.reset = 1;
+    BLOCK_SYNC();
     // ---- mj_Euler with implicit joint damping
     arrow_copy_w(S.H, S.M, T);
     if (p >= 6 && p < NP && !dummy) {
@@ -804,9 +820,17 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
     arrow_solve_w(S.H, S.X, T);
     const double vnew = v + TIMESTEP * S.X[T];
     __syncwarp();
-    if (d >= 0) { warm_g[d] = x; qvel_g[d] = vnew; }
+    if (badacc) {
+        if (live) {
+            for (int i = T; i < NQ; i += 32) qpos_g[i] = (i == 1) ? 2.0 : ((i == 3 || i == 11 || i == 18 || i == 24 || i == 30) ? 1.0 : 0.0);
+            if (d >= 0) { qvel_g[d] = 0; warm_g[d] = 0; }
+        }
+        return;
+    }
+    if (d >= 0 && live) { warm_g[d] = x; qvel_g[d] = vnew; }
     S.X[T] = vnew;
     __syncwarp();
+    if (!live) return;
     // ---- mj_integratePos with the new velocity
     if (T < 3) qpos_g[T] = S.q[T] + TIMESTEP * S.X[T];
     else if (T == 3) {
@@ -826,6 +850,7 @@ __device__ void step_car_warp(WarpShared& S, const ModelConsts& mc, double* __re
         for (int a = 0; a < 4; a++) qpos_g[qb + a] = qq[a];
     }
     __syncwarp();
+#undef BLOCK_SYNC
 }
 
 #endif  // __CUDACC__

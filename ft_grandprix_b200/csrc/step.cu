@@ -112,15 +112,19 @@ struct WallsWarp {                              // warp-per-car flavour: lane v 
     }
 };
 
-__global__ void __launch_bounds__(128, 4)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 step_warp_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
                  double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
-                 const int32_t* __restrict__ lap, int64_t ncars, int nsteps, int32_t* __restrict__ status) {
+                 const int32_t* __restrict__ lap, const int32_t* __restrict__ perm, int64_t ncars, int nsteps,
+                 int32_t* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char smraw[];
     WarpShared* SS = reinterpret_cast<WarpShared*>(smraw);
     const int T = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t car = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    if (car >= ncars) return;
+    int64_t car = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const bool live = car < ncars;
+    if (!live) car = ncars - 1;                     // padding warp: same barriers, no stores
+    if (perm) car = perm[car];                      // cars grouped by their last Newton iteration count
     WarpShared& S = SS[wib];
     WallsWarp walls{nullptr, nullptr};
     const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
@@ -133,11 +137,11 @@ step_warp_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
     int st = 0;
     for (int s = 0; s < nsteps; s++) {
         StepInfo info;
-        step_car_warp(S, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, T, info);
-        __syncwarp();
+        step_car_warp(S, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, T, live, info);
+        __syncthreads();
         st = (info.iters & 0xFF) | (info.reset ? 0x100 : (st & 0x100)) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24);
     }
-    if (status && T == 0) status[car] = st;
+    if (status && T == 0 && live) status[car] = st;
 }
 
 __global__ void __launch_bounds__(64)
@@ -170,6 +174,40 @@ step_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double
     if (status) status[car] = st;
 }
 
+// The warp-per-car kernel runs the cars of a CTA in lock-step, so a CTA takes as many Newton rounds as its slowest
+// car.  The iteration count is strongly correlated from one step to the next (measured: mean 2, max over 8 random
+// cars 3.6), so cars are grouped by (last iteration count, in wall contact or not) with a counting sort.
+constexpr int NBIN = 16;
+__device__ __forceinline__ int order_bin(int st) { return min(st & 0xFF, 7) + (((st >> 16) & 0xFF) ? 8 : 0); }
+__global__ void order_hist_kernel(const int32_t* __restrict__ status, int64_t ncars, int32_t* __restrict__ hist) {
+    __shared__ int h[NBIN];
+    if (threadIdx.x < NBIN) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncars) atomicAdd(&h[order_bin(status[i])], 1);
+    __syncthreads();
+    if (threadIdx.x < NBIN && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void order_scatter_kernel(const int32_t* __restrict__ status, int64_t ncars, const int32_t* __restrict__ hist,
+                                     int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+    __shared__ int h[NBIN], base[NBIN];
+    if (threadIdx.x < NBIN) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int bin = 0, rank = 0;
+    if (i < ncars) { bin = order_bin(status[i]); rank = atomicAdd(&h[bin], 1); }
+    __syncthreads();
+    if (threadIdx.x < NBIN) {
+        int start = 0;
+        for (int b = 0; b < (int)threadIdx.x; b++) start += hist[b];
+        base[threadIdx.x] = start + (h[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], h[threadIdx.x]) : 0);
+    }
+    __syncthreads();
+    if (i < ncars) perm[base[bin] + rank] = (int32_t)i;
+}
+struct OrderScratch { int32_t* perm = nullptr; int32_t* counters = nullptr; int64_t cap = 0; };
+static OrderScratch g_order[16];
+
 int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
                 const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
                 cudaStream_t stream) {
@@ -188,17 +226,44 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
         step_kernel<<<(unsigned)((ncars + threads - 1) / threads), threads, 0, stream>>>(
             blob, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status);
     } else {
-        static int warps = 0;
-        if (!warps) { const char* e = getenv("FTGP_STEP_WARPS"); warps = e ? atoi(e) : 4; if (warps < 1 || warps > 4) warps = 4; }
-        const size_t smem = warps * sizeof(WarpShared);
-        static bool attr[16] = {false};
-        if (dev < 16 && !attr[dev]) {
-            FTGP_CUDA(cudaFuncSetAttribute(step_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            FTGP_CUDA(cudaFuncSetAttribute(step_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            attr[dev] = true;
+        // CTA shape: `warps` cars per CTA (the CTA runs its cars in lock-step phases), register budget by variant
+        static int warps = 0, variant = 0;
+        if (!warps) {
+            const char* e = getenv("FTGP_STEP_WARPS"); warps = e ? atoi(e) : 8; if (warps < 1 || warps > 16) warps = 8;
+            const char* v = getenv("FTGP_STEP_VARIANT"); variant = v ? atoi(v) : 0;
         }
-        step_warp_kernel<<<(unsigned)((ncars + warps - 1) / warps), warps * 32, smem, stream>>>(
-            blob, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status);
+        const size_t smem = warps * sizeof(WarpShared);
+        const int32_t* perm = nullptr;
+        static int use_order = -1;
+        if (use_order < 0) { const char* e = getenv("FTGP_STEP_ORDER"); use_order = (e && e[0] == '0') ? 0 : 1; }
+        if (use_order && status && ncars >= 1024 && ncars < (int64_t)1 << 31 && dev < 16) {
+            OrderScratch& o = g_order[dev];
+            if (o.cap < ncars) {
+                if (o.perm) cudaFree(o.perm);
+                if (!o.counters) FTGP_CUDA(cudaMalloc(&o.counters, 2 * NBIN * sizeof(int32_t)));
+                o.perm = nullptr; o.cap = 0;
+                FTGP_CUDA(cudaMalloc(&o.perm, ncars * sizeof(int32_t)));
+                o.cap = ncars;
+            }
+            FTGP_CUDA(cudaMemsetAsync(o.counters, 0, 2 * NBIN * sizeof(int32_t), stream));
+            const unsigned nb = (unsigned)((ncars + 255) / 256);
+            order_hist_kernel<<<nb, 256, 0, stream>>>(status, ncars, o.counters);
+            order_scatter_kernel<<<nb, 256, 0, stream>>>(status, ncars, o.counters, o.counters + NBIN, o.perm);
+            count_launch(2);
+            perm = o.perm;
+        }
+        auto launch = [&](auto kern) -> int {
+            FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            kern<<<(unsigned)((ncars + warps - 1) / warps), warps * 32, smem, stream>>>(
+                blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status);
+            return FTGP_OK;
+        };
+        int rc2;
+        if (variant == 1 && warps <= 8) rc2 = launch(step_warp_kernel<256, 1>);          // 255 registers, no spills
+        else if (variant == 2 && warps <= 12) rc2 = launch(step_warp_kernel<384, 1>);     // 168 registers
+        else rc2 = launch(step_warp_kernel<512, 1>);                                      // 128 registers
+        if (rc2) return rc2;
     }
     count_launch();
     FTGP_CUDA(cudaGetLastError());
