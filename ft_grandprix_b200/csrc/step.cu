@@ -10,6 +10,7 @@
 #include "common.h"
 #include "mushr_consts.h"
 #include "mushr_step_warp.cuh"
+#include "mushr_step_quad.cuh"
 #include <cstdlib>
 
 namespace ftgp {
@@ -31,7 +32,7 @@ static int ensure_model(int device) {
 // chassis-vs-wall contacts (this framework's definition, identical to oracle/step.c wall_contacts()):
 // each chassis hull vertex below the hfield surface gives one condim-3 contact against the surface
 // triangle's plane.  Reads the compiled track from global memory (L2-resident, ~50 KB).
-struct WallHit { double dist, nrm[3], t1[3], t2[3], pnt[3]; };
+typedef QWallHit WallHit;     // { dist, nrm[3], t1[3], t2[3], pnt[3] }
 
 __device__ bool wall_probe(const uint32_t* blob, const TrackHeader* th, const double* R1, const double* p1, int v, WallHit& h) {
     const double hull[MUSHR_CHASSIS_NHULL][3] = MUSHR_CHASSIS_HULL;
@@ -174,6 +175,45 @@ step_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double
     if (status) status[car] = st;
 }
 
+struct WallsQuad {                              // quad-per-car flavour: probe of one hull vertex
+    const uint32_t* blob; const TrackHeader* th;
+    __device__ __forceinline__ bool enabled() const { return blob != nullptr; }
+    __device__ __forceinline__ bool operator()(const double* R1, const double* p1, int v, QWallHit& h) const { return wall_probe(blob, th, R1, p1, v, h); }
+};
+
+// Quad-per-car: four lanes (one per wheel chain) advance one car, 8 cars per warp; see mushr_step_quad.cuh.
+// Shared memory: [slot][thread] for the lane-private slots, then [slot][car] for the per-car slots.
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
+                 double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
+                 const int32_t* __restrict__ lap, const int32_t* __restrict__ perm, int64_t ncars, int nsteps,
+                 int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double* sm = reinterpret_cast<double*>(smraw);
+    const int tid = threadIdx.x, cib = tid >> 2;
+    int64_t car = (int64_t)blockIdx.x * (NT / 4) + cib;
+    if (car >= ncars) return;                       // whole quads leave together: nothing in this kernel spans quads
+    if (perm) car = perm[car];                      // cars grouped by their last Newton iteration count
+    QuadDev<NT, NT / 4> qd;
+    qd.w = tid & 3; qd.priv = sm + tid; qd.shr = sm + QP_N * NT + cib; qd.mask = 0xFu << (tid & 28);
+    WallsQuad walls{nullptr, nullptr};
+    const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
+    if (blob && !shadowed) {
+        const GeomHeader* gh = reinterpret_cast<const GeomHeader*>(blob);
+        int tid_ = track_id ? track_id[car] : 0;
+        if (tid_ < 0 || tid_ >= gh->ntracks) tid_ = 0;
+        walls.blob = blob; walls.th = reinterpret_cast<const TrackHeader*>(blob + gh->track_off[tid_]);
+    }
+    int st = 0;
+    for (int s = 0; s < nsteps; s++) {
+        StepInfo info;
+        step_car_quad(qd, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, true, info);
+        st = (info.iters & 0xFF) | (info.reset ? 0x100 : (st & 0x100)) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24);
+    }
+    if (status && qd.w == 0) status[car] = st;
+}
+
 // The warp-per-car kernel runs the cars of a CTA in lock-step, so a CTA takes as many Newton rounds as its slowest
 // car.  The iteration count is strongly correlated from one step to the next (measured: mean 2, max over 8 random
 // cars 3.6), so cars are grouped by (last iteration count, in wall contact or not) with a counting sort.
@@ -208,19 +248,63 @@ __global__ void order_scatter_kernel(const int32_t* __restrict__ status, int64_t
 struct OrderScratch { int32_t* perm = nullptr; int32_t* counters = nullptr; int64_t cap = 0; };
 static OrderScratch g_order[16];
 
+// cars grouped by (last Newton iteration count, wall contact) for the kernels that run several cars in lock-step
+static int order_cars(const int32_t* status, int64_t ncars, int dev, cudaStream_t stream, const int32_t** perm) {
+    *perm = nullptr;
+    static int use_order = -1;
+    if (use_order < 0) { const char* e = getenv("FTGP_STEP_ORDER"); use_order = (e && e[0] == '0') ? 0 : 1; }
+    if (!use_order || !status || ncars < 1024 || ncars >= (int64_t)1 << 31 || dev >= 16) return FTGP_OK;
+    OrderScratch& o = g_order[dev];
+    if (o.cap < ncars) {
+        if (o.perm) cudaFree(o.perm);
+        if (!o.counters) FTGP_CUDA(cudaMalloc(&o.counters, 2 * NBIN * sizeof(int32_t)));
+        o.perm = nullptr; o.cap = 0;
+        FTGP_CUDA(cudaMalloc(&o.perm, ncars * sizeof(int32_t)));
+        o.cap = ncars;
+    }
+    FTGP_CUDA(cudaMemsetAsync(o.counters, 0, 2 * NBIN * sizeof(int32_t), stream));
+    const unsigned nb = (unsigned)((ncars + 255) / 256);
+    order_hist_kernel<<<nb, 256, 0, stream>>>(status, ncars, o.counters);
+    order_scatter_kernel<<<nb, 256, 0, stream>>>(status, ncars, o.counters, o.counters + NBIN, o.perm);
+    count_launch(2);
+    *perm = o.perm;
+    return FTGP_OK;
+}
+
 int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
                 const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
                 cudaStream_t stream) {
     int dev = 0;
     FTGP_CUDA(cudaGetDevice(&dev));
     int rc = ensure_model(dev); if (rc) return rc;
-    // Two implementations of the same arithmetic (both parity-tested): thread-per-car (default: fewer issue
-    // slots per car, local-memory bound) and warp-per-car (FTGP_STEP_IMPL=warp: state in registers / shared
-    // memory, instruction-fetch bound).  Measured on B200 at 65,536 cars: 3.8 ms vs 9.3 ms per step.
+    // Three implementations of the same arithmetic (all parity-tested), FTGP_STEP_IMPL = quad (default) | thread | warp:
+    //   quad   four lanes per car, one per wheel chain (mushr_step_quad.cuh): factorisations in registers
+    //   thread one thread per car (mushr_step.cuh): fewest instructions, 16.7 KB local frame per thread, DRAM-latency bound
+    //   warp   one warp per car (mushr_step_warp.cuh): state in shared memory, 5.4x the instructions
     static int impl = -1;
-    if (impl < 0) { const char* e = getenv("FTGP_STEP_IMPL"); impl = (e && e[0] == 'w') ? 0 : 1; }
+    if (impl < 0) { const char* e = getenv("FTGP_STEP_IMPL"); impl = !e ? 2 : (e[0] == 'w' ? 0 : (e[0] == 't' ? 1 : 2)); }
     const uint32_t* blob = g ? g->d_blob : nullptr;
-    if (impl == 1) {
+    if (impl == 2) {
+        static int qt = 0, minb = 0;
+        if (!qt) {
+            const char* e = getenv("FTGP_STEP_QT"); qt = e ? atoi(e) : 64; if (qt != 32 && qt != 64 && qt != 128) qt = 64;
+            const char* m = getenv("FTGP_STEP_MINB"); minb = m ? atoi(m) : 0;
+        }
+        const int32_t* perm = nullptr;
+        if ((rc = order_cars(status, ncars, dev, stream, &perm))) return rc;
+        const size_t smem = (size_t)qt * (QP_N + QC_N / 4) * sizeof(double);
+        auto launch = [&](auto kern) -> int {
+            FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(unsigned)((ncars + qt / 4 - 1) / (qt / 4)), qt, smem, stream>>>(
+                blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status);
+            return FTGP_OK;
+        };
+        int rc2;
+        if (qt == 32) rc2 = minb == 1 ? launch(step_quad_kernel<32, 8>) : launch(step_quad_kernel<32, 1>);
+        else if (qt == 128) rc2 = minb == 1 ? launch(step_quad_kernel<128, 2>) : launch(step_quad_kernel<128, 1>);
+        else rc2 = minb == 1 ? launch(step_quad_kernel<64, 4>) : launch(step_quad_kernel<64, 1>);
+        if (rc2) return rc2;
+    } else if (impl == 1) {
         static int threads = 0;
         if (!threads) { const char* e = getenv("FTGP_STEP_BLOCK"); threads = e ? atoi(e) : 64; if (threads < 32 || threads > 64) threads = 64; }
         step_kernel<<<(unsigned)((ncars + threads - 1) / threads), threads, 0, stream>>>(
@@ -234,24 +318,7 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
         }
         const size_t smem = warps * sizeof(WarpShared);
         const int32_t* perm = nullptr;
-        static int use_order = -1;
-        if (use_order < 0) { const char* e = getenv("FTGP_STEP_ORDER"); use_order = (e && e[0] == '0') ? 0 : 1; }
-        if (use_order && status && ncars >= 1024 && ncars < (int64_t)1 << 31 && dev < 16) {
-            OrderScratch& o = g_order[dev];
-            if (o.cap < ncars) {
-                if (o.perm) cudaFree(o.perm);
-                if (!o.counters) FTGP_CUDA(cudaMalloc(&o.counters, 2 * NBIN * sizeof(int32_t)));
-                o.perm = nullptr; o.cap = 0;
-                FTGP_CUDA(cudaMalloc(&o.perm, ncars * sizeof(int32_t)));
-                o.cap = ncars;
-            }
-            FTGP_CUDA(cudaMemsetAsync(o.counters, 0, 2 * NBIN * sizeof(int32_t), stream));
-            const unsigned nb = (unsigned)((ncars + 255) / 256);
-            order_hist_kernel<<<nb, 256, 0, stream>>>(status, ncars, o.counters);
-            order_scatter_kernel<<<nb, 256, 0, stream>>>(status, ncars, o.counters, o.counters + NBIN, o.perm);
-            count_launch(2);
-            perm = o.perm;
-        }
+        if ((rc = order_cars(status, ncars, dev, stream, &perm))) return rc;
         auto launch = [&](auto kern) -> int {
             FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
