@@ -14,8 +14,12 @@
 // kinematics / CRB / RNE of the wheel and softener bodies) runs 4-wide with no communication; the root block is
 // reduced across the quad with two xor-shuffles per value and then handled redundantly by the four lanes, which
 // keeps every loop bound and branch quad-uniform (sums are bit-identical in the four lanes).
-// A warp holds 8 cars; per-lane state is ~1/4 of a car: the factorisation runs entirely in registers, M and the
-// wheel contact Jacobian sit in shared memory ([slot][thread] layout: conflict-free), the rest is a ~1 KB frame.
+// A warp holds 8 cars; per-lane state is ~1/4 of a car and ALL of the solver's persistent state is in shared
+// memory: lane-private slots in [slot][thread] layout (conflict-free), root parts of the dof vectors and the root
+// block of M once per car in [slot][car] layout (the four lanes read them as a broadcast).  1 250 B per lane, so
+// 160 lanes (40 cars) are resident per SM; the factorisation itself runs entirely in registers.
+// Rule for the per-car slots: every lane computes the same value and every lane writes it, always after a quad
+// sync that follows the last read of the old value (read phase, sync, write phase).
 //
 // The code is __host__ __device__ over a communicator policy Q (device: shuffles inside the quad; host tests:
 // four OS threads and a barrier, tests/host_harness/step_quad_host.cpp), so its arithmetic is checked against the
@@ -36,23 +40,48 @@ namespace mushr {
 constexpr int QP_MW = 0;             // 21  chain block of M, lower triangle
 constexpr int QP_MB = 21;            // 36  border of M: slot l x root dof j < 6 (column 6 of M's border is zero)
 constexpr int QP_CJ = 57;            // 18  wheel-ground contact Jacobian, row a x (3 root rotations, 3 chain slots)
-constexpr int QP_N = 75;
+constexpr int QP_FRA = 75;           // 6   aref of the friction-loss rows of the chain slots
+constexpr int QP_EQ = 81;            // 3   Ackermann equality of a front chain: D (0: none), aref, dP/dx
+constexpr int QP_LIM = 84;           // 6   suspension / front steering limit: D[2] (0: inactive), aref[2], sign[2]
+constexpr int QP_WC = 90;            // 5   wheel-ground contact: D (0: none), aref[4]
+constexpr int QP_WD = 95;            // 6   line search: contact-frame dots J x, J s
+constexpr int QP_VEC = 101;          // 6 x 6 chain parts of the dof vectors below
+constexpr int QP_N = 137;
 constexpr int QC_MR = 0;             // 28  root block of M, lower triangle
-constexpr int QC_N = 28;
+constexpr int QC_R6 = 28;            // 4   rows of root dof 6 (steering wheel): friction aref, limit D, aref, sign
+constexpr int QC_VEC = 32;           // 6 x 7 root parts of the dof vectors
+constexpr int QC_N = 74;
+struct QVec { int p, c; };           // dof vector: chain part at P(p + l), root part at C(c + i)
+#define VQFS (QVec{QP_VEC, QC_VEC})
+#define VQAS (QVec{QP_VEC + 6, QC_VEC + 7})
+#define VX (QVec{QP_VEC + 12, QC_VEC + 14})
+#define VMA (QVec{QP_VEC + 18, QC_VEC + 21})
+#define VS (QVec{QP_VEC + 24, QC_VEC + 28})
+#define VMV (QVec{QP_VEC + 30, QC_VEC + 35})
+// model constants of the friction-loss rows (pos = 0, so impedance and regulariser never change): (D, R f, f) for
+// chain slot (w, l) at 3 (6 w + l), root dof 6 at 72
+constexpr int QK_N = 75;
 
 template <int PS_, int CS_>
 struct QuadMem {                     // PS: stride between slots of private data (threads per CTA), CS: cars per CTA
     static constexpr int PS = PS_, CS = CS_;
-    double* priv; double* shr; int w;
+    double* priv; double* shr; const double* ktab; int w;
     FT_HD double& P(int i) const { return priv[i * PS]; }
     FT_HD double& C(int i) const { return shr[i * CS]; }
+    FT_HD double K(int i) const { return ktab[i]; }
     FT_HD int lane() const { return w; }
 };
 
 #if defined(__CUDACC__)
+extern __shared__ __align__(16) double quad_sm[];      // the kernel's dynamic shared memory (so that accesses are LDS/STS)
 template <int PS_, int CS_>
-struct QuadDev : QuadMem<PS_, CS_> {
-    unsigned mask;
+struct QuadDev {                     // po / co / ko: offsets (in doubles) of the lane's, the car's and the table's first slot
+    static constexpr int PS = PS_, CS = CS_;
+    int po, co, ko, w; unsigned mask;
+    __device__ __forceinline__ double& P(int i) const { return quad_sm[po + i * PS]; }
+    __device__ __forceinline__ double& C(int i) const { return quad_sm[co + i * CS]; }
+    __device__ __forceinline__ double K(int i) const { return quad_sm[ko + i]; }
+    __device__ __forceinline__ int lane() const { return w; }
     __device__ __forceinline__ double sum(double v) const {
         v += __shfl_xor_sync(mask, v, 1);
         v += __shfl_xor_sync(mask, v, 2);
@@ -64,139 +93,131 @@ struct QuadDev : QuadMem<PS_, CS_> {
 };
 #endif
 
-// ---- per-lane solver state ------------------------------------------------------------------------------------
-constexpr int QMAXCH = 2;            // chassis contacts one lane can own (MAXCON = 8 over four lanes)
-struct QRows {
-    double fr_D[NC], fr_Rf[NC], fr_f[NC], fr_aref[NC];     // friction loss of the chain slots (f = 0: no row)
-    double eq_D, eq_aref, eq_der;                           // Ackermann equality of a front chain (D = 0: none)
-    double lim_D[2], lim_aref[2], lim_sign[2];              // suspension, front steering (sign 0: inactive)
-    double fr6_D, fr6_Rf, fr6_f, fr6_aref;                  // rows of root dof 6 (steering wheel): lane 0 only
-    double lim6_D, lim6_aref, lim6_sign;
-    double wc_D, wc_aref[4];                                // wheel-ground contact, D = 0: none
-    int nch;                                                // chassis (wall) contacts owned by this lane
-    double ch_D[QMAXCH], ch_aref[QMAXCH][4], ch_J[QMAXCH][3][6];
-};
-struct QCar {
-    QRows r;
-    double qfs_r[NR], qfs_c[NC], qas_r[NR], qas_c[NC];
-    double x_r[NR], x_c[NC], Ma_r[NR], Ma_c[NC], g_r[NR], g_c[NC], s_r[NR], s_c[NC], Mv_r[NR], Mv_c[NC];
-    double fc_r[NR], fc_c[NC];
-    double cost, gauss;
-    unsigned mask;                   // which rows are in their quadratic zone at x (bits below)
-};
+FT_HDN void quad_const_entry(const ModelConsts& mc, int g, double* t) {      // g: 0..23 chain slot (w, l), 24: root dof 6
+    const int p = g < 24 ? NR + g : 6;
+    const double f = dof_dummy(p) ? 0.0 : dof_floss(p);
+    double K, B, imp, R;
+    kbi(0.9, 0.0, mc.dof_invweight0[p], K, B, imp, R);
+    t[3 * g] = f > 0 ? 1 / R : 0.0; t[3 * g + 1] = f > 0 ? R * f : 0.0; t[3 * g + 2] = f;
+}
+
+// chassis (wall) contacts owned by the lane: rare, kept in the lane's frame and only touched when nch > 0
+constexpr int QMAXCH = 2;            // MAXCON = 8 contacts over four lanes
+struct QChassis { double D[QMAXCH], aref[QMAXCH][4], J[QMAXCH][3][6], dx[QMAXCH][3], ds[QMAXCH][3]; };
+struct QState { double cost, gauss; unsigned mask; int nch; };
 constexpr int QB_FR = 0, QB_FR6 = 6, QB_LIM = 7, QB_LIM6 = 9, QB_WC = 10, QB_CH = 14;
 constexpr double WC_MU = 0.5, CH_MU = 1.0;
+constexpr double REF_B = 2 / (0.95 * 0.02);          // kbi(): B of the default solref with dmax 0.95
 
 FT_HD int popc4(unsigned m) { return (int)((m & 1u) + ((m >> 1) & 1u) + ((m >> 2) & 1u) + ((m >> 3) & 1u)); }
 FT_HD double dot6q(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3] + a[4] * b[4] + a[5] * b[5]; }
 
-// wheel contact Jacobian row a (0 normal, 1, 2 tangents) in the lane's 9 columns (root 0-5, chain slots 0-2):
-// frame n = (0,0,1), t1 = (0,1,0), t2 = (-1,0,0); the translation columns are constants
-template <class Q>
-FT_HD void wc_jac(const Q& qd, double J[3][9]) {
-    J[0][0] = 0; J[0][1] = 0; J[0][2] = 1;
-    J[1][0] = 0; J[1][1] = 1; J[1][2] = 0;
-    J[2][0] = -1; J[2][1] = 0; J[2][2] = 0;
+template <class Q> FT_HD void vec_load(const Q& qd, QVec v, double* r, double* c) {
 #pragma unroll
-    for (int a = 0; a < 3; a++)
+    for (int i = 0; i < NR; i++) r[i] = qd.C(v.c + i);
 #pragma unroll
-        for (int k = 0; k < 6; k++) J[a][3 + k] = qd.P(QP_CJ + 6 * a + k);
+    for (int l = 0; l < NC; l++) c[l] = qd.P(v.p + l);
 }
-FT_HD void wc_dots(const double J[3][9], const double* xr, const double* xc, double* d3) {
+template <class Q> FT_HD void vec_store(const Q& qd, QVec v, const double* r, const double* c) {   // caller has synced
+#pragma unroll
+    for (int i = 0; i < NR; i++) qd.C(v.c + i) = r[i];
+#pragma unroll
+    for (int l = 0; l < NC; l++) qd.P(v.p + l) = c[l];
+}
+
+// wheel contact in its frame n = (0,0,1), t1 = (0,1,0), t2 = (-1,0,0): d3 = J x.  The translation columns of J are
+// those unit vectors; the other six (root rotations, chain slots 0-2) are in shared memory.
+template <class Q>
+FT_HD void wc_dots(const Q& qd, const double* xr, const double* xc, double* d3) {
+    d3[0] = xr[2]; d3[1] = xr[1]; d3[2] = -xr[0];
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        double s = 0;
+        double s = d3[a];
 #pragma unroll
-        for (int col = 0; col < 6; col++) s += J[a][col] * xr[col];
-#pragma unroll
-        for (int col = 0; col < 3; col++) s += J[a][6 + col] * xc[col];
+        for (int k = 0; k < 3; k++) s += qd.P(QP_CJ + 6 * a + k) * xr[3 + k] + qd.P(QP_CJ + 6 * a + 3 + k) * xc[k];
         d3[a] = s;
     }
 }
-FT_HD void ch_dots(const double J[3][6], const double* xr, double* d3) {
-    for (int a = 0; a < 3; a++) d3[a] = dot6q(J[a], xr);
-}
 
-// ---- cost of this lane's rows at (xr, xc): forces J^T f into fr (root, partial) / fc (chain), zone mask ----------
+// ---- cost of this lane's rows at the vector X: forces J^T f into fr (root, lane's share) / fc (chain), zone mask --
 template <class Q>
-FT_QN double rows_eval(const Q& qd, const QRows& r, const double* xr, const double* xc, double* fr, double* fc, unsigned& mask_out) {
+FT_QN double rows_eval(const Q& qd, const QChassis& ch, int nch, QVec X, double* fr, double* fc, unsigned& mask_out) {
+    const int w = qd.lane();
+    double xr[NR], xc[NC];
+    vec_load(qd, X, xr, xc);
     double cost = 0;
     unsigned mask = 0;
+#pragma unroll
     for (int i = 0; i < NR; i++) fr[i] = 0;
-    for (int l = 0; l < NC; l++) fc[l] = 0;
-    if (r.eq_D > 0) {                                                    // equality: always quadratic
-        const double jar = xc[1] - r.eq_der * xr[6] - r.eq_aref, D = r.eq_D;
+#pragma unroll
+    for (int l = 0; l < NC; l++) {                                       // friction loss: quadratic inside +-R f, linear outside
+        const double D = qd.K(3 * (6 * w + l)), Rf = qd.K(3 * (6 * w + l) + 1), f = qd.K(3 * (6 * w + l) + 2);
+        const double jar = xc[l] - qd.P(QP_FRA + l);
+        const bool lo = jar <= -Rf, hi = jar >= Rf, lin = lo || hi;
+        cost += lin ? -0.5 * Rf * f + f * (lo ? -jar : jar) : 0.5 * D * jar * jar;
+        fc[l] = lin ? (lo ? f : -f) : -D * jar;
+        if (!lin) mask |= 1u << (QB_FR + l);
+    }
+    {                                                                    // equality (D = 0 on the rear lanes)
+        const double D = qd.P(QP_EQ), der = qd.P(QP_EQ + 2), jar = xc[1] - der * xr[6] - qd.P(QP_EQ + 1);
         cost += 0.5 * D * jar * jar;
         const double f = -D * jar;
-        fc[1] += f; fr[6] -= r.eq_der * f;
+        fc[1] += f; fr[6] -= der * f;
     }
 #pragma unroll
-    for (int l = 0; l < NC; l++) {                                       // friction loss
-        const double f = r.fr_f[l];
-        if (f <= 0) continue;
-        const double jar = xc[l] - r.fr_aref[l], Rf = r.fr_Rf[l], D = r.fr_D[l];
-        if (jar <= -Rf) { cost += -0.5 * Rf * f - f * jar; fc[l] += f; }
-        else if (jar >= Rf) { cost += -0.5 * Rf * f + f * jar; fc[l] -= f; }
-        else { cost += 0.5 * D * jar * jar; fc[l] += -D * jar; mask |= 1u << (QB_FR + l); }
+    for (int k = 0; k < 2; k++) {                                        // limits: active when jar < 0 (D = 0: no row)
+        const double D = qd.P(QP_LIM + k), sg = qd.P(QP_LIM + 4 + k), jar = sg * xc[k] - qd.P(QP_LIM + 2 + k);
+        if (D > 0 && jar < 0) { cost += 0.5 * D * jar * jar; fc[k] += sg * (-D * jar); mask |= 1u << (QB_LIM + k); }
     }
-    if (r.fr6_f > 0) {
-        const double f = r.fr6_f, jar = xr[6] - r.fr6_aref, Rf = r.fr6_Rf, D = r.fr6_D;
-        if (jar <= -Rf) { cost += -0.5 * Rf * f - f * jar; fr[6] += f; }
-        else if (jar >= Rf) { cost += -0.5 * Rf * f + f * jar; fr[6] -= f; }
-        else { cost += 0.5 * D * jar * jar; fr[6] += -D * jar; mask |= 1u << QB_FR6; }
+    if (w == 0) {                                                        // rows of the steering-wheel dof
+        const double D = qd.K(72), Rf = qd.K(73), f = qd.K(74), jar = xr[6] - qd.C(QC_R6);
+        const bool lo = jar <= -Rf, hi = jar >= Rf, lin = lo || hi;
+        cost += lin ? -0.5 * Rf * f + f * (lo ? -jar : jar) : 0.5 * D * jar * jar;
+        fr[6] += lin ? (lo ? f : -f) : -D * jar;
+        if (!lin) mask |= 1u << QB_FR6;
+        const double D6 = qd.C(QC_R6 + 1), sg = qd.C(QC_R6 + 3), jar6 = sg * xr[6] - qd.C(QC_R6 + 2);
+        if (D6 > 0 && jar6 < 0) { cost += 0.5 * D6 * jar6 * jar6; fr[6] += sg * (-D6 * jar6); mask |= 1u << QB_LIM6; }
     }
-#pragma unroll
-    for (int k = 0; k < 2; k++) {                                        // limits: active when jar < 0
-        const double sg = r.lim_sign[k];
-        if (sg == 0) continue;
-        const double jar = sg * xc[k] - r.lim_aref[k], D = r.lim_D[k];
-        if (jar < 0) { cost += 0.5 * D * jar * jar; fc[k] += sg * (-D * jar); mask |= 1u << (QB_LIM + k); }
-    }
-    if (r.lim6_sign != 0) {
-        const double sg = r.lim6_sign, jar = sg * xr[6] - r.lim6_aref, D = r.lim6_D;
-        if (jar < 0) { cost += 0.5 * D * jar * jar; fr[6] += sg * (-D * jar); mask |= 1u << QB_LIM6; }
-    }
-    if (r.wc_D > 0) {                                                    // pyramidal rows of the wheel contact
-        double J[3][9], d3[3];
-        wc_jac(qd, J);
-        wc_dots(J, xr, xc, d3);
-        const double D = r.wc_D;
+    const double Dw = qd.P(QP_WC);
+    if (Dw > 0) {                                                        // pyramidal rows of the wheel contact
+        double d3[3], F[3] = {0, 0, 0};                                  // F: sum of the row forces in the contact frame
+        wc_dots(qd, xr, xc, d3);
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
             const double sg = (rr & 1) ? -WC_MU : WC_MU; const int ta = 1 + (rr >> 1);
-            const double jar = d3[0] + sg * d3[ta] - r.wc_aref[rr];
-            if (jar >= 0) continue;
-            cost += 0.5 * D * jar * jar;
-            mask |= 1u << (QB_WC + rr);
-            const double f = -D * jar;
+            const double jar = d3[0] + sg * d3[ta] - qd.P(QP_WC + 1 + rr);
+            if (jar < 0) { cost += 0.5 * Dw * jar * jar; mask |= 1u << (QB_WC + rr); const double f = -Dw * jar; F[0] += f; F[ta] += sg * f; }
+        }
+        fr[0] -= F[2]; fr[1] += F[1]; fr[2] += F[0];
 #pragma unroll
-            for (int col = 0; col < 6; col++) fr[col] += (J[0][col] + sg * J[ta][col]) * f;
-#pragma unroll
-            for (int col = 0; col < 3; col++) fc[col] += (J[0][6 + col] + sg * J[ta][6 + col]) * f;
+        for (int k = 0; k < 3; k++) {
+            fr[3 + k] += qd.P(QP_CJ + k) * F[0] + qd.P(QP_CJ + 6 + k) * F[1] + qd.P(QP_CJ + 12 + k) * F[2];
+            fc[k] += qd.P(QP_CJ + 3 + k) * F[0] + qd.P(QP_CJ + 9 + k) * F[1] + qd.P(QP_CJ + 15 + k) * F[2];
         }
     }
-    for (int s = 0; s < r.nch; s++) {                                    // chassis contacts (walls): root dofs only
+    for (int s = 0; s < nch; s++) {                                      // chassis contacts (walls): root dofs only
         double d3[3];
-        ch_dots(r.ch_J[s], xr, d3);
-        const double D = r.ch_D[s];
+        for (int a = 0; a < 3; a++) d3[a] = dot6q(ch.J[s][a], xr);
+        const double D = ch.D[s];
         for (int rr = 0; rr < 4; rr++) {
             const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-            const double jar = d3[0] + sg * d3[ta] - r.ch_aref[s][rr];
+            const double jar = d3[0] + sg * d3[ta] - ch.aref[s][rr];
             if (jar >= 0) continue;
             cost += 0.5 * D * jar * jar;
             mask |= 1u << (QB_CH + 4 * s + rr);
             const double f = -D * jar;
-            for (int col = 0; col < 6; col++) fr[col] += (r.ch_J[s][0][col] + sg * r.ch_J[s][ta][col]) * f;
+            for (int col = 0; col < 6; col++) fr[col] += (ch.J[s][0][col] + sg * ch.J[s][ta][col]) * f;
         }
     }
     mask_out = mask;
     return cost;
 }
 
-// y = M x with M in shared memory; root part replicated
+// Y = M X with M in shared memory
 template <class Q>
-FT_QN void quad_mul(const Q& qd, const double* xr, const double* xc, double* yr, double* yc) {
-    double part[6];
+FT_QN void quad_mul(const Q& qd, QVec X, QVec Y) {
+    double xr[NR], xc[NC], yr[NR], yc[NC], part[6];
+    vec_load(qd, X, xr, xc);
 #pragma unroll
     for (int j = 0; j < 6; j++) part[j] = 0;
 #pragma unroll
@@ -216,33 +237,41 @@ FT_QN void quad_mul(const Q& qd, const double* xr, const double* xc, double* yr,
         if (i < 6) s += qd.sum(part[i]);
         yr[i] = s;
     }
+    qd.sync();
+    vec_store(qd, Y, yr, yc);
 }
 
-// gradient, cost and constraint force at c.x (needs c.Ma = M c.x)
+// cost, Gauss term and gradient (into S) at X (needs MA = M X)
 template <class Q>
-FT_QN void quad_evaluate(const Q& qd, QCar& c) {
-    double fr[NR];
+FT_QN void quad_evaluate(const Q& qd, const QChassis& ch, QState& st) {
+    double fr[NR], fc[NC], g_r[NR], g_c[NC];
     unsigned mask;
-    double cc = rows_eval(qd, c.r, c.x_r, c.x_c, fr, c.fc_c, mask);
-    c.mask = mask;
+    double cc = rows_eval(qd, ch, st.nch, VX, fr, fc, mask);
+    st.mask = mask;
     double g = 0;
 #pragma unroll
-    for (int l = 0; l < NC; l++) g += (c.Ma_c[l] - c.qfs_c[l]) * (c.x_c[l] - c.qas_c[l]);
+    for (int l = 0; l < NC; l++) {
+        const double d = qd.P(VMA.p + l) - qd.P(VQFS.p + l);
+        g += d * (qd.P(VX.p + l) - qd.P(VQAS.p + l));
+        g_c[l] = d - fc[l];
+    }
     cc = qd.sum(cc); g = qd.sum(g);
 #pragma unroll
-    for (int i = 0; i < NR; i++) { c.fc_r[i] = qd.sum(fr[i]); g += (c.Ma_r[i] - c.qfs_r[i]) * (c.x_r[i] - c.qas_r[i]); }
-    c.gauss = 0.5 * g; c.cost = cc + c.gauss;
-#pragma unroll
-    for (int i = 0; i < NR; i++) c.g_r[i] = c.Ma_r[i] - c.qfs_r[i] - c.fc_r[i];
-#pragma unroll
-    for (int l = 0; l < NC; l++) c.g_c[l] = c.Ma_c[l] - c.qfs_c[l] - c.fc_c[l];
+    for (int i = 0; i < NR; i++) {
+        const double d = qd.C(VMA.c + i) - qd.C(VQFS.c + i);
+        g += d * (qd.C(VX.c + i) - qd.C(VQAS.c + i));
+        g_r[i] = d - qd.sum(fr[i]);
+    }
+    st.gauss = 0.5 * g; st.cost = cc + st.gauss;
+    qd.sync();
+    vec_store(qd, VS, g_r, g_c);
 }
 
-// (b_r, b_c) <- A^-1 (b_r, b_c) with A = M (mode 0), M + J^T D J over the rows flagged in c.mask (mode 1),
-// M + h diag(damping) (mode 2).  The whole factorisation lives in registers: chain Cholesky, Y = L^-1 B, the lane's
-// share of the Schur complement, one 28-value reduction across the quad, root Cholesky (replicated), solve.
+// V <- sign * A^-1 V with A = M (mode 0), M + J^T D J over the rows flagged in st.mask (mode 1), M + h diag(damping)
+// (mode 2).  The whole factorisation lives in registers: chain Cholesky, Y = L^-1 B, the lane's share of the Schur
+// complement, one 28-value reduction across the quad, root Cholesky (replicated), solve.
 template <class Q>
-FT_QN void quad_factor_solve(const Q& qd, const QCar& c, int mode, double* br, double* bc) {
+FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, int mode, QVec V, double sign) {
     const int w = qd.lane();
     double W[21], B[NC][NR], Pp[28];
 #pragma unroll
@@ -261,49 +290,53 @@ FT_QN void quad_factor_solve(const Q& qd, const QCar& c, int mode, double* br, d
         W[tri(2, 2)] += TIMESTEP * 0.01;
         if (w == 0) Pp[tri(6, 6)] += TIMESTEP * 0.1;
     } else if (mode == 1) {
-        const QRows& r = c.r; const unsigned mask = c.mask;
-        if (r.eq_D > 0) { W[tri(1, 1)] += r.eq_D; B[1][6] -= r.eq_D * r.eq_der; Pp[tri(6, 6)] += r.eq_D * r.eq_der * r.eq_der; }
+        const unsigned mask = st.mask;
+        { const double D = qd.P(QP_EQ), der = qd.P(QP_EQ + 2); W[tri(1, 1)] += D; B[1][6] -= D * der; Pp[tri(6, 6)] += D * der * der; }
 #pragma unroll
-        for (int l = 0; l < NC; l++) if (mask >> (QB_FR + l) & 1u) W[tri(l, l)] += r.fr_D[l];
-        if (mask >> QB_FR6 & 1u) Pp[tri(6, 6)] += r.fr6_D;
+        for (int l = 0; l < NC; l++) if (mask >> (QB_FR + l) & 1u) W[tri(l, l)] += qd.K(3 * (6 * w + l));
 #pragma unroll
-        for (int k = 0; k < 2; k++) if (mask >> (QB_LIM + k) & 1u) W[tri(k, k)] += r.lim_D[k];
-        if (mask >> QB_LIM6 & 1u) Pp[tri(6, 6)] += r.lim6_D;
+        for (int k = 0; k < 2; k++) if (mask >> (QB_LIM + k) & 1u) W[tri(k, k)] += qd.P(QP_LIM + k);
+        if (mask >> QB_FR6 & 1u) Pp[tri(6, 6)] += qd.K(72);
+        if (mask >> QB_LIM6 & 1u) Pp[tri(6, 6)] += qd.C(QC_R6 + 1);
         if (mask >> QB_WC & 0xFu) {
-            double J[3][9];
-            wc_jac(qd, J);
-            const double D = r.wc_D;
+            // the active pyramid rows n +- mu t1, n +- mu t2 sum to J^T K J with a 3x3 K in the contact frame
+            const double D = qd.P(QP_WC);
+            const double a0 = (mask >> QB_WC & 1u) ? 1.0 : 0.0, a1 = (mask >> (QB_WC + 1) & 1u) ? 1.0 : 0.0,
+                         a2 = (mask >> (QB_WC + 2) & 1u) ? 1.0 : 0.0, a3 = (mask >> (QB_WC + 3) & 1u) ? 1.0 : 0.0;
+            const double k00 = D * (a0 + a1 + a2 + a3), k01 = D * WC_MU * (a0 - a1), k02 = D * WC_MU * (a2 - a3),
+                         k11 = D * WC_MU * WC_MU * (a0 + a1), k22 = D * WC_MU * WC_MU * (a2 + a3);
+            double J[3][9], T[3][9];
+            J[0][0] = 0; J[0][1] = 0; J[0][2] = 1; J[1][0] = 0; J[1][1] = 1; J[1][2] = 0; J[2][0] = -1; J[2][1] = 0; J[2][2] = 0;
 #pragma unroll
-            for (int rr = 0; rr < 4; rr++) {
-                if (!(mask >> (QB_WC + rr) & 1u)) continue;
-                const double sg = (rr & 1) ? -WC_MU : WC_MU; const int ta = 1 + (rr >> 1);
-                double Jr[9];
+            for (int a = 0; a < 3; a++)
 #pragma unroll
-                for (int col = 0; col < 9; col++) Jr[col] = J[0][col] + sg * J[ta][col];
+                for (int k = 0; k < 6; k++) J[a][3 + k] = qd.P(QP_CJ + 6 * a + k);
 #pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    const double di = D * Jr[i];
+            for (int col = 0; col < 9; col++) {
+                T[0][col] = k00 * J[0][col] + k01 * J[1][col] + k02 * J[2][col];
+                T[1][col] = k01 * J[0][col] + k11 * J[1][col];
+                T[2][col] = k02 * J[0][col] + k22 * J[2][col];
+            }
 #pragma unroll
-                    for (int j = 0; j <= i; j++) Pp[tri(i, j)] += di * Jr[j];
-                }
+            for (int i = 0; i < 6; i++)
 #pragma unroll
-                for (int l = 0; l < 3; l++) {
-                    const double dl = D * Jr[6 + l];
+                for (int j = 0; j <= i; j++) Pp[tri(i, j)] += J[0][i] * T[0][j] + J[1][i] * T[1][j] + J[2][i] * T[2][j];
 #pragma unroll
-                    for (int k = 0; k <= l; k++) W[tri(l, k)] += dl * Jr[6 + k];
+            for (int l = 0; l < 3; l++) {
 #pragma unroll
-                    for (int j = 0; j < 6; j++) B[l][j] += dl * Jr[j];
-                }
+                for (int k = 0; k <= l; k++) W[tri(l, k)] += J[0][6 + l] * T[0][6 + k] + J[1][6 + l] * T[1][6 + k] + J[2][6 + l] * T[2][6 + k];
+#pragma unroll
+                for (int j = 0; j < 6; j++) B[l][j] += J[0][6 + l] * T[0][j] + J[1][6 + l] * T[1][j] + J[2][6 + l] * T[2][j];
             }
         }
-        for (int s = 0; s < r.nch; s++) {
-            const double D = r.ch_D[s];
+        for (int s = 0; s < st.nch; s++) {
+            const double D = ch.D[s];
             for (int rr = 0; rr < 4; rr++) {
                 if (!(mask >> (QB_CH + 4 * s + rr) & 1u)) continue;
                 const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
                 double Jr[6];
 #pragma unroll
-                for (int col = 0; col < 6; col++) Jr[col] = r.ch_J[s][0][col] + sg * r.ch_J[s][ta][col];
+                for (int col = 0; col < 6; col++) Jr[col] = ch.J[s][0][col] + sg * ch.J[s][ta][col];
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
                     const double di = D * Jr[i];
@@ -341,7 +374,7 @@ FT_QN void quad_factor_solve(const Q& qd, const QCar& c, int mode, double* br, d
             for (int k = 0; k < l; k++) s -= W[tri(l, k)] * B[k][col];
             B[l][col] = s * W[tri(l, l)];
         }
-        double s = bc[l];
+        double s = qd.P(V.p + l);
 #pragma unroll
         for (int k = 0; k < l; k++) s -= W[tri(l, k)] * z[k];
         z[l] = s * W[tri(l, l)];
@@ -360,7 +393,7 @@ FT_QN void quad_factor_solve(const Q& qd, const QCar& c, int mode, double* br, d
         double s = 0;
 #pragma unroll
         for (int l = 0; l < NC; l++) s += B[l][i] * z[l];
-        xr[i] = br[i] - qd.sum(s);
+        xr[i] = qd.C(V.c + i) - qd.sum(s);
     }
     // root block (replicated in the four lanes)
 #pragma unroll
@@ -380,73 +413,94 @@ FT_QN void quad_factor_solve(const Q& qd, const QCar& c, int mode, double* br, d
         }
     }
 #pragma unroll
-    for (int i = 0; i < NR; i++) { double s = xr[i]; for (int k = 0; k < i; k++) s -= R[tri(i, k)] * xr[k]; xr[i] = s * R[tri(i, i)]; }
+    for (int i = 0; i < NR; i++) {
+        double s = xr[i];
 #pragma unroll
-    for (int i = NR - 1; i >= 0; i--) { double s = xr[i]; for (int k = i + 1; k < NR; k++) s -= R[tri(k, i)] * xr[k]; xr[i] = s * R[tri(i, i)]; }
+        for (int k = 0; k < i; k++) s -= R[tri(i, k)] * xr[k];
+        xr[i] = s * R[tri(i, i)];
+    }
+#pragma unroll
+    for (int i = NR - 1; i >= 0; i--) {
+        double s = xr[i];
+#pragma unroll
+        for (int k = i + 1; k < NR; k++) s -= R[tri(k, i)] * xr[k];
+        xr[i] = s * R[tri(i, i)];
+    }
     // back substitution of the chain: x_c = L^-T (z - Y x_r)
 #pragma unroll
-    for (int l = 0; l < NC; l++) { double s = 0; for (int j = 0; j < NR; j++) s += B[l][j] * xr[j]; z[l] -= s; }
+    for (int l = 0; l < NC; l++) {
+        double s = 0;
 #pragma unroll
-    for (int l = NC - 1; l >= 0; l--) { double s = z[l]; for (int k = l + 1; k < NC; k++) s -= W[tri(k, l)] * z[k]; z[l] = s * W[tri(l, l)]; }
+        for (int j = 0; j < NR; j++) s += B[l][j] * xr[j];
+        z[l] -= s;
+    }
 #pragma unroll
-    for (int i = 0; i < NR; i++) br[i] = xr[i];
+    for (int l = NC - 1; l >= 0; l--) {
+        double s = z[l];
 #pragma unroll
-    for (int l = 0; l < NC; l++) bc[l] = z[l];
+        for (int k = l + 1; k < NC; k++) s -= W[tri(k, l)] * z[k];
+        z[l] = s * W[tri(l, l)];
+    }
+#pragma unroll
+    for (int i = 0; i < NR; i++) xr[i] *= sign;
+#pragma unroll
+    for (int l = 0; l < NC; l++) z[l] *= sign;
+    qd.sync();                        // (the reductions above already follow every lane's reads of V's root part)
+    vec_store(qd, V, xr, z);
 }
 
 // ---- exact line search (PrimalSearch) ---------------------------------------------------------------------------
-struct QLs { double qg0, qg1, qg2; double wdx[3], wds[3], cdx[QMAXCH][3], cds[QMAXCH][3]; };
+struct QLs { double qg0, qg1, qg2; };
 
 template <class Q>
-FT_QN void quad_ls_eval(const Q& qd, const QCar& c, const QLs& L, LsPoint& pt, double alpha) {
-    const QRows& r = c.r;
+FT_QN void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, const QLs& L, LsPoint& pt, double alpha) {
+    const int w = qd.lane();
     double q0 = 0, q1 = 0, q2 = 0;
-    if (r.eq_D > 0) {
-        const double jar = c.x_c[1] - r.eq_der * c.x_r[6] - r.eq_aref, jv = c.s_c[1] - r.eq_der * c.s_r[6], D = r.eq_D;
-        q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv;
-    }
+    const double x6 = qd.C(VX.c + 6), s6 = qd.C(VS.c + 6);
 #pragma unroll
     for (int l = 0; l < NC; l++) {
-        const double f = r.fr_f[l];
-        if (f <= 0) continue;
-        const double jar = c.x_c[l] - r.fr_aref[l], jv = c.s_c[l], Rf = r.fr_Rf[l], D = r.fr_D[l];
-        const double xx = jar + alpha * jv;
-        if (xx <= -Rf) { q0 += f * (-0.5 * Rf - jar); q1 += -f * jv; }
-        else if (xx >= Rf) { q0 += f * (-0.5 * Rf + jar); q1 += f * jv; }
-        else { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
+        const double D = qd.K(3 * (6 * w + l)), Rf = qd.K(3 * (6 * w + l) + 1), f = qd.K(3 * (6 * w + l) + 2);
+        const double jar = qd.P(VX.p + l) - qd.P(QP_FRA + l), jv = qd.P(VS.p + l), xx = jar + alpha * jv;
+        const bool lo = xx <= -Rf, hi = xx >= Rf, lin = lo || hi;
+        const double sj = lo ? -1.0 : 1.0;
+        q0 += lin ? f * (-0.5 * Rf + sj * jar) : 0.5 * D * jar * jar;
+        q1 += lin ? sj * f * jv : D * jar * jv;
+        q2 += lin ? 0.0 : 0.5 * D * jv * jv;
+        if (l == 1) {                                                    // equality row of the front steering slot
+            const double De = qd.P(QP_EQ), der = qd.P(QP_EQ + 2);
+            const double je = qd.P(VX.p + 1) - der * x6 - qd.P(QP_EQ + 1), ve = jv - der * s6;
+            q0 += 0.5 * De * je * je; q1 += De * je * ve; q2 += 0.5 * De * ve * ve;
+        }
+        if (l < 2) {                                                     // limit row of slots 0, 1
+            const double Dl = qd.P(QP_LIM + l), sg = qd.P(QP_LIM + 4 + l);
+            const double jl = sg * qd.P(VX.p + l) - qd.P(QP_LIM + 2 + l), vl = sg * jv;
+            if (Dl > 0 && jl + alpha * vl < 0) { q0 += 0.5 * Dl * jl * jl; q1 += Dl * jl * vl; q2 += 0.5 * Dl * vl * vl; }
+        }
     }
-    if (r.fr6_f > 0) {
-        const double f = r.fr6_f, jar = c.x_r[6] - r.fr6_aref, jv = c.s_r[6], Rf = r.fr6_Rf, D = r.fr6_D;
-        const double xx = jar + alpha * jv;
-        if (xx <= -Rf) { q0 += f * (-0.5 * Rf - jar); q1 += -f * jv; }
-        else if (xx >= Rf) { q0 += f * (-0.5 * Rf + jar); q1 += f * jv; }
-        else { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
+    if (w == 0) {
+        const double D = qd.K(72), Rf = qd.K(73), f = qd.K(74), jar = x6 - qd.C(QC_R6), jv = s6, xx = jar + alpha * jv;
+        const bool lo = xx <= -Rf, hi = xx >= Rf, lin = lo || hi;
+        const double sj = lo ? -1.0 : 1.0;
+        q0 += lin ? f * (-0.5 * Rf + sj * jar) : 0.5 * D * jar * jar;
+        q1 += lin ? sj * f * jv : D * jar * jv;
+        q2 += lin ? 0.0 : 0.5 * D * jv * jv;
+        const double D6 = qd.C(QC_R6 + 1), sg = qd.C(QC_R6 + 3), j6 = sg * x6 - qd.C(QC_R6 + 2), v6 = sg * s6;
+        if (D6 > 0 && j6 + alpha * v6 < 0) { q0 += 0.5 * D6 * j6 * j6; q1 += D6 * j6 * v6; q2 += 0.5 * D6 * v6 * v6; }
     }
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const double sg = r.lim_sign[k];
-        if (sg == 0) continue;
-        const double jar = sg * c.x_c[k] - r.lim_aref[k], jv = sg * c.s_c[k], D = r.lim_D[k];
-        if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
-    }
-    if (r.lim6_sign != 0) {
-        const double sg = r.lim6_sign, jar = sg * c.x_r[6] - r.lim6_aref, jv = sg * c.s_r[6], D = r.lim6_D;
-        if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
-    }
-    if (r.wc_D > 0) {
-        const double D = r.wc_D;
+    const double Dw = qd.P(QP_WC);
+    if (Dw > 0) {
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
             const double sg = (rr & 1) ? -WC_MU : WC_MU; const int ta = 1 + (rr >> 1);
-            const double jar = L.wdx[0] + sg * L.wdx[ta] - r.wc_aref[rr], jv = L.wds[0] + sg * L.wds[ta];
-            if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
+            const double jar = qd.P(QP_WD) + sg * qd.P(QP_WD + ta) - qd.P(QP_WC + 1 + rr), jv = qd.P(QP_WD + 3) + sg * qd.P(QP_WD + 3 + ta);
+            if (jar + alpha * jv < 0) { q0 += 0.5 * Dw * jar * jar; q1 += Dw * jar * jv; q2 += 0.5 * Dw * jv * jv; }
         }
     }
-    for (int s = 0; s < r.nch; s++) {
-        const double D = r.ch_D[s];
+    for (int s = 0; s < nch; s++) {
+        const double D = ch.D[s];
         for (int rr = 0; rr < 4; rr++) {
             const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-            const double jar = L.cdx[s][0] + sg * L.cdx[s][ta] - r.ch_aref[s][rr], jv = L.cds[s][0] + sg * L.cds[s][ta];
+            const double jar = ch.dx[s][0] + sg * ch.dx[s][ta] - ch.aref[s][rr], jv = ch.ds[s][0] + sg * ch.ds[s][ta];
             if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
         }
     }
@@ -457,35 +511,43 @@ FT_QN void quad_ls_eval(const Q& qd, const QCar& c, const QLs& L, LsPoint& pt, d
 }
 
 template <class Q>
-FT_QN double quad_line_search(const Q& qd, QCar& c, double scale) {
-    double sn = 0;
-#pragma unroll
-    for (int l = 0; l < NC; l++) sn += c.s_c[l] * c.s_c[l];
-    sn = qd.sum(sn);
-#pragma unroll
-    for (int i = 0; i < NR; i++) sn += c.s_r[i] * c.s_r[i];
-    const double snorm = sqrt(sn);
-    if (snorm < MINVAL) return 0;
-    quad_mul(qd, c.s_r, c.s_c, c.Mv_r, c.Mv_c);
+FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, double scale) {
     QLs L;
-    double g1 = 0, g2 = 0;
+    double snorm;
+    {
+        double sr[NR], sc[NC], xr[NR], xc[NC];
+        vec_load(qd, VS, sr, sc);
+        double sn = 0;
 #pragma unroll
-    for (int l = 0; l < NC; l++) { g1 += c.s_c[l] * (c.Ma_c[l] - c.qfs_c[l]); g2 += 0.5 * c.s_c[l] * c.Mv_c[l]; }
-    g1 = qd.sum(g1); g2 = qd.sum(g2);
+        for (int l = 0; l < NC; l++) sn += sc[l] * sc[l];
+        sn = qd.sum(sn);
 #pragma unroll
-    for (int i = 0; i < NR; i++) { g1 += c.s_r[i] * (c.Ma_r[i] - c.qfs_r[i]); g2 += 0.5 * c.s_r[i] * c.Mv_r[i]; }
-    L.qg0 = c.gauss; L.qg1 = g1; L.qg2 = g2;
-    if (c.r.wc_D > 0) {
-        double J[3][9];
-        wc_jac(qd, J);
-        wc_dots(J, c.x_r, c.x_c, L.wdx); wc_dots(J, c.s_r, c.s_c, L.wds);
+        for (int i = 0; i < NR; i++) sn += sr[i] * sr[i];
+        snorm = sqrt(sn);
+        if (snorm < MINVAL) return 0;
+        quad_mul(qd, VS, VMV);
+        double g1 = 0, g2 = 0;
+#pragma unroll
+        for (int l = 0; l < NC; l++) { g1 += sc[l] * (qd.P(VMA.p + l) - qd.P(VQFS.p + l)); g2 += 0.5 * sc[l] * qd.P(VMV.p + l); }
+        g1 = qd.sum(g1); g2 = qd.sum(g2);
+#pragma unroll
+        for (int i = 0; i < NR; i++) { g1 += sr[i] * (qd.C(VMA.c + i) - qd.C(VQFS.c + i)); g2 += 0.5 * sr[i] * qd.C(VMV.c + i); }
+        L.qg0 = st.gauss; L.qg1 = g1; L.qg2 = g2;
+        vec_load(qd, VX, xr, xc);
+        if (qd.P(QP_WC) > 0) {
+            double d3[3];
+            wc_dots(qd, xr, xc, d3); for (int a = 0; a < 3; a++) qd.P(QP_WD + a) = d3[a];
+            wc_dots(qd, sr, sc, d3); for (int a = 0; a < 3; a++) qd.P(QP_WD + 3 + a) = d3[a];
+        }
+        for (int s = 0; s < st.nch; s++)
+            for (int a = 0; a < 3; a++) { ch.dx[s][a] = dot6q(ch.J[s][a], xr); ch.ds[s][a] = dot6q(ch.J[s][a], sr); }
     }
-    for (int s = 0; s < c.r.nch; s++) { ch_dots(c.r.ch_J[s], c.x_r, L.cdx[s]); ch_dots(c.r.ch_J[s], c.s_r, L.cds[s]); }
+    const int nch = st.nch;
     const double gtol = SOLVER_TOL * LS_TOL * snorm / scale;
     LsPoint p0, p1, p2, pm, a1, a2;
     int it = 0;
-    quad_ls_eval(qd, c, L, p0, 0);
-    quad_ls_eval(qd, c, L, p1, p0.alpha - p0.d0 / p0.d1);
+    quad_ls_eval(qd, ch, nch, L, p0, 0);
+    quad_ls_eval(qd, ch, nch, L, p1, p0.alpha - p0.d0 / p0.d1);
     if (p0.cost < p1.cost) p1 = p0;
     if (fabs(p1.d0) < gtol) return p1.alpha;
     const double dir = p1.d0 < 0 ? 1.0 : -1.0;
@@ -493,14 +555,14 @@ FT_QN double quad_line_search(const Q& qd, QCar& c, double scale) {
     p2 = p1;
     while (p1.d0 * dir <= -gtol && it < LS_ITER) {
         p2 = p1; p2update = true;
-        quad_ls_eval(qd, c, L, p1, p1.alpha - p1.d0 / p1.d1); it++;
+        quad_ls_eval(qd, ch, nch, L, p1, p1.alpha - p1.d0 / p1.d1); it++;
         if (fabs(p1.d0) < gtol) return p1.alpha;
     }
     if (it >= LS_ITER || !p2update) return p1.alpha;
     while (it < LS_ITER) {
-        quad_ls_eval(qd, c, L, pm, 0.5 * (p1.alpha + p2.alpha)); it++;
-        quad_ls_eval(qd, c, L, a1, p1.alpha - p1.d0 / p1.d1);
-        quad_ls_eval(qd, c, L, a2, p2.alpha - p2.d0 / p2.d1);
+        quad_ls_eval(qd, ch, nch, L, pm, 0.5 * (p1.alpha + p2.alpha)); it++;
+        quad_ls_eval(qd, ch, nch, L, a1, p1.alpha - p1.d0 / p1.d1);
+        quad_ls_eval(qd, ch, nch, L, a2, p2.alpha - p2.d0 / p2.d1);
         if (fabs(a1.d0) < gtol) return a1.alpha;
         if (fabs(a2.d0) < gtol) return a2.alpha;
         if (fabs(pm.d0) < gtol) return pm.alpha;
@@ -526,10 +588,10 @@ struct QNoWalls {                    // open ground
 
 template <class Q, class WallFn>
 FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, const double* qc, const double* vr, const double* vc,
-                        const double* ctrl, const WallFn& walls, QCar& c, StepInfo& info) {
+                        const double* ctrl, const WallFn& walls, QChassis& ch, QState& st, StepInfo& info) {
     const int w = qd.lane();
     const bool fr = front(w);
-    qd.sync();                       // the quad is done with the previous step's shared M
+    qd.sync();                       // the quad is done with the previous step's shared slots
     // ---- kinematics (root replicated, own wheel chain)
     double q1[4] = {qr[3], qr[4], qr[5], qr[6]}, R1[9];
     quat_norm(q1); quat2mat(R1, q1);
@@ -589,10 +651,10 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
         for (int a = 0; a < 10; a++) { crbw[a] = cinw[a] + cins[a]; crb1[a] = cin1[a] + cinsw[a] + qd.sum(crbw[a]); }
         for (int i = 0; i < 6; i++) {
             inert_mul(buf, crb1, cdr[i]);
-            for (int j = 0; j <= i; j++) { const double s = dot6q(cdr[j], buf); if (((tri(i, j)) & 3) == w) qd.C(QC_MR + tri(i, j)) = s; }
+            for (int j = 0; j <= i; j++) { const double s = dot6q(cdr[j], buf); qd.C(QC_MR + tri(i, j)) = s; }
         }
         inert_mul(buf, cinsw, cdr[6]);
-        for (int j = 0; j <= 6; j++) { double s = dot6q(cdr[j], buf); if (j == 6) s += dof_armature(6); if (((tri(6, j)) & 3) == w) qd.C(QC_MR + tri(6, j)) = s; }
+        for (int j = 0; j <= 6; j++) { double s = dot6q(cdr[j], buf); if (j == 6) s += dof_armature(6); qd.C(QC_MR + tri(6, j)) = s; }
         for (int l = 0; l < NC; l++) {
             inert_mul(buf, l < 3 ? crbw : cins, cd[l]);
             for (int kk = 0; kk <= l; kk++) {
@@ -650,58 +712,55 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
         for (int l = 0; l < NC; l++) bias_c[l] = dot6q(cd[l], l < 3 ? fw : fs);
         for (int i = 0; i < 6; i++) bias_r[i] = dot6q(cdr[i], cfrc1);
     }
-    for (int i = 0; i < NR; i++) c.qfs_r[i] = -bias_r[i] - dof_damping(i) * vr[i];
-    for (int l = 0; l < NC; l++) c.qfs_c[l] = -bias_c[l] - dof_damping(NR + l) * vc[l];
-    c.qfs_c[0] += -500.0 * (qc[0] - (-0.015));                                            // suspension spring :63
-    if (!fr) c.qfs_c[1] = 0;
     {
-        c.qfs_r[6] += 20.0 * ctrl[1] - 20.0 * qr[7];                                      // <position kp=20> :179
+        double fs_r[NR], fs_c[NC];
+        for (int i = 0; i < NR; i++) fs_r[i] = -bias_r[i] - dof_damping(i) * vr[i];
+        for (int l = 0; l < NC; l++) fs_c[l] = -bias_c[l] - dof_damping(NR + l) * vc[l];
+        fs_c[0] += -500.0 * (qc[0] - (-0.015));                                           // suspension spring :63
+        if (!fr) fs_c[1] = 0;
+        fs_r[6] += 20.0 * ctrl[1] - 20.0 * qr[7];                                         // <position kp=20> :179
         const double tv = qd.sum(0.25 * vc[2]);
         double f = 100.0 * ctrl[0] - 100.0 * (0.04 * tv);                                 // <velocity kv=100 gear=0.04> :180
         f = f > 500.0 ? 500.0 : (f < -500.0 ? -500.0 : f);
-        c.qfs_c[2] += 0.04 * 0.25 * f;
+        fs_c[2] += 0.04 * 0.25 * f;
+        vec_store(qd, VQFS, fs_r, fs_c);
+        vec_store(qd, VQAS, fs_r, fs_c);             // right-hand side of qacc_smooth = M^-1 qfrc_smooth
     }
     // ---- rows
-    QRows& r = c.r;
     double K, B, imp, R;
-    for (int l = 0; l < NC; l++) {
-        const double f = (l == 1 && !fr) ? 0.0 : dof_floss(NR + l);
-        r.fr_f[l] = f; r.fr_D[l] = 0; r.fr_Rf[l] = 0; r.fr_aref[l] = 0;
-        if (f <= 0) continue;
-        kbi(0.9, 0.0, mc.dof_invweight0[NR + NC * w + l], K, B, imp, R);
-        r.fr_D[l] = 1 / R; r.fr_Rf[l] = R * f; r.fr_aref[l] = -B * vc[l];
-    }
-    r.fr6_f = 0; r.fr6_D = 0; r.fr6_Rf = 0; r.fr6_aref = 0;
-    r.lim6_sign = 0; r.lim6_D = 0; r.lim6_aref = 0;
-    if (w == 0) {
-        kbi(0.9, 0.0, mc.dof_invweight0[6], K, B, imp, R);
-        r.fr6_f = dof_floss(6); r.fr6_D = 1 / R; r.fr6_Rf = R * r.fr6_f; r.fr6_aref = -B * vr[6];
+    for (int l = 0; l < NC; l++) qd.P(QP_FRA + l) = -REF_B * vc[l];
+    {
+        double a6 = -REF_B * vr[6], D6 = 0, r6 = 0, s6 = 0;
         const double q = qr[7];
         double dist = 0, sign = 0;
         if (q + 1 < 0) { dist = q + 1; sign = 1; } else if (1 - q < 0) { dist = 1 - q; sign = -1; }
         if (sign != 0) {
             kbi(0.9, dist, mc.dof_invweight0[6], K, B, imp, R);
-            r.lim6_sign = sign; r.lim6_D = 1 / R; r.lim6_aref = -B * (sign * vr[6]) - K * imp * dist;
+            s6 = sign; D6 = 1 / R; r6 = -B * (sign * vr[6]) - K * imp * dist;
         }
+        qd.C(QC_R6) = a6; qd.C(QC_R6 + 1) = D6; qd.C(QC_R6 + 2) = r6; qd.C(QC_R6 + 3) = s6;
     }
-    r.eq_D = 0; r.eq_aref = 0; r.eq_der = 0;
-    if (fr) {
-        const double x = qr[7], pos = qc[1] - poly_val(w, x), der = poly_der(w, x);
-        kbi(0.9, pos, mc.dof_invweight0[NR + NC * w + 1] + mc.dof_invweight0[6], K, B, imp, R);
-        r.eq_der = der; r.eq_D = 1 / R; r.eq_aref = -B * (vc[1] - der * vr[6]) - K * imp * pos;
+    {
+        double D = 0, aref = 0, der = 0;
+        if (fr) {
+            const double x = qr[7], pos = qc[1] - poly_val(w, x);
+            der = poly_der(w, x);
+            kbi(0.9, pos, mc.dof_invweight0[NR + NC * w + 1] + mc.dof_invweight0[6], K, B, imp, R);
+            D = 1 / R; aref = -B * (vc[1] - der * vr[6]) - K * imp * pos;
+        }
+        qd.P(QP_EQ) = D; qd.P(QP_EQ + 1) = aref; qd.P(QP_EQ + 2) = der;
     }
     for (int k = 0; k < 2; k++) {
-        r.lim_sign[k] = 0; r.lim_D[k] = 0; r.lim_aref[k] = 0;
-        if (k == 1 && !fr) continue;
+        double D = 0, aref = 0, sign = 0, dist = 0;
         const double q = qc[k], lo = k == 0 ? -0.03 : -1.0, hi = k == 0 ? 0.0 : 1.0;
-        double dist, sign;
-        if (q - lo < 0) { dist = q - lo; sign = 1; } else if (hi - q < 0) { dist = hi - q; sign = -1; } else continue;
-        kbi(0.9, dist, mc.dof_invweight0[NR + NC * w + k], K, B, imp, R);
-        r.lim_sign[k] = sign; r.lim_D[k] = 1 / R; r.lim_aref[k] = -B * (sign * vc[k]) - K * imp * dist;
+        if (!(k == 1 && !fr)) { if (q - lo < 0) { dist = q - lo; sign = 1; } else if (hi - q < 0) { dist = hi - q; sign = -1; } }
+        if (sign != 0) {
+            kbi(0.9, dist, mc.dof_invweight0[NR + NC * w + k], K, B, imp, R);
+            D = 1 / R; aref = -B * (sign * vc[k]) - K * imp * dist;
+        }
+        qd.P(QP_LIM + k) = D; qd.P(QP_LIM + 2 + k) = aref; qd.P(QP_LIM + 4 + k) = sign;
     }
     // ---- wheel ellipsoid vs ground plane
-    r.wc_D = 0;
-    for (int rr = 0; rr < 4; rr++) r.wc_aref[rr] = 0;
     {
         const double dl[3] = {-Rw[6], -Rw[7], -Rw[8]};
         double s[3] = {WS0 * dl[0], WS1 * dl[1], WS2 * dl[2]};
@@ -712,6 +771,7 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
         for (int a = 0; a < 3; a++) sw[a] += pw[a];
         const double dist = sw[2] - PLANE_Z;
         const bool on = !(dist > 0);
+        double Dw = 0;
         if (on) {
             const double o[3] = {sw[0] - com[0], sw[1] - com[1], sw[2] - 0.5 * dist - com[2]};
             double vel[3] = {vr[2], vr[1], -vr[0]};                       // translation columns of the frame
@@ -726,17 +786,18 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
             }
             kbi(0.45, dist, mc.wheel_invweight0[w], K, B, imp, R);
             double Rpy = 2 * WC_MU * WC_MU * R; if (Rpy < MINVAL) Rpy = MINVAL;
-            r.wc_D = 1 / Rpy;
+            Dw = 1 / Rpy;
             for (int rr = 0; rr < 4; rr++) {
                 const double sg = (rr & 1) ? -1.0 : 1.0;
-                r.wc_aref[rr] = -B * (vel[0] + sg * WC_MU * vel[1 + (rr >> 1)]) - K * imp * dist;
+                qd.P(QP_WC + 1 + rr) = -B * (vel[0] + sg * WC_MU * vel[1 + (rr >> 1)]) - K * imp * dist;
             }
         }
+        qd.P(QP_WC) = Dw;
         info.ncon_wheel = popc4(qd.ballot(on));
     }
     // ---- chassis hull vertices vs walls: hit i (in vertex order, capped like the thread-per-car version) goes to
     // lane i & 3, slot i >> 2
-    r.nch = 0;
+    st.nch = 0;
     info.ncon_wall = 0;
     if (walls.enabled()) {
         unsigned hits = 0;
@@ -754,7 +815,7 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
                 if ((rank & 3) == w) {
                     QWallHit h;
                     walls(R1, p1, v, h);
-                    const int s = r.nch++;
+                    const int s = st.nch++;
                     double o[3], vel[3] = {0, 0, 0};
                     for (int a = 0; a < 3; a++) o[a] = h.pnt[a] - com[a];
                     for (int col = 0; col < 6; col++) {
@@ -762,15 +823,15 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
                         cross3(jp, cdr[col], o);
                         for (int a = 0; a < 3; a++) jp[a] += cdr[col][3 + a];
                         const double j0 = dot3(h.nrm, jp), j1 = dot3(h.t1, jp), j2 = dot3(h.t2, jp);
-                        r.ch_J[s][0][col] = j0; r.ch_J[s][1][col] = j1; r.ch_J[s][2][col] = j2;
+                        ch.J[s][0][col] = j0; ch.J[s][1][col] = j1; ch.J[s][2][col] = j2;
                         vel[0] += j0 * vr[col]; vel[1] += j1 * vr[col]; vel[2] += j2 * vr[col];
                     }
                     kbi(0.9, h.dist, mc.chassis_invweight0, K, B, imp, R);
                     double Rpy = 2 * CH_MU * CH_MU * R; if (Rpy < MINVAL) Rpy = MINVAL;
-                    r.ch_D[s] = 1 / Rpy;
+                    ch.D[s] = 1 / Rpy;
                     for (int rr = 0; rr < 4; rr++) {
                         const double sg = (rr & 1) ? -1.0 : 1.0;
-                        r.ch_aref[s][rr] = -B * (vel[0] + sg * CH_MU * vel[1 + (rr >> 1)]) - K * imp * h.dist;
+                        ch.aref[s][rr] = -B * (vel[0] + sg * CH_MU * vel[1 + (rr >> 1)]) - K * imp * h.dist;
                     }
                 }
                 rank++;
@@ -778,116 +839,131 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
             info.ncon_wall = rank;
         }
     }
-    qd.sync();                       // M (shared part) visible to the quad
+    qd.sync();                       // per-car slots visible to the quad
+}
+
+// state of the lane: root (replicated) + own chain in slot order (susp, steer, throttle, ball)
+FT_HD void quad_load(int w, const double* qpos, const double* qvel, double* qr, double* qc, double* vr, double* vc) {
+    const int qa = chain_q(w), da = chain_d(w);
+    for (int i = 0; i < 8; i++) qr[i] = qpos[i];
+    for (int i = 0; i < NR; i++) vr[i] = qvel[i];
+    if (front(w)) {
+        for (int i = 0; i < 7; i++) qc[i] = qpos[qa + i];
+        for (int l = 0; l < NC; l++) vc[l] = qvel[da + l];
+    } else {
+        qc[0] = qpos[qa]; qc[1] = 0; for (int i = 2; i < 7; i++) qc[i] = qpos[qa + i - 1];
+        vc[0] = qvel[da]; vc[1] = 0; for (int l = 2; l < NC; l++) vc[l] = qvel[da + l - 1];
+    }
+}
+FT_HD void quad_store_chain(int w, double* dst, const double* c, int base) {   // 6 chain slots -> dof addresses (rear: no steering dof)
+    if (front(w)) { for (int l = 0; l < NC; l++) dst[base + l] = c[l]; }
+    else { dst[base] = c[0]; for (int l = 2; l < NC; l++) dst[base + l - 1] = c[l]; }
 }
 
 // ---- the step -----------------------------------------------------------------------------------------------------
 template <class Q, class WallFn>
 FT_HDN void step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, double* qvel, double* warm, const double* ctrl,
-                          const WallFn& walls, bool live, StepInfo& info) {
+                          const WallFn& walls, StepInfo& info) {
     const int w = qd.lane();
     const bool fr = front(w);
     const int qa = chain_q(w), da = chain_d(w);
-    // ---- state of the lane: root (replicated) + own chain in slot order (susp, steer, throttle, ball)
-    double qr[8], qc[7], vr[NR], vc[NC], wr[NR], wc[NC];
-    for (int i = 0; i < 8; i++) qr[i] = qpos[i];
-    for (int i = 0; i < NR; i++) { vr[i] = qvel[i]; wr[i] = warm[i]; }
-    if (fr) {
-        for (int i = 0; i < 7; i++) qc[i] = qpos[qa + i];
-        for (int l = 0; l < NC; l++) { vc[l] = qvel[da + l]; wc[l] = warm[da + l]; }
-    } else {
-        qc[0] = qpos[qa]; qc[1] = 0; for (int i = 2; i < 7; i++) qc[i] = qpos[qa + i - 1];
-        vc[0] = qvel[da]; vc[1] = 0; wc[0] = warm[da]; wc[1] = 0;
-        for (int l = 2; l < NC; l++) { vc[l] = qvel[da + l - 1]; wc[l] = warm[da + l - 1]; }
-    }
+    QChassis ch;
+    QState st;
     info.reset = 0; info.iters = 0;
+    qd.sync();                                                             // previous step's root state is in memory
     {
+        double qr[8], qc[7], vr[NR], vc[NC];
+        quad_load(w, qpos, qvel, qr, qc, vr, vc);
         bool bad = false;                                                  // mj_checkPos / mj_checkVel
         for (int i = 0; i < 8; i++) bad |= bad_value(qr[i]);
         for (int i = 0; i < 7; i++) bad |= bad_value(qc[i]);
         for (int i = 0; i < NR; i++) bad |= bad_value(vr[i]);
         for (int l = 0; l < NC; l++) bad |= bad_value(vc[l]);
-        if (qd.any(bad)) {
+        if (qd.any(bad)) {                                                 // mj_resetData, then the step goes on from qpos0
             info.reset = 1;
             for (int i = 0; i < 8; i++) qr[i] = 0;
             qr[1] = 2.0; qr[3] = 1.0;
             for (int i = 0; i < 7; i++) qc[i] = 0;
             qc[3] = 1.0;
-            for (int i = 0; i < NR; i++) { vr[i] = 0; wr[i] = 0; }
-            for (int l = 0; l < NC; l++) { vc[l] = 0; wc[l] = 0; }
+            for (int i = 0; i < NR; i++) vr[i] = 0;
+            for (int l = 0; l < NC; l++) vc[l] = 0;
+            qd.sync();
+            if (w == 0) { for (int i = 0; i < 8; i++) qpos[i] = qr[i]; for (int i = 0; i < NR; i++) { qvel[i] = 0; warm[i] = 0; } }
+            const int nq = fr ? 7 : 6, nd = fr ? 6 : 5;
+            for (int i = 0; i < nq; i++) qpos[qa + i] = (i == nq - 4) ? 1.0 : 0.0;
+            for (int i = 0; i < nd; i++) { qvel[da + i] = 0; warm[da + i] = 0; }
+            qd.sync();
         }
+        quad_prepare(qd, mc, qr, qc, vr, vc, ctrl, walls, ch, st, info);
     }
-    QCar c;
-    quad_prepare(qd, mc, qr, qc, vr, vc, ctrl, walls, c, info);
-    // ---- qacc_smooth = M^-1 qfrc_smooth
-    for (int i = 0; i < NR; i++) c.qas_r[i] = c.qfs_r[i];
-    for (int l = 0; l < NC; l++) c.qas_c[l] = c.qfs_c[l];
-    int mode = 0;
     const double scale = 1.0 / (mc.meaninertia * NV);
     // one copy of the factor/solve code serves qacc_smooth (mode 0), every Newton direction (1) and the
     // implicit-damping Euler update (2)
-    double* br = c.qas_r; double* bc = c.qas_c;
-    double qa_r[NR], qa_c[NC];
+    int mode = 0;
     for (;;) {
-        quad_factor_solve(qd, c, mode, br, bc);
+        quad_factor_solve(qd, ch, st, mode, mode == 0 ? VQAS : VS, mode == 1 ? -1.0 : 1.0);
         if (mode == 2) break;
         bool done = false;
         if (mode == 0) {
             // warm start if its cost beats qacc_smooth's (mj_fwdConstraint)
-            double fr_[NR], fc_[NC]; unsigned m_;
-            quad_mul(qd, wr, wc, c.Ma_r, c.Ma_c);
-            double cw = qd.sum(rows_eval(qd, c.r, wr, wc, fr_, fc_, m_)), gw = 0;
-            for (int l = 0; l < NC; l++) gw += 0.5 * (c.Ma_c[l] - c.qfs_c[l]) * (wc[l] - c.qas_c[l]);
-            gw = qd.sum(gw);
-            for (int i = 0; i < NR; i++) gw += 0.5 * (c.Ma_r[i] - c.qfs_r[i]) * (wr[i] - c.qas_r[i]);
-            cw += gw;
-            const double cs = qd.sum(rows_eval(qd, c.r, c.qas_r, c.qas_c, fr_, fc_, m_));
-            if (cw > cs) {
-                for (int i = 0; i < NR; i++) { c.x_r[i] = c.qas_r[i]; c.Ma_r[i] = c.qfs_r[i]; }
-                for (int l = 0; l < NC; l++) { c.x_c[l] = c.qas_c[l]; c.Ma_c[l] = c.qfs_c[l]; }
-            } else {
-                for (int i = 0; i < NR; i++) c.x_r[i] = wr[i];
-                for (int l = 0; l < NC; l++) c.x_c[l] = wc[l];
+            {
+                double wr[NR], wc[NC] = {0, 0, 0, 0, 0, 0};
+                for (int i = 0; i < NR; i++) wr[i] = warm[i];
+                if (fr) { for (int l = 0; l < NC; l++) wc[l] = warm[da + l]; }
+                else { wc[0] = warm[da]; for (int l = 2; l < NC; l++) wc[l] = warm[da + l - 1]; }
+                if (info.reset) { for (int i = 0; i < NR; i++) wr[i] = 0; for (int l = 0; l < NC; l++) wc[l] = 0; }
+                qd.sync();
+                vec_store(qd, VX, wr, wc);
             }
-            quad_evaluate(qd, c);
+            quad_mul(qd, VX, VMA);
+            quad_evaluate(qd, ch, st);
+            double fr_[NR], fc_[NC]; unsigned m_;
+            const double cs = qd.sum(rows_eval(qd, ch, st.nch, VQAS, fr_, fc_, m_));
+            if (st.cost > cs) {
+                double r[NR], c[NC];
+                vec_load(qd, VQAS, r, c); qd.sync(); vec_store(qd, VX, r, c);
+                vec_load(qd, VQFS, r, c); qd.sync(); vec_store(qd, VMA, r, c);
+                quad_evaluate(qd, ch, st);
+            }
             mode = 1;
         } else {
-            for (int i = 0; i < NR; i++) c.s_r[i] = -c.s_r[i];
-            for (int l = 0; l < NC; l++) c.s_c[l] = -c.s_c[l];
-            const double alpha = quad_line_search(qd, c, scale);
-            if (alpha == 0) done = true;
+            const double alpha = quad_line_search(qd, ch, st, scale);
+            if (alpha == 0) { quad_evaluate(qd, ch, st); done = true; }      // the gradient goes back into S
             else {
-                for (int i = 0; i < NR; i++) { c.x_r[i] += alpha * c.s_r[i]; c.Ma_r[i] += alpha * c.Mv_r[i]; }
-                for (int l = 0; l < NC; l++) { c.x_c[l] += alpha * c.s_c[l]; c.Ma_c[l] += alpha * c.Mv_c[l]; }
-                const double oldcost = c.cost;
-                quad_evaluate(qd, c);
+                double xr[NR], xc[NC], mr[NR], mcn[NC];
+                for (int i = 0; i < NR; i++) { xr[i] = qd.C(VX.c + i) + alpha * qd.C(VS.c + i); mr[i] = qd.C(VMA.c + i) + alpha * qd.C(VMV.c + i); }
+                for (int l = 0; l < NC; l++) { xc[l] = qd.P(VX.p + l) + alpha * qd.P(VS.p + l); mcn[l] = qd.P(VMA.p + l) + alpha * qd.P(VMV.p + l); }
+                qd.sync();
+                vec_store(qd, VX, xr, xc); vec_store(qd, VMA, mr, mcn);
+                const double oldcost = st.cost;
+                quad_evaluate(qd, ch, st);
                 double gn = 0;
-                for (int l = 0; l < NC; l++) gn += c.g_c[l] * c.g_c[l];
+                for (int l = 0; l < NC; l++) gn += qd.P(VS.p + l) * qd.P(VS.p + l);
                 gn = qd.sum(gn);
-                for (int i = 0; i < NR; i++) gn += c.g_r[i] * c.g_r[i];
+                for (int i = 0; i < NR; i++) gn += qd.C(VS.c + i) * qd.C(VS.c + i);
                 info.iters++;
-                if (scale * (oldcost - c.cost) < SOLVER_TOL || scale * sqrt(gn) < SOLVER_TOL || info.iters >= SOLVER_ITER) done = true;
+                if (scale * (oldcost - st.cost) < SOLVER_TOL || scale * sqrt(gn) < SOLVER_TOL || info.iters >= SOLVER_ITER) done = true;
             }
         }
         if (done) {
-            // mj_Euler with implicit joint damping: (M + h diag(b)) qacc' = qfrc_smooth + qfrc_constraint
+            // mj_Euler with implicit joint damping: (M + h diag(b)) qacc' = qfrc_smooth + qfrc_constraint = M a - grad
+            double r[NR], c[NC];
+            for (int i = 0; i < NR; i++) r[i] = qd.C(VMA.c + i) - qd.C(VS.c + i);
+            for (int l = 0; l < NC; l++) c[l] = qd.P(VMA.p + l) - qd.P(VS.p + l);
+            qd.sync();
+            vec_store(qd, VS, r, c);
             mode = 2;
-            for (int i = 0; i < NR; i++) qa_r[i] = c.qfs_r[i] + c.fc_r[i];
-            for (int l = 0; l < NC; l++) qa_c[l] = c.qfs_c[l] + c.fc_c[l];
-            br = qa_r; bc = qa_c;
-        } else {
-            for (int i = 0; i < NR; i++) c.s_r[i] = c.g_r[i];
-            for (int l = 0; l < NC; l++) c.s_c[l] = c.g_c[l];
-            br = c.s_r; bc = c.s_c;
         }
     }
+    double xr[NR], xc[NC], ar[NR], ac[NC];
+    vec_load(qd, VX, xr, xc);
+    vec_load(qd, VS, ar, ac);
     {
         bool bad = false;                                                  // mj_checkAcc
-        for (int i = 0; i < NR; i++) bad |= bad_value(c.x_r[i]);
-        for (int l = 0; l < NC; l++) bad |= bad_value(c.x_c[l]);
+        for (int i = 0; i < NR; i++) bad |= bad_value(xr[i]);
+        for (int l = 0; l < NC; l++) bad |= bad_value(xc[l]);
         if (qd.any(bad)) {
             info.reset = 1;
-            if (!live) return;
             if (w == 0) { for (int i = 0; i < 8; i++) qpos[i] = (i == 1) ? 2.0 : (i == 3 ? 1.0 : 0.0); for (int i = 0; i < NR; i++) { qvel[i] = 0; warm[i] = 0; } }
             const int nq = fr ? 7 : 6, nd = fr ? 6 : 5;
             for (int i = 0; i < nq; i++) qpos[qa + i] = (i == nq - 4) ? 1.0 : 0.0;
@@ -895,27 +971,25 @@ FT_HDN void step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, doub
             return;
         }
     }
-    if (!live) return;
-    // ---- velocity, then mj_integratePos with the new velocity
-    for (int i = 0; i < NR; i++) vr[i] += TIMESTEP * qa_r[i];
-    for (int l = 0; l < NC; l++) vc[l] += TIMESTEP * qa_c[l];
+    // ---- velocity, then mj_integratePos with the new velocity (state re-read: it was not kept across the solver)
+    double qr[8], qc[7], vr[NR], vc[NC];
+    quad_load(w, qpos, qvel, qr, qc, vr, vc);
+    qd.sync();                                                             // every lane has re-read the root state
+    for (int i = 0; i < NR; i++) vr[i] += TIMESTEP * ar[i];
+    for (int l = 0; l < NC; l++) vc[l] += TIMESTEP * ac[l];
     if (w == 0) {
         for (int a = 0; a < 3; a++) qr[a] += TIMESTEP * vr[a];
         quat_integrate(qr + 3, vr + 3, TIMESTEP);
         qr[7] += TIMESTEP * vr[6];
         for (int i = 0; i < 8; i++) qpos[i] = qr[i];
-        for (int i = 0; i < NR; i++) { qvel[i] = vr[i]; warm[i] = c.x_r[i]; }
+        for (int i = 0; i < NR; i++) { qvel[i] = vr[i]; warm[i] = xr[i]; }
     }
     for (int l = 0; l < 3; l++) qc[l] += TIMESTEP * vc[l];
     quat_integrate(qc + 3, vc + 3, TIMESTEP);
-    if (fr) {
-        for (int i = 0; i < 7; i++) qpos[qa + i] = qc[i];
-        for (int l = 0; l < NC; l++) { qvel[da + l] = vc[l]; warm[da + l] = c.x_c[l]; }
-    } else {
-        qpos[qa] = qc[0]; for (int i = 2; i < 7; i++) qpos[qa + i - 1] = qc[i];
-        qvel[da] = vc[0]; warm[da] = c.x_c[0];
-        for (int l = 2; l < NC; l++) { qvel[da + l - 1] = vc[l]; warm[da + l - 1] = c.x_c[l]; }
-    }
+    if (fr) { for (int i = 0; i < 7; i++) qpos[qa + i] = qc[i]; }
+    else { qpos[qa] = qc[0]; for (int i = 2; i < 7; i++) qpos[qa + i - 1] = qc[i]; }
+    quad_store_chain(w, qvel, vc, da);
+    quad_store_chain(w, warm, xc, da);
 }
 
 }  // namespace mushr

@@ -182,21 +182,25 @@ struct WallsQuad {                              // quad-per-car flavour: probe o
 };
 
 // Quad-per-car: four lanes (one per wheel chain) advance one car, 8 cars per warp; see mushr_step_quad.cuh.
-// Shared memory: [slot][thread] for the lane-private slots, then [slot][car] for the per-car slots.
+// Shared memory: [slot][thread] for the lane-private slots, [slot][car] for the per-car slots, then the table of
+// friction-loss row constants.  1 250 B per lane: five 32-thread CTAs (40 cars) per SM.
+template <int NT> constexpr size_t quad_smem_bytes() { return (size_t)(NT * QP_N + NT / 4 * QC_N + QK_N + 1) * sizeof(double); }
+
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
                  double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
                  const int32_t* __restrict__ lap, const int32_t* __restrict__ perm, int64_t ncars, int nsteps,
                  int32_t* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    double* sm = reinterpret_cast<double*>(smraw);
     const int tid = threadIdx.x, cib = tid >> 2;
+    constexpr int KO = NT * QP_N + NT / 4 * QC_N;
+    for (int g = tid; g < 25; g += NT) quad_const_entry(c_model, g, quad_sm + KO);
+    __syncthreads();
     int64_t car = (int64_t)blockIdx.x * (NT / 4) + cib;
-    if (car >= ncars) return;                       // whole quads leave together: nothing in this kernel spans quads
+    if (car >= ncars) return;                       // whole quads leave together: nothing below spans quads
     if (perm) car = perm[car];                      // cars grouped by their last Newton iteration count
     QuadDev<NT, NT / 4> qd;
-    qd.w = tid & 3; qd.priv = sm + tid; qd.shr = sm + QP_N * NT + cib; qd.mask = 0xFu << (tid & 28);
+    qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.mask = 0xFu << (tid & 28);
     WallsQuad walls{nullptr, nullptr};
     const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
     if (blob && !shadowed) {
@@ -208,7 +212,7 @@ step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
     int st = 0;
     for (int s = 0; s < nsteps; s++) {
         StepInfo info;
-        step_car_quad(qd, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, true, info);
+        step_car_quad(qd, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, info);
         st = (info.iters & 0xFF) | (info.reset ? 0x100 : (st & 0x100)) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24);
     }
     if (status && qd.w == 0) status[car] = st;
@@ -285,24 +289,22 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     if (impl < 0) { const char* e = getenv("FTGP_STEP_IMPL"); impl = !e ? 2 : (e[0] == 'w' ? 0 : (e[0] == 't' ? 1 : 2)); }
     const uint32_t* blob = g ? g->d_blob : nullptr;
     if (impl == 2) {
-        static int qt = 0, minb = 0;
-        if (!qt) {
-            const char* e = getenv("FTGP_STEP_QT"); qt = e ? atoi(e) : 64; if (qt != 32 && qt != 64 && qt != 128) qt = 64;
-            const char* m = getenv("FTGP_STEP_MINB"); minb = m ? atoi(m) : 0;
-        }
+        static int qt = 0;
+        if (!qt) { const char* e = getenv("FTGP_STEP_QT"); qt = e ? atoi(e) : 160; if (qt != 32 && qt != 64 && qt != 128 && qt != 160) qt = 160; }
         const int32_t* perm = nullptr;
         if ((rc = order_cars(status, ncars, dev, stream, &perm))) return rc;
-        const size_t smem = (size_t)qt * (QP_N + QC_N / 4) * sizeof(double);
-        auto launch = [&](auto kern) -> int {
+        auto launch = [&](auto kern, size_t smem) -> int {
             FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             kern<<<(unsigned)((ncars + qt / 4 - 1) / (qt / 4)), qt, smem, stream>>>(
                 blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status);
             return FTGP_OK;
         };
         int rc2;
-        if (qt == 32) rc2 = minb == 1 ? launch(step_quad_kernel<32, 8>) : launch(step_quad_kernel<32, 1>);
-        else if (qt == 128) rc2 = minb == 1 ? launch(step_quad_kernel<128, 2>) : launch(step_quad_kernel<128, 1>);
-        else rc2 = minb == 1 ? launch(step_quad_kernel<64, 4>) : launch(step_quad_kernel<64, 1>);
+        if (qt == 32) rc2 = launch(step_quad_kernel<32, 5>, quad_smem_bytes<32>());
+        else if (qt == 64) rc2 = launch(step_quad_kernel<64, 2>, quad_smem_bytes<64>());
+        else if (qt == 160) rc2 = launch(step_quad_kernel<160, 1>, quad_smem_bytes<160>());
+        else rc2 = launch(step_quad_kernel<128, 1>, quad_smem_bytes<128>());
         if (rc2) return rc2;
     } else if (impl == 1) {
         static int threads = 0;

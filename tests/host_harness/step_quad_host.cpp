@@ -20,7 +20,7 @@ struct SpinBarrier {
 struct QuadHostShared {
     SpinBarrier bar;
     double slot[4]; unsigned bits[4];
-    double priv[QP_N * 4]; double shr[QC_N];
+    double priv[QP_N * 4]; double shr[QC_N]; double ktab[QK_N];
 };
 struct QuadHost : QuadMem<4, 1> {
     QuadHostShared* s;
@@ -45,14 +45,15 @@ static bool g_ready = false;
 extern "C" int hq_step(double* qpos, double* qvel, double* warm, const double* ctrl, long n, int nsteps, int* info4) {
     if (!g_ready) { g_mc = model_constants(); g_ready = true; }
     QuadHostShared sh;
+    for (int g = 0; g < 25; g++) quad_const_entry(g_mc, g, sh.ktab);
     std::vector<std::thread> th;
     for (int w = 0; w < 4; w++)
         th.emplace_back([&, w]() {
-            QuadHost q; q.s = &sh; q.w = w; q.priv = sh.priv + w; q.shr = sh.shr;
+            QuadHost q; q.s = &sh; q.w = w; q.priv = sh.priv + w; q.shr = sh.shr; q.ktab = sh.ktab;
             for (long i = 0; i < n; i++)
                 for (int k = 0; k < nsteps; k++) {
                     StepInfo si;
-                    step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), true, si);
+                    step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), si);
                     q.sync();
                     if (info4 && w == 0) { info4[4 * i] = si.iters; info4[4 * i + 1] = si.ncon_wheel; info4[4 * i + 2] = si.ncon_wall; info4[4 * i + 3] = si.reset; }
                 }
