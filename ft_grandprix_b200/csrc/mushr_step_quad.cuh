@@ -18,6 +18,11 @@
 // memory: lane-private slots in [slot][thread] layout (conflict-free), root parts of the dof vectors and the root
 // block of M once per car in [slot][car] layout (the four lanes read them as a broadcast).  1 250 B per lane, so
 // 160 lanes (40 cars) are resident per SM; the factorisation itself runs entirely in registers.
+// Control flow is WARP-UNIFORM (and CTA-uniform at the Newton loop head): every lane of a warp reaches every
+// collective in the same order, so the quad reductions are plain full-mask shuffles and the warps of a CTA walk the
+// same code at the same time (one instruction-cache fill serves all of them).  A quad whose car has converged keeps
+// going through the motions with its stores switched off until the last car of its CTA is done; the exact line
+// search is a per-quad state machine clocked by one warp-uniform cost evaluation per tick.
 // Rule for the per-car slots: every lane computes the same value and every lane writes it, always after a quad
 // sync that follows the last read of the old value (read phase, sync, write phase).
 //
@@ -77,19 +82,22 @@ extern __shared__ __align__(16) double quad_sm[];      // the kernel's dynamic s
 template <int PS_, int CS_>
 struct QuadDev {                     // po / co / ko: offsets (in doubles) of the lane's, the car's and the table's first slot
     static constexpr int PS = PS_, CS = CS_;
-    int po, co, ko, w; unsigned mask;
+    int po, co, ko, w, qs;           // qs: position of the quad in the warp (lane & 28)
     __device__ __forceinline__ double& P(int i) const { return quad_sm[po + i * PS]; }
     __device__ __forceinline__ double& C(int i) const { return quad_sm[co + i * CS]; }
     __device__ __forceinline__ double K(int i) const { return quad_sm[ko + i]; }
     __device__ __forceinline__ int lane() const { return w; }
+    // collectives: called by all 32 lanes of the warp together (cany: by the whole CTA)
     __device__ __forceinline__ double sum(double v) const {
-        v += __shfl_xor_sync(mask, v, 1);
-        v += __shfl_xor_sync(mask, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
         return v;
     }
-    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(mask, p) >> (__ffs(mask) - 1)) & 0xFu; }
-    __device__ __forceinline__ bool any(bool p) const { return __any_sync(mask, p) != 0; }
-    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+    __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(0xffffffffu, p) >> qs) & 0xFu; }
+    __device__ __forceinline__ bool any(bool p) const { return ballot(p) != 0; }
+    __device__ __forceinline__ bool wany(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
+    __device__ __forceinline__ bool cany(bool p) const { return __syncthreads_or(p) != 0; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 #endif
 
@@ -118,7 +126,8 @@ template <class Q> FT_HD void vec_load(const Q& qd, QVec v, double* r, double* c
 #pragma unroll
     for (int l = 0; l < NC; l++) c[l] = qd.P(v.p + l);
 }
-template <class Q> FT_HD void vec_store(const Q& qd, QVec v, const double* r, const double* c) {   // caller has synced
+template <class Q> FT_HD void vec_store(const Q& qd, QVec v, const double* r, const double* c, bool on = true) {   // caller has synced
+    if (!on) return;
 #pragma unroll
     for (int i = 0; i < NR; i++) qd.C(v.c + i) = r[i];
 #pragma unroll
@@ -215,7 +224,7 @@ FT_QN double rows_eval(const Q& qd, const QChassis& ch, int nch, QVec X, double*
 
 // Y = M X with M in shared memory
 template <class Q>
-FT_QN void quad_mul(const Q& qd, QVec X, QVec Y) {
+FT_QN void quad_mul(const Q& qd, QVec X, QVec Y, bool on) {
     double xr[NR], xc[NC], yr[NR], yc[NC], part[6];
     vec_load(qd, X, xr, xc);
 #pragma unroll
@@ -238,16 +247,15 @@ FT_QN void quad_mul(const Q& qd, QVec X, QVec Y) {
         yr[i] = s;
     }
     qd.sync();
-    vec_store(qd, Y, yr, yc);
+    vec_store(qd, Y, yr, yc, on);
 }
 
 // cost, Gauss term and gradient (into S) at X (needs MA = M X)
 template <class Q>
-FT_QN void quad_evaluate(const Q& qd, const QChassis& ch, QState& st) {
+FT_QN void quad_evaluate(const Q& qd, const QChassis& ch, QState& st, bool on) {
     double fr[NR], fc[NC], g_r[NR], g_c[NC];
     unsigned mask;
     double cc = rows_eval(qd, ch, st.nch, VX, fr, fc, mask);
-    st.mask = mask;
     double g = 0;
 #pragma unroll
     for (int l = 0; l < NC; l++) {
@@ -262,16 +270,16 @@ FT_QN void quad_evaluate(const Q& qd, const QChassis& ch, QState& st) {
         g += d * (qd.C(VX.c + i) - qd.C(VQAS.c + i));
         g_r[i] = d - qd.sum(fr[i]);
     }
-    st.gauss = 0.5 * g; st.cost = cc + st.gauss;
+    if (on) { st.mask = mask; st.gauss = 0.5 * g; st.cost = cc + st.gauss; }
     qd.sync();
-    vec_store(qd, VS, g_r, g_c);
+    vec_store(qd, VS, g_r, g_c, on);
 }
 
 // V <- sign * A^-1 V with A = M (mode 0), M + J^T D J over the rows flagged in st.mask (mode 1), M + h diag(damping)
 // (mode 2).  The whole factorisation lives in registers: chain Cholesky, Y = L^-1 B, the lane's share of the Schur
 // complement, one 28-value reduction across the quad, root Cholesky (replicated), solve.
 template <class Q>
-FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, int mode, QVec V, double sign) {
+FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, int mode, QVec V, double sign, bool on) {
     const int w = qd.lane();
     double W[21], B[NC][NR], Pp[28];
 #pragma unroll
@@ -446,7 +454,7 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
 #pragma unroll
     for (int l = 0; l < NC; l++) z[l] *= sign;
     qd.sync();                        // (the reductions above already follow every lane's reads of V's root part)
-    vec_store(qd, V, xr, z);
+    vec_store(qd, V, xr, z, on);
 }
 
 // ---- exact line search (PrimalSearch) ---------------------------------------------------------------------------
@@ -510,8 +518,10 @@ FT_QN void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, const QLs& L, 
     if (pt.d1 <= 0) pt.d1 = MINVAL;
 }
 
+// MuJoCo's PrimalSearch as a state machine: every tick of the warp-uniform loop evaluates the cost once, at the
+// point each quad asked for, then each quad moves on by itself (no collectives in the transitions).
 template <class Q>
-FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, double scale) {
+FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, double scale, bool on) {
     QLs L;
     double snorm;
     {
@@ -524,8 +534,7 @@ FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, doubl
 #pragma unroll
         for (int i = 0; i < NR; i++) sn += sr[i] * sr[i];
         snorm = sqrt(sn);
-        if (snorm < MINVAL) return 0;
-        quad_mul(qd, VS, VMV);
+        quad_mul(qd, VS, VMV, on);
         double g1 = 0, g2 = 0;
 #pragma unroll
         for (int l = 0; l < NC; l++) { g1 += sc[l] * (qd.P(VMA.p + l) - qd.P(VQFS.p + l)); g2 += 0.5 * sc[l] * qd.P(VMV.p + l); }
@@ -544,39 +553,68 @@ FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, doubl
     }
     const int nch = st.nch;
     const double gtol = SOLVER_TOL * LS_TOL * snorm / scale;
-    LsPoint p0, p1, p2, pm, a1, a2;
-    int it = 0;
-    quad_ls_eval(qd, ch, nch, L, p0, 0);
-    quad_ls_eval(qd, ch, nch, L, p1, p0.alpha - p0.d0 / p0.d1);
-    if (p0.cost < p1.cost) p1 = p0;
-    if (fabs(p1.d0) < gtol) return p1.alpha;
-    const double dir = p1.d0 < 0 ? 1.0 : -1.0;
+    enum { S_P0, S_P1, S_NEWTON, S_MID, S_A1, S_A2, S_DONE };
+    int state = (on && snorm >= MINVAL) ? S_P0 : S_DONE, it = 0;
+    double alpha = 0, res = 0, dir = 1;
     bool p2update = false;
-    p2 = p1;
-    while (p1.d0 * dir <= -gtol && it < LS_ITER) {
-        p2 = p1; p2update = true;
-        quad_ls_eval(qd, ch, nch, L, p1, p1.alpha - p1.d0 / p1.d1); it++;
-        if (fabs(p1.d0) < gtol) return p1.alpha;
-    }
-    if (it >= LS_ITER || !p2update) return p1.alpha;
-    while (it < LS_ITER) {
-        quad_ls_eval(qd, ch, nch, L, pm, 0.5 * (p1.alpha + p2.alpha)); it++;
-        quad_ls_eval(qd, ch, nch, L, a1, p1.alpha - p1.d0 / p1.d1);
-        quad_ls_eval(qd, ch, nch, L, a2, p2.alpha - p2.d0 / p2.d1);
-        if (fabs(a1.d0) < gtol) return a1.alpha;
-        if (fabs(a2.d0) < gtol) return a2.alpha;
-        if (fabs(pm.d0) < gtol) return pm.alpha;
-        bool b1 = false, b2 = false;
-        double lo = fmin(p1.alpha, p2.alpha), hi = fmax(p1.alpha, p2.alpha);
-        for (int cnd = 0; cnd < 3; cnd++) {
-            const LsPoint& q = cnd == 0 ? a1 : (cnd == 1 ? a2 : pm);
-            if (q.alpha <= lo || q.alpha >= hi) continue;
-            if ((q.d0 < 0) == (p1.d0 < 0)) { p1 = q; b1 = true; } else { p2 = q; b2 = true; }
-            lo = fmin(p1.alpha, p2.alpha); hi = fmax(p1.alpha, p2.alpha);
+    LsPoint p0, p1, p2, pm, a1, pt;
+    p0.alpha = p0.cost = p0.d0 = 0; p0.d1 = 1; p1 = p0; p2 = p0; pm = p0; a1 = p0;
+    while (qd.wany(state != S_DONE)) {
+        quad_ls_eval(qd, ch, nch, L, pt, alpha);
+        bool loop1 = false, loop2 = false;
+        switch (state) {
+        case S_P0:
+            p0 = pt; alpha = p0.alpha - p0.d0 / p0.d1; state = S_P1;
+            break;
+        case S_P1:
+            p1 = pt;
+            if (p0.cost < p1.cost) p1 = p0;
+            if (fabs(p1.d0) < gtol) { res = p1.alpha; state = S_DONE; break; }
+            dir = p1.d0 < 0 ? 1.0 : -1.0;
+            p2 = p1;
+            loop1 = true;
+            break;
+        case S_NEWTON:
+            p1 = pt; it++;
+            if (fabs(p1.d0) < gtol) { res = p1.alpha; state = S_DONE; break; }
+            loop1 = true;
+            break;
+        case S_MID:
+            pm = pt; it++; alpha = p1.alpha - p1.d0 / p1.d1; state = S_A1;
+            break;
+        case S_A1:
+            a1 = pt; alpha = p2.alpha - p2.d0 / p2.d1; state = S_A2;
+            break;
+        case S_A2: {
+            const LsPoint a2 = pt;
+            if (fabs(a1.d0) < gtol) { res = a1.alpha; state = S_DONE; break; }
+            if (fabs(a2.d0) < gtol) { res = a2.alpha; state = S_DONE; break; }
+            if (fabs(pm.d0) < gtol) { res = pm.alpha; state = S_DONE; break; }
+            bool b1 = false, b2 = false;
+            double lo = fmin(p1.alpha, p2.alpha), hi = fmax(p1.alpha, p2.alpha);
+            for (int cnd = 0; cnd < 3; cnd++) {
+                const LsPoint q = cnd == 0 ? a1 : (cnd == 1 ? a2 : pm);
+                if (q.alpha <= lo || q.alpha >= hi) continue;
+                if ((q.d0 < 0) == (p1.d0 < 0)) { p1 = q; b1 = true; } else { p2 = q; b2 = true; }
+                lo = fmin(p1.alpha, p2.alpha); hi = fmax(p1.alpha, p2.alpha);
+            }
+            if (!b1 && !b2) { res = p1.cost <= p2.cost ? p1.alpha : p2.alpha; state = S_DONE; break; }
+            loop2 = true;
+            break;
         }
-        if (!b1 && !b2) break;
+        default: break;
+        }
+        if (loop1) {                 // while (p1.d0 * dir <= -gtol && it < LS_ITER) { p2 = p1; p1 = newton step from p1 }
+            if (p1.d0 * dir <= -gtol && it < LS_ITER) { p2 = p1; p2update = true; alpha = p1.alpha - p1.d0 / p1.d1; state = S_NEWTON; }
+            else if (it >= LS_ITER || !p2update) { res = p1.alpha; state = S_DONE; }
+            else loop2 = true;
+        }
+        if (loop2) {                 // bracketing: midpoint and the two Newton steps
+            if (it < LS_ITER) { alpha = 0.5 * (p1.alpha + p2.alpha); state = S_MID; }
+            else { res = p1.cost <= p2.cost ? p1.alpha : p2.alpha; state = S_DONE; }
+        }
     }
-    return p1.cost <= p2.cost ? p1.alpha : p2.alpha;
+    return res;
 }
 
 // ---- position + velocity stage of the lane: kinematics, M -> shared memory, bias, smooth force, contacts, rows ----
@@ -799,12 +837,12 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
     // lane i & 3, slot i >> 2
     st.nch = 0;
     info.ncon_wall = 0;
-    if (walls.enabled()) {
+    if (qd.wany(walls.enabled())) {
         unsigned hits = 0;
         for (int k = 0; k < 3; k++) {
             const int v = 4 * k + w;
             QWallHit h;
-            const bool hit = v < MUSHR_CHASSIS_NHULL && walls(R1, p1, v, h);
+            const bool hit = walls.enabled() && v < MUSHR_CHASSIS_NHULL && walls(R1, p1, v, h);
             hits |= qd.ballot(hit) << (4 * k);
         }
         if (hits) {
@@ -861,14 +899,17 @@ FT_HD void quad_store_chain(int w, double* dst, const double* c, int base) {   /
 }
 
 // ---- the step -----------------------------------------------------------------------------------------------------
+// live = false: a padding quad (it re-does the last car so that it can take part in the collectives, and stores
+// nothing to global memory)
 template <class Q, class WallFn>
 FT_HDN void step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, double* qvel, double* warm, const double* ctrl,
-                          const WallFn& walls, StepInfo& info) {
+                          const WallFn& walls, bool live, StepInfo& info) {
     const int w = qd.lane();
     const bool fr = front(w);
     const int qa = chain_q(w), da = chain_d(w);
     QChassis ch;
     QState st;
+    st.cost = 0; st.gauss = 0; st.mask = 0;
     info.reset = 0; info.iters = 0;
     qd.sync();                                                             // previous step's root state is in memory
     {
@@ -879,7 +920,9 @@ FT_HDN void step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, doub
         for (int i = 0; i < 7; i++) bad |= bad_value(qc[i]);
         for (int i = 0; i < NR; i++) bad |= bad_value(vr[i]);
         for (int l = 0; l < NC; l++) bad |= bad_value(vc[l]);
-        if (qd.any(bad)) {                                                 // mj_resetData, then the step goes on from qpos0
+        bad = qd.any(bad);
+        qd.sync();                                                         // every lane has read the root state
+        if (bad) {                                                         // mj_resetData, then the step goes on from qpos0
             info.reset = 1;
             for (int i = 0; i < 8; i++) qr[i] = 0;
             qr[1] = 2.0; qr[3] = 1.0;
@@ -887,24 +930,27 @@ FT_HDN void step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, doub
             qc[3] = 1.0;
             for (int i = 0; i < NR; i++) vr[i] = 0;
             for (int l = 0; l < NC; l++) vc[l] = 0;
-            qd.sync();
-            if (w == 0) { for (int i = 0; i < 8; i++) qpos[i] = qr[i]; for (int i = 0; i < NR; i++) { qvel[i] = 0; warm[i] = 0; } }
-            const int nq = fr ? 7 : 6, nd = fr ? 6 : 5;
-            for (int i = 0; i < nq; i++) qpos[qa + i] = (i == nq - 4) ? 1.0 : 0.0;
-            for (int i = 0; i < nd; i++) { qvel[da + i] = 0; warm[da + i] = 0; }
-            qd.sync();
+            if (live) {
+                if (w == 0) { for (int i = 0; i < 8; i++) qpos[i] = qr[i]; for (int i = 0; i < NR; i++) { qvel[i] = 0; warm[i] = 0; } }
+                const int nq = fr ? 7 : 6, nd = fr ? 6 : 5;
+                for (int i = 0; i < nq; i++) qpos[qa + i] = (i == nq - 4) ? 1.0 : 0.0;
+                for (int i = 0; i < nd; i++) { qvel[da + i] = 0; warm[da + i] = 0; }
+            }
         }
         quad_prepare(qd, mc, qr, qc, vr, vc, ctrl, walls, ch, st, info);
     }
     const double scale = 1.0 / (mc.meaninertia * NV);
-    // one copy of the factor/solve code serves qacc_smooth (mode 0), every Newton direction (1) and the
-    // implicit-damping Euler update (2)
+    // One copy of the factor/solve code serves qacc_smooth (mode 0), every Newton direction (1) and the
+    // implicit-damping Euler update (2); mode 3 = finished, waiting for the rest of the CTA.
     int mode = 0;
+    bool first = true;
     for (;;) {
-        quad_factor_solve(qd, ch, st, mode, mode == 0 ? VQAS : VS, mode == 1 ? -1.0 : 1.0);
-        if (mode == 2) break;
-        bool done = false;
-        if (mode == 0) {
+        quad_factor_solve(qd, ch, st, mode == 3 ? 2 : mode, mode == 0 ? VQAS : VS, mode == 1 ? -1.0 : 1.0, mode < 3);
+        if (mode == 2) mode = 3;
+        if (!first && !qd.cany(mode == 1)) break;
+        bool upd = false;
+        const bool was_first = first;
+        if (first) {
             // warm start if its cost beats qacc_smooth's (mj_fwdConstraint)
             {
                 double wr[NR], wc[NC] = {0, 0, 0, 0, 0, 0};
@@ -915,66 +961,73 @@ FT_HDN void step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, doub
                 qd.sync();
                 vec_store(qd, VX, wr, wc);
             }
-            quad_mul(qd, VX, VMA);
-            quad_evaluate(qd, ch, st);
+            quad_mul(qd, VX, VMA, true);
             double fr_[NR], fc_[NC]; unsigned m_;
+            double cw = rows_eval(qd, ch, st.nch, VX, fr_, fc_, m_), gw = 0;
+            for (int l = 0; l < NC; l++) gw += (qd.P(VMA.p + l) - qd.P(VQFS.p + l)) * (qd.P(VX.p + l) - qd.P(VQAS.p + l));
+            cw = qd.sum(cw); gw = qd.sum(gw);
+            for (int i = 0; i < NR; i++) gw += (qd.C(VMA.c + i) - qd.C(VQFS.c + i)) * (qd.C(VX.c + i) - qd.C(VQAS.c + i));
+            cw += 0.5 * gw;
             const double cs = qd.sum(rows_eval(qd, ch, st.nch, VQAS, fr_, fc_, m_));
-            if (st.cost > cs) {
-                double r[NR], c[NC];
-                vec_load(qd, VQAS, r, c); qd.sync(); vec_store(qd, VX, r, c);
-                vec_load(qd, VQFS, r, c); qd.sync(); vec_store(qd, VMA, r, c);
-                quad_evaluate(qd, ch, st);
-            }
-            mode = 1;
+            double r[NR], c[NC], r2[NR], c2[NC];
+            vec_load(qd, VQAS, r, c); vec_load(qd, VQFS, r2, c2);
+            qd.sync();
+            vec_store(qd, VX, r, c, cw > cs); vec_store(qd, VMA, r2, c2, cw > cs);
+            mode = live ? 1 : 3; first = false;
         } else {
-            const double alpha = quad_line_search(qd, ch, st, scale);
-            if (alpha == 0) { quad_evaluate(qd, ch, st); done = true; }      // the gradient goes back into S
-            else {
-                double xr[NR], xc[NC], mr[NR], mcn[NC];
-                for (int i = 0; i < NR; i++) { xr[i] = qd.C(VX.c + i) + alpha * qd.C(VS.c + i); mr[i] = qd.C(VMA.c + i) + alpha * qd.C(VMV.c + i); }
-                for (int l = 0; l < NC; l++) { xc[l] = qd.P(VX.p + l) + alpha * qd.P(VS.p + l); mcn[l] = qd.P(VMA.p + l) + alpha * qd.P(VMV.p + l); }
-                qd.sync();
-                vec_store(qd, VX, xr, xc); vec_store(qd, VMA, mr, mcn);
-                const double oldcost = st.cost;
-                quad_evaluate(qd, ch, st);
-                double gn = 0;
-                for (int l = 0; l < NC; l++) gn += qd.P(VS.p + l) * qd.P(VS.p + l);
-                gn = qd.sum(gn);
-                for (int i = 0; i < NR; i++) gn += qd.C(VS.c + i) * qd.C(VS.c + i);
-                info.iters++;
-                if (scale * (oldcost - st.cost) < SOLVER_TOL || scale * sqrt(gn) < SOLVER_TOL || info.iters >= SOLVER_ITER) done = true;
-            }
+            const double alpha = quad_line_search(qd, ch, st, scale, mode == 1);
+            double xr[NR], xc[NC], mr[NR], mcn[NC];
+            for (int i = 0; i < NR; i++) { xr[i] = qd.C(VX.c + i) + alpha * qd.C(VS.c + i); mr[i] = qd.C(VMA.c + i) + alpha * qd.C(VMV.c + i); }
+            for (int l = 0; l < NC; l++) { xc[l] = qd.P(VX.p + l) + alpha * qd.P(VS.p + l); mcn[l] = qd.P(VMA.p + l) + alpha * qd.P(VMV.p + l); }
+            upd = mode == 1 && alpha != 0;
+            qd.sync();
+            vec_store(qd, VX, xr, xc, upd); vec_store(qd, VMA, mr, mcn, upd);
         }
-        if (done) {
+        // cost and gradient (into S) at the new point; a quad that stopped with alpha = 0 gets its gradient back
+        const double oldcost = st.cost;
+        quad_evaluate(qd, ch, st, mode == 1);
+        double gn = 0;
+        for (int l = 0; l < NC; l++) gn += qd.P(VS.p + l) * qd.P(VS.p + l);
+        gn = qd.sum(gn);
+        for (int i = 0; i < NR; i++) gn += qd.C(VS.c + i) * qd.C(VS.c + i);
+        if (!was_first && mode == 1) {
+            bool done = !upd;                                              // alpha == 0
+            if (upd) {
+                info.iters++;
+                done = scale * (oldcost - st.cost) < SOLVER_TOL || scale * sqrt(gn) < SOLVER_TOL || info.iters >= SOLVER_ITER;
+            }
+            if (done) mode = 2;
+        }
+        {
             // mj_Euler with implicit joint damping: (M + h diag(b)) qacc' = qfrc_smooth + qfrc_constraint = M a - grad
             double r[NR], c[NC];
             for (int i = 0; i < NR; i++) r[i] = qd.C(VMA.c + i) - qd.C(VS.c + i);
             for (int l = 0; l < NC; l++) c[l] = qd.P(VMA.p + l) - qd.P(VS.p + l);
             qd.sync();
-            vec_store(qd, VS, r, c);
-            mode = 2;
+            vec_store(qd, VS, r, c, mode == 2);
         }
     }
     double xr[NR], xc[NC], ar[NR], ac[NC];
     vec_load(qd, VX, xr, xc);
     vec_load(qd, VS, ar, ac);
-    {
-        bool bad = false;                                                  // mj_checkAcc
-        for (int i = 0; i < NR; i++) bad |= bad_value(xr[i]);
-        for (int l = 0; l < NC; l++) bad |= bad_value(xc[l]);
-        if (qd.any(bad)) {
-            info.reset = 1;
-            if (w == 0) { for (int i = 0; i < 8; i++) qpos[i] = (i == 1) ? 2.0 : (i == 3 ? 1.0 : 0.0); for (int i = 0; i < NR; i++) { qvel[i] = 0; warm[i] = 0; } }
-            const int nq = fr ? 7 : 6, nd = fr ? 6 : 5;
-            for (int i = 0; i < nq; i++) qpos[qa + i] = (i == nq - 4) ? 1.0 : 0.0;
-            for (int i = 0; i < nd; i++) { qvel[da + i] = 0; warm[da + i] = 0; }
-            return;
-        }
-    }
+    bool bad = false;                                                      // mj_checkAcc
+    for (int i = 0; i < NR; i++) bad |= bad_value(xr[i]);
+    for (int l = 0; l < NC; l++) bad |= bad_value(xc[l]);
+    bad = qd.any(bad);
     // ---- velocity, then mj_integratePos with the new velocity (state re-read: it was not kept across the solver)
     double qr[8], qc[7], vr[NR], vc[NC];
     quad_load(w, qpos, qvel, qr, qc, vr, vc);
     qd.sync();                                                             // every lane has re-read the root state
+    if (bad) {
+        info.reset = 1;
+        if (!live) return;
+        if (w == 0) { for (int i = 0; i < 8; i++) qpos[i] = (i == 1) ? 2.0 : (i == 3 ? 1.0 : 0.0); for (int i = 0; i < NR; i++) { qvel[i] = 0; warm[i] = 0; } }
+        const int nq = fr ? 7 : 6, nd = fr ? 6 : 5;
+        for (int i = 0; i < nq; i++) qpos[qa + i] = (i == nq - 4) ? 1.0 : 0.0;
+        for (int i = 0; i < nd; i++) { qvel[da + i] = 0; warm[da + i] = 0; }
+        return;
+    }
+    if (!live) return;
     for (int i = 0; i < NR; i++) vr[i] += TIMESTEP * ar[i];
     for (int l = 0; l < NC; l++) vc[l] += TIMESTEP * ac[l];
     if (w == 0) {

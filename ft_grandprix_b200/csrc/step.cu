@@ -197,10 +197,11 @@ step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
     for (int g = tid; g < 25; g += NT) quad_const_entry(c_model, g, quad_sm + KO);
     __syncthreads();
     int64_t car = (int64_t)blockIdx.x * (NT / 4) + cib;
-    if (car >= ncars) return;                       // whole quads leave together: nothing below spans quads
+    const bool live = car < ncars;
+    if (!live) car = ncars - 1;                     // padding quad: same collectives, no stores
     if (perm) car = perm[car];                      // cars grouped by their last Newton iteration count
     QuadDev<NT, NT / 4> qd;
-    qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.mask = 0xFu << (tid & 28);
+    qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.qs = tid & 28;
     WallsQuad walls{nullptr, nullptr};
     const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
     if (blob && !shadowed) {
@@ -212,10 +213,10 @@ step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
     int st = 0;
     for (int s = 0; s < nsteps; s++) {
         StepInfo info;
-        step_car_quad(qd, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, info);
+        step_car_quad(qd, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, live, info);
         st = (info.iters & 0xFF) | (info.reset ? 0x100 : (st & 0x100)) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24);
     }
-    if (status && qd.w == 0) status[car] = st;
+    if (status && qd.w == 0 && live) status[car] = st;
 }
 
 // The warp-per-car kernel runs the cars of a CTA in lock-step, so a CTA takes as many Newton rounds as its slowest

@@ -37,12 +37,17 @@ struct QuadHost : QuadMem<4, 1> {
         return m;
     }
     bool any(bool p) const { return ballot(p) != 0; }
+    // the host "warp" is the quad; `ghost` extra rounds emulate a quad that has to keep pace with slower cars of its
+    // warp / CTA (its stores are switched off: the results must not change)
+    mutable int ghost_w = 0, ghost_c = 0;
+    bool wany(bool p) const { const bool a = any(p); if (!a && ghost_w > 0) { ghost_w--; return true; } return a; }
+    bool cany(bool p) const { const bool a = any(p); if (!a && ghost_c > 0) { ghost_c--; return true; } return a; }
     void sync() const { s->bar.wait(); }
 };
 
 static ModelConsts g_mc;
 static bool g_ready = false;
-extern "C" int hq_step(double* qpos, double* qvel, double* warm, const double* ctrl, long n, int nsteps, int* info4) {
+extern "C" int hq_step_ghost(double* qpos, double* qvel, double* warm, const double* ctrl, long n, int nsteps, int* info4, int ghost_w, int ghost_c) {
     if (!g_ready) { g_mc = model_constants(); g_ready = true; }
     QuadHostShared sh;
     for (int g = 0; g < 25; g++) quad_const_entry(g_mc, g, sh.ktab);
@@ -53,11 +58,15 @@ extern "C" int hq_step(double* qpos, double* qvel, double* warm, const double* c
             for (long i = 0; i < n; i++)
                 for (int k = 0; k < nsteps; k++) {
                     StepInfo si;
-                    step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), si);
+                    q.ghost_w = ghost_w; q.ghost_c = ghost_c;
+                    step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), true, si);
                     q.sync();
                     if (info4 && w == 0) { info4[4 * i] = si.iters; info4[4 * i + 1] = si.ncon_wheel; info4[4 * i + 2] = si.ncon_wall; info4[4 * i + 3] = si.reset; }
                 }
         });
     for (auto& t : th) t.join();
     return 0;
+}
+extern "C" int hq_step(double* qpos, double* qvel, double* warm, const double* ctrl, long n, int nsteps, int* info4) {
+    return hq_step_ghost(qpos, qvel, warm, ctrl, n, nsteps, info4, 0, 0);
 }
