@@ -49,9 +49,8 @@ constexpr int QP_FRA = 75;           // 6   aref of the friction-loss rows of th
 constexpr int QP_EQ = 81;            // 3   Ackermann equality of a front chain: D (0: none), aref, dP/dx
 constexpr int QP_LIM = 84;           // 6   suspension / front steering limit: D[2] (0: inactive), aref[2], sign[2]
 constexpr int QP_WC = 90;            // 5   wheel-ground contact: D (0: none), aref[4]
-constexpr int QP_WD = 95;            // 6   line search: contact-frame dots J x, J s
-constexpr int QP_VEC = 101;          // 6 x 6 chain parts of the dof vectors below
-constexpr int QP_N = 137;
+constexpr int QP_VEC = 95;           // 6 x 6 chain parts of the dof vectors below
+constexpr int QP_N = 131;
 constexpr int QC_MR = 0;             // 28  root block of M, lower triangle
 constexpr int QC_R6 = 28;            // 4   rows of root dof 6 (steering wheel): friction aref, limit D, aref, sign
 constexpr int QC_VEC = 32;           // 6 x 7 root parts of the dof vectors
@@ -79,7 +78,7 @@ struct QuadMem {                     // PS: stride between slots of private data
 
 #if defined(__CUDACC__)
 extern __shared__ __align__(16) double quad_sm[];      // the kernel's dynamic shared memory (so that accesses are LDS/STS)
-template <int PS_, int CS_>
+template <int PS_, int CS_, bool CTA_LOCKSTEP>
 struct QuadDev {                     // po / co / ko: offsets (in doubles) of the lane's, the car's and the table's first slot
     static constexpr int PS = PS_, CS = CS_;
     int po, co, ko, w, qs;           // qs: position of the quad in the warp (lane & 28)
@@ -96,7 +95,7 @@ struct QuadDev {                     // po / co / ko: offsets (in doubles) of th
     __device__ __forceinline__ unsigned ballot(bool p) const { return (__ballot_sync(0xffffffffu, p) >> qs) & 0xFu; }
     __device__ __forceinline__ bool any(bool p) const { return ballot(p) != 0; }
     __device__ __forceinline__ bool wany(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
-    __device__ __forceinline__ bool cany(bool p) const { return __syncthreads_or(p) != 0; }
+    __device__ __forceinline__ bool cany(bool p) const { return CTA_LOCKSTEP ? __syncthreads_or(p) != 0 : wany(p); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 #endif
@@ -458,50 +457,49 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
 }
 
 // ---- exact line search (PrimalSearch) ---------------------------------------------------------------------------
-struct QLs { double qg0, qg1, qg2; };
+// Everything the cost along the search line needs, gathered once per line search and kept in registers: per row
+// the residual at alpha = 0 (j) and its slope (v); always-quadratic terms (Gauss, equality) are folded into c0-c2.
+struct QLs {
+    double c0, c1, c2;               // lane's always-quadratic rows (added before the quad sum)
+    double g0, g1, g2;               // Gauss term (replicated, added after the sum)
+    double fj[NC], fv[NC], fD[NC], fRf[NC], ff[NC];          // friction loss of the chain slots
+    double lj[2], lv[2], lD[2];      // limits (D = 0: no row)
+    double wj[4], wv[4], wD;         // wheel contact pyramid rows (D = 0: no contact)
+    double r6j, r6v, l6j, l6v, l6D;  // rows of root dof 6 (lane 0)
+};
 
 template <class Q>
-FT_QN void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, const QLs& L, LsPoint& pt, double alpha) {
-    const int w = qd.lane();
-    double q0 = 0, q1 = 0, q2 = 0;
-    const double x6 = qd.C(VX.c + 6), s6 = qd.C(VS.c + 6);
+FT_HD void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, const QLs& L, LsPoint& pt, double alpha) {
+    double q0 = L.c0, q1 = L.c1, q2 = L.c2;
 #pragma unroll
     for (int l = 0; l < NC; l++) {
-        const double D = qd.K(3 * (6 * w + l)), Rf = qd.K(3 * (6 * w + l) + 1), f = qd.K(3 * (6 * w + l) + 2);
-        const double jar = qd.P(VX.p + l) - qd.P(QP_FRA + l), jv = qd.P(VS.p + l), xx = jar + alpha * jv;
+        const double jar = L.fj[l], jv = L.fv[l], xx = jar + alpha * jv, Rf = L.fRf[l], f = L.ff[l], D = L.fD[l];
         const bool lo = xx <= -Rf, hi = xx >= Rf, lin = lo || hi;
         const double sj = lo ? -1.0 : 1.0;
         q0 += lin ? f * (-0.5 * Rf + sj * jar) : 0.5 * D * jar * jar;
         q1 += lin ? sj * f * jv : D * jar * jv;
         q2 += lin ? 0.0 : 0.5 * D * jv * jv;
-        if (l == 1) {                                                    // equality row of the front steering slot
-            const double De = qd.P(QP_EQ), der = qd.P(QP_EQ + 2);
-            const double je = qd.P(VX.p + 1) - der * x6 - qd.P(QP_EQ + 1), ve = jv - der * s6;
-            q0 += 0.5 * De * je * je; q1 += De * je * ve; q2 += 0.5 * De * ve * ve;
-        }
-        if (l < 2) {                                                     // limit row of slots 0, 1
-            const double Dl = qd.P(QP_LIM + l), sg = qd.P(QP_LIM + 4 + l);
-            const double jl = sg * qd.P(VX.p + l) - qd.P(QP_LIM + 2 + l), vl = sg * jv;
-            if (Dl > 0 && jl + alpha * vl < 0) { q0 += 0.5 * Dl * jl * jl; q1 += Dl * jl * vl; q2 += 0.5 * Dl * vl * vl; }
-        }
     }
-    if (w == 0) {
-        const double D = qd.K(72), Rf = qd.K(73), f = qd.K(74), jar = x6 - qd.C(QC_R6), jv = s6, xx = jar + alpha * jv;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double D = L.lD[k], jar = L.lj[k], jv = L.lv[k];
+        if (D > 0 && jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
+    }
+    if (qd.lane() == 0) {
+        const double D = qd.K(72), Rf = qd.K(73), f = qd.K(74), jar = L.r6j, jv = L.r6v, xx = jar + alpha * jv;
         const bool lo = xx <= -Rf, hi = xx >= Rf, lin = lo || hi;
         const double sj = lo ? -1.0 : 1.0;
         q0 += lin ? f * (-0.5 * Rf + sj * jar) : 0.5 * D * jar * jar;
         q1 += lin ? sj * f * jv : D * jar * jv;
         q2 += lin ? 0.0 : 0.5 * D * jv * jv;
-        const double D6 = qd.C(QC_R6 + 1), sg = qd.C(QC_R6 + 3), j6 = sg * x6 - qd.C(QC_R6 + 2), v6 = sg * s6;
+        const double D6 = L.l6D, j6 = L.l6j, v6 = L.l6v;
         if (D6 > 0 && j6 + alpha * v6 < 0) { q0 += 0.5 * D6 * j6 * j6; q1 += D6 * j6 * v6; q2 += 0.5 * D6 * v6 * v6; }
     }
-    const double Dw = qd.P(QP_WC);
-    if (Dw > 0) {
+    if (L.wD > 0) {
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
-            const double sg = (rr & 1) ? -WC_MU : WC_MU; const int ta = 1 + (rr >> 1);
-            const double jar = qd.P(QP_WD) + sg * qd.P(QP_WD + ta) - qd.P(QP_WC + 1 + rr), jv = qd.P(QP_WD + 3) + sg * qd.P(QP_WD + 3 + ta);
-            if (jar + alpha * jv < 0) { q0 += 0.5 * Dw * jar * jar; q1 += Dw * jar * jv; q2 += 0.5 * Dw * jv * jv; }
+            const double jar = L.wj[rr], jv = L.wv[rr];
+            if (jar + alpha * jv < 0) { q0 += 0.5 * L.wD * jar * jar; q1 += L.wD * jar * jv; q2 += 0.5 * L.wD * jv * jv; }
         }
     }
     for (int s = 0; s < nch; s++) {
@@ -512,7 +510,7 @@ FT_QN void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, const QLs& L, 
             if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
         }
     }
-    q0 = qd.sum(q0) + L.qg0; q1 = qd.sum(q1) + L.qg1; q2 = qd.sum(q2) + L.qg2;
+    q0 = qd.sum(q0) + L.g0; q1 = qd.sum(q1) + L.g1; q2 = qd.sum(q2) + L.g2;
     pt.alpha = alpha; pt.cost = alpha * alpha * q2 + alpha * q1 + q0;
     pt.d0 = 2 * alpha * q2 + q1; pt.d1 = 2 * q2;
     if (pt.d1 <= 0) pt.d1 = MINVAL;
@@ -541,12 +539,40 @@ FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, doubl
         g1 = qd.sum(g1); g2 = qd.sum(g2);
 #pragma unroll
         for (int i = 0; i < NR; i++) { g1 += sr[i] * (qd.C(VMA.c + i) - qd.C(VQFS.c + i)); g2 += 0.5 * sr[i] * qd.C(VMV.c + i); }
-        L.qg0 = st.gauss; L.qg1 = g1; L.qg2 = g2;
+        L.g0 = st.gauss; L.g1 = g1; L.g2 = g2;
         vec_load(qd, VX, xr, xc);
-        if (qd.P(QP_WC) > 0) {
-            double d3[3];
-            wc_dots(qd, xr, xc, d3); for (int a = 0; a < 3; a++) qd.P(QP_WD + a) = d3[a];
-            wc_dots(qd, sr, sc, d3); for (int a = 0; a < 3; a++) qd.P(QP_WD + 3 + a) = d3[a];
+        const int w = qd.lane();
+#pragma unroll
+        for (int l = 0; l < NC; l++) {
+            L.fD[l] = qd.K(3 * (6 * w + l)); L.fRf[l] = qd.K(3 * (6 * w + l) + 1); L.ff[l] = qd.K(3 * (6 * w + l) + 2);
+            L.fj[l] = xc[l] - qd.P(QP_FRA + l); L.fv[l] = sc[l];
+        }
+        {
+            const double De = qd.P(QP_EQ), der = qd.P(QP_EQ + 2), je = xc[1] - der * xr[6] - qd.P(QP_EQ + 1), ve = sc[1] - der * sr[6];
+            L.c0 = 0.5 * De * je * je; L.c1 = De * je * ve; L.c2 = 0.5 * De * ve * ve;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double sg = qd.P(QP_LIM + 4 + k);
+            L.lD[k] = qd.P(QP_LIM + k); L.lj[k] = sg * xc[k] - qd.P(QP_LIM + 2 + k); L.lv[k] = sg * sc[k];
+        }
+        {
+            const double sg = qd.C(QC_R6 + 3);
+            L.r6j = xr[6] - qd.C(QC_R6); L.r6v = sr[6];
+            L.l6D = qd.C(QC_R6 + 1); L.l6j = sg * xr[6] - qd.C(QC_R6 + 2); L.l6v = sg * sr[6];
+        }
+        L.wD = qd.P(QP_WC);
+        if (L.wD > 0) {
+            double dx[3], ds[3];
+            wc_dots(qd, xr, xc, dx); wc_dots(qd, sr, sc, ds);
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++) {
+                const double sg = (rr & 1) ? -WC_MU : WC_MU; const int ta = 1 + (rr >> 1);
+                L.wj[rr] = dx[0] + sg * dx[ta] - qd.P(QP_WC + 1 + rr); L.wv[rr] = ds[0] + sg * ds[ta];
+            }
+        } else {
+#pragma unroll
+            for (int rr = 0; rr < 4; rr++) { L.wj[rr] = 0; L.wv[rr] = 0; }
         }
         for (int s = 0; s < st.nch; s++)
             for (int a = 0; a < 3; a++) { ch.dx[s][a] = dot6q(ch.J[s][a], xr); ch.ds[s][a] = dot6q(ch.J[s][a], sr); }

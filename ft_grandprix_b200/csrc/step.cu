@@ -186,8 +186,8 @@ struct WallsQuad {                              // quad-per-car flavour: probe o
 // friction-loss row constants.  1 250 B per lane: five 32-thread CTAs (40 cars) per SM.
 template <int NT> constexpr size_t quad_smem_bytes() { return (size_t)(NT * QP_N + NT / 4 * QC_N + QK_N + 1) * sizeof(double); }
 
-template <int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
+template <int NT, bool LOCK>
+__global__ void __launch_bounds__(NT, 1)
 step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
                  double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
                  const int32_t* __restrict__ lap, const int32_t* __restrict__ perm, int64_t ncars, int nsteps,
@@ -200,7 +200,7 @@ step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
     const bool live = car < ncars;
     if (!live) car = ncars - 1;                     // padding quad: same collectives, no stores
     if (perm) car = perm[car];                      // cars grouped by their last Newton iteration count
-    QuadDev<NT, NT / 4> qd;
+    QuadDev<NT, NT / 4, LOCK> qd;
     qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.qs = tid & 28;
     WallsQuad walls{nullptr, nullptr};
     const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
@@ -290,8 +290,11 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     if (impl < 0) { const char* e = getenv("FTGP_STEP_IMPL"); impl = !e ? 2 : (e[0] == 'w' ? 0 : (e[0] == 't' ? 1 : 2)); }
     const uint32_t* blob = g ? g->d_blob : nullptr;
     if (impl == 2) {
-        static int qt = 0;
-        if (!qt) { const char* e = getenv("FTGP_STEP_QT"); qt = e ? atoi(e) : 160; if (qt != 32 && qt != 64 && qt != 128 && qt != 160) qt = 160; }
+        static int qt = 0, lock = 1;
+        if (!qt) {
+            const char* e = getenv("FTGP_STEP_QT"); qt = e ? atoi(e) : 192; if (qt != 64 && qt != 128 && qt != 160 && qt != 192) qt = 192;
+            const char* l = getenv("FTGP_STEP_LOCK"); lock = (l && l[0] == '0') ? 0 : 1;
+        }
         const int32_t* perm = nullptr;
         if ((rc = order_cars(status, ncars, dev, stream, &perm))) return rc;
         auto launch = [&](auto kern, size_t smem) -> int {
@@ -302,10 +305,10 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
             return FTGP_OK;
         };
         int rc2;
-        if (qt == 32) rc2 = launch(step_quad_kernel<32, 5>, quad_smem_bytes<32>());
-        else if (qt == 64) rc2 = launch(step_quad_kernel<64, 2>, quad_smem_bytes<64>());
-        else if (qt == 160) rc2 = launch(step_quad_kernel<160, 1>, quad_smem_bytes<160>());
-        else rc2 = launch(step_quad_kernel<128, 1>, quad_smem_bytes<128>());
+        if (qt == 64) rc2 = lock ? launch(step_quad_kernel<64, true>, quad_smem_bytes<64>()) : launch(step_quad_kernel<64, false>, quad_smem_bytes<64>());
+        else if (qt == 128) rc2 = lock ? launch(step_quad_kernel<128, true>, quad_smem_bytes<128>()) : launch(step_quad_kernel<128, false>, quad_smem_bytes<128>());
+        else if (qt == 192) rc2 = lock ? launch(step_quad_kernel<192, true>, quad_smem_bytes<192>()) : launch(step_quad_kernel<192, false>, quad_smem_bytes<192>());
+        else rc2 = lock ? launch(step_quad_kernel<160, true>, quad_smem_bytes<160>()) : launch(step_quad_kernel<160, false>, quad_smem_bytes<160>());
         if (rc2) return rc2;
     } else if (impl == 1) {
         static int threads = 0;

@@ -30,6 +30,19 @@ def host_kernel():
     return C.CDLL(out)
 
 
+@pytest.fixture(scope="module")
+def host_quad_kernel():
+    """The quad-per-car kernel source compiled for the host: four OS threads play the four lanes of a quad."""
+    src = os.path.join(ROOT, "tests", "host_harness", "step_quad_host.cpp")
+    out = os.path.join(ROOT, "tests", "host_harness", "libstep_quad_host.so")
+    deps = [src] + [os.path.join(ROOT, "ft_grandprix_b200", "csrc", f) for f in ("mushr_step_quad.cuh", "mushr_step.cuh", "mushr_consts.h", "mushr_mesh.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-pthread", "-o", out, src])
+    lib = C.CDLL(out)
+    lib.hq_step_ghost.argtypes = [C.c_void_p] * 4 + [C.c_long, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    return lib
+
+
 def random_state(model, rng):
     q = model.reset(0, 0, 0)[0]
     q[0:3] = rng.normal(size=3)
@@ -164,3 +177,47 @@ def test_product_kernel_source_single_step_parity(model, host_kernel):
             worst = max(worst, np.abs(vh - vo).max())
             q, v, w = qo, vo, wo
     assert worst < 1e-10
+
+
+def test_quad_kernel_source_single_step_parity(model, host_quad_kernel):
+    """The quad-per-car kernel (four lanes per car, csrc/mushr_step_quad.cuh) against the oracle: 1e-5 relative bar,
+    same Newton iteration counts; and a quad that is kept going after its car converged (as in a warp / CTA whose
+    other cars need more iterations) must leave bit-identical results."""
+    rng = np.random.default_rng(3)
+    worst = 0
+    for car in range(4):
+        q, v, w = model.reset(rng.normal(), rng.normal(), rng.uniform(-3, 3))
+        for k in range(200):
+            ctrl = np.array([rng.uniform(0, 4), rng.uniform(-0.6, 0.6)]) if k % 25 == 0 else ctrl
+            qo, vo, wo = q.copy(), v.copy(), w.copy()
+            _, info_o = model.step(None, qo, vo, wo, ctrl)
+            ref = None
+            for gw, gc in ((0, 0), (3, 2)) if k % 10 == 0 else ((0, 0),):
+                qh, vh, wh = q.copy(), v.copy(), w.copy()
+                info = np.zeros(4, dtype=np.int32)
+                host_quad_kernel.hq_step_ghost(P(qh), P(vh), P(wh), P(ctrl), 1, 1, P(info), gw, gc)
+                if ref is None:
+                    ref = (qh, vh, wh, info)
+                else:
+                    assert all(np.array_equal(a, b) for a, b in zip(ref, (qh, vh, wh, info)))
+            qh, vh, wh, info = ref
+            np.testing.assert_allclose(qh, qo, rtol=1e-5, atol=1e-10)
+            np.testing.assert_allclose(vh, vo, rtol=1e-5, atol=1e-9)
+            np.testing.assert_allclose(wh, wo, rtol=1e-5, atol=1e-6)
+            assert info[0] == info_o[0] and info[1] == info_o[2]
+            worst = max(worst, np.abs(vh - vo).max())
+            q, v, w = qo, vo, wo
+    assert worst < 1e-10
+
+
+def test_quad_kernel_source_resets_bad_state(model, host_quad_kernel):
+    q, v, w = model.reset(3, 4, 1)
+    v[0] = 1e11
+    qo, vo, wo = q.copy(), v.copy(), w.copy()
+    rc, _ = model.step(None, qo, vo, wo, np.zeros(2))
+    info = np.zeros(4, dtype=np.int32)
+    ctrl = np.zeros(2)
+    host_quad_kernel.hq_step_ghost(P(q), P(v), P(w), P(ctrl), 1, 1, P(info), 0, 0)
+    assert rc == 1 and info[3] == 1
+    np.testing.assert_allclose(q, qo, rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(v, vo, rtol=1e-5, atol=1e-9)
