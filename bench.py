@@ -263,14 +263,23 @@ def run_gpu(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kevs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     with torch.cuda.stream(stream):
-        for (a, b), kev in zip(ev, kevs):
+        for a, b in ev:
             flush.fill_(1)
             a.record(stream)
-            one_step(kev)
+            if wl == "tick":
+                fleet.tick(1)            # the product's fused entry point (ftgp_tick): same kernels, one C call
+            else:
+                one_step()
             b.record(stream)
     barrier()
     clocks = sampler.stop()
     launches = lib.ftgp_launch_count() - launches0
+    # second pass, same regime: the two heavy kernels bracketed by their own CUDA events on the launching stream
+    with torch.cuda.stream(stream):
+        for kev in kevs:
+            flush.fill_(1)
+            one_step(kev)
+    barrier()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     lidar_ms = np.mean([k[0].elapsed_time(k[1]) for k in kevs]) if wl != "step" else None
     step_ms = np.mean([k[2].elapsed_time(k[3]) for k in kevs]) if wl != "lidar" else None
@@ -319,9 +328,11 @@ def run_gpu(args):
     peak, peak_src = peaks()
     # roofline of the dominant kernel (step_kernel in the tick, else the only kernel): algorithmic bytes of ONE launch
     # (1,488 B per car-step, 416 B per 90-ray scan) / its own CUDA-event duration in this timed region
-    dom = "lidar_kernel" if wl == "lidar" else "step_kernel"
-    dom_ms = lidar_ms if wl == "lidar" else step_ms
-    per_unit = (BYTES["lidar"] if wl == "lidar" else BYTES["step"])
+    STEP_KERNEL = "step_quad_kernel"
+    dom_is_lidar = wl == "lidar" or (wl == "tick" and lidar_ms > step_ms)
+    dom = "lidar_kernel" if dom_is_lidar else STEP_KERNEL
+    dom_ms = lidar_ms if dom_is_lidar else step_ms
+    per_unit = (BYTES["lidar"] if dom_is_lidar else BYTES["step"])
     achieved = cars * per_unit / (dom_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -332,8 +343,9 @@ def run_gpu(args):
         kernels["lidar_kernel"] = {"ms": float(lidar_ms), "rays_per_s": cars * 90 / (lidar_ms * 1e-3), "ns_per_ray": lidar_ms * 1e6 / (cars * 90),
                                    "algorithmic_GBps": cars * BYTES["lidar"] / (lidar_ms * 1e-3) / 1e9}
     if step_ms is not None:
-        kernels["step_kernel"] = {"ms": float(step_ms), "car_steps_per_s": cars / (step_ms * 1e-3),
-                                  "algorithmic_GBps": cars * BYTES["step"] / (step_ms * 1e-3) / 1e9}
+        kernels[STEP_KERNEL] = {"ms": float(step_ms), "car_steps_per_s": cars / (step_ms * 1e-3),
+                                "algorithmic_GBps": cars * BYTES["step"] / (step_ms * 1e-3) / 1e9,
+                                "includes": "the two counting-sort launches that group cars by Newton iteration count"}
     metric, unit = ("lidar rays/s", "rays/s") if wl == "lidar" else ("car-steps/s", "car-steps/s")
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -341,7 +353,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": workload_name(wl, cars), "cars_per_gpu": cars, "beams": 90, "track": "track.png",
                        "driver": "nidc (device)", "l2": "flushed (512 MiB write) between timed steps",
-                       "timing": "CUDA events on the launching stream per step, summed; max over ranks",
+                       "timing": "CUDA events on the launching stream per step, summed; max over ranks; per-kernel times from a second pass",
                        "sharding": f"{world} x {cars} cars, no collective on the step path"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": dom, "kernel_ms": float(dom_ms),

@@ -389,18 +389,27 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                     }
                 }
             }
-            // ---------------- one step over the chunk grid
+            // ---------------- over the chunk grid to the next non-empty chunk (empty chunks: one shared-memory load each)
             if (L.state == ST_CHUNK) {
                 const TrackHeader* th = L.th;
-                const int hc = th->hc;
-                const float tmx = L.inv_dgx != 0.f ? ((float)(L.ix - L.ix0 + (L.stepx > 0 ? 1 : 0)) - L.fx0) * L.inv_dgx : BIG;
-                const float tmy = L.inv_dgy != 0.f ? ((float)(L.iy - L.iy0 + (L.stepy > 0 ? 1 : 0)) - L.fy0) * L.inv_dgy : BIG;
-                L.exit_axis = tmx <= tmy ? 0 : 1;
-                L.t1 = fminf(tmx, tmy);
+                const int hc = th->hc, vc = th->vc;
                 const uint16_t* index = reinterpret_cast<const uint16_t*>(geo + th->index_off);
-                const uint32_t cid = index[L.iy * hc + L.ix];
-                L.nonempty = cid != EMPTY_CHUNK;
-                L.need_advance = true;
+                uint32_t cid;
+                for (;;) {
+                    const float tmx = L.inv_dgx != 0.f ? ((float)(L.ix - L.ix0 + (L.stepx > 0 ? 1 : 0)) - L.fx0) * L.inv_dgx : BIG;
+                    const float tmy = L.inv_dgy != 0.f ? ((float)(L.iy - L.iy0 + (L.stepy > 0 ? 1 : 0)) - L.fy0) * L.inv_dgy : BIG;
+                    L.exit_axis = tmx <= tmy ? 0 : 1;
+                    L.t1 = fminf(tmx, tmy);
+                    cid = index[L.iy * hc + L.ix];
+                    if (cid != EMPTY_CHUNK) break;
+                    // empty chunk: nothing to hit, leave it at once
+                    if (L.t1 >= L.tend) { finish(L, L.best < BIG ? L.best : -1.f, ranges, min_range, base_car); break; }
+                    if (L.exit_axis == 0) L.ix += L.stepx; else L.iy += L.stepy;
+                    if (L.ix < 0 || L.ix >= hc || L.iy < 0 || L.iy >= vc) { finish(L, L.best < BIG ? L.best : -1.f, ranges, min_range, base_car); break; }
+                    L.t0 = L.t1; L.entry_axis = L.exit_axis;
+                }
+                L.nonempty = L.state == ST_CHUNK;
+                L.need_advance = L.nonempty;
                 if (L.nonempty) {
                     const uint32_t* m = geo + th->chunks_off + cid * CHUNK_WORDS;
                     L.m = m;
@@ -458,25 +467,30 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                     }
                 }
             }
-            // ---------------- one major-axis column of cells inside the current chunk
+            // ---------------- inside the current chunk: on to the next line of cells with a candidate, then test them
             if (L.state == ST_SWEEP) {
-                float s0 = 0.f, s1 = L.span;
-                if (L.inv_dM != 0.f) {
-                    const float e0 = ((float)(L.c + (L.sg > 0 ? 0 : 1)) - L.Ma) * L.inv_dM;
-                    const float e1 = ((float)(L.c + (L.sg > 0 ? 1 : 0)) - L.Ma) * L.inv_dM;
-                    s0 = fmaxf(s0, e0); s1 = fminf(s1, e1);
-                }
-                const float m0 = L.ma + s0 * L.dm, m1 = L.ma + s1 * L.dm;
-                int rlo = (int)floorf(fminf(m0, m1) - 1e-3f), rhi = (int)floorf(fmaxf(m0, m1) + 1e-3f);
-                rlo = min(max(rlo, 0), L.nm - 1); rhi = min(max(rhi, 0), L.nm - 1);
-                // vertex bits of lines c and c+1 along the fast axis (row-major masks for rows, transposed for columns)
-                const uint32_t* mk = L.major_x ? L.m + 15 : L.m;
+                uint32_t cand, lineA, lineB;
+                const uint32_t* mk = L.major_x ? L.m + 15 : L.m;        // row-major masks for rows, transposed for columns
                 const int nline = L.major_x ? L.nrow : L.ncol;          // vertices per line
-                const uint32_t lineA = mask_line(mk, L.c * nline, nline), lineB = mask_line(mk, (L.c + 1) * nline, nline);
-                uint32_t occ = lineA | lineB;
-                occ |= occ >> 1;                                        // cell k has a wall vertex among its 4 corners
-                const uint32_t range = (2u << rhi) - (1u << rlo);       // cells rlo..rhi
-                uint32_t cand = L.floor_reach ? range : (occ & range);
+                for (;;) {
+                    float s0 = 0.f, s1 = L.span;
+                    if (L.inv_dM != 0.f) {
+                        const float e0 = ((float)(L.c + (L.sg > 0 ? 0 : 1)) - L.Ma) * L.inv_dM;
+                        const float e1 = ((float)(L.c + (L.sg > 0 ? 1 : 0)) - L.Ma) * L.inv_dM;
+                        s0 = fmaxf(s0, e0); s1 = fminf(s1, e1);
+                    }
+                    const float m0 = L.ma + s0 * L.dm, m1 = L.ma + s1 * L.dm;
+                    int rlo = (int)floorf(fminf(m0, m1) - 1e-3f), rhi = (int)floorf(fmaxf(m0, m1) + 1e-3f);
+                    rlo = min(max(rlo, 0), L.nm - 1); rhi = min(max(rhi, 0), L.nm - 1);
+                    // vertex bits of lines c and c+1 along the fast axis
+                    lineA = mask_line(mk, L.c * nline, nline); lineB = mask_line(mk, (L.c + 1) * nline, nline);
+                    uint32_t occ = lineA | lineB;
+                    occ |= occ >> 1;                                    // cell k has a wall vertex among its 4 corners
+                    const uint32_t range = (2u << rhi) - (1u << rlo);   // cells rlo..rhi
+                    cand = L.floor_reach ? range : (occ & range);
+                    if (cand || L.c == L.cend) break;
+                    L.c += L.sg;
+                }
                 float found = BIG;
                 while (cand && found == BIG) {
                     const int k = L.dm >= 0.f ? __ffs(cand) - 1 : 31 - __clz(cand);

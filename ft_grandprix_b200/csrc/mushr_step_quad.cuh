@@ -281,6 +281,8 @@ template <class Q>
 FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, int mode, QVec V, double sign, bool on) {
     const int w = qd.lane();
     double W[21], B[NC][NR], Pp[28];
+    double k00 = 0, k01 = 0, k02 = 0, k11 = 0, k22 = 0, eqb = 0;      // contact-frame K and the equality's border entry (mode 1)
+    bool wcon = false;
 #pragma unroll
     for (int i = 0; i < 21; i++) W[i] = qd.P(QP_MW + i);
 #pragma unroll
@@ -298,7 +300,7 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
         if (w == 0) Pp[tri(6, 6)] += TIMESTEP * 0.1;
     } else if (mode == 1) {
         const unsigned mask = st.mask;
-        { const double D = qd.P(QP_EQ), der = qd.P(QP_EQ + 2); W[tri(1, 1)] += D; B[1][6] -= D * der; Pp[tri(6, 6)] += D * der * der; }
+        { const double D = qd.P(QP_EQ), der = qd.P(QP_EQ + 2); eqb = -D * der; W[tri(1, 1)] += D; B[1][6] += eqb; Pp[tri(6, 6)] += D * der * der; }
 #pragma unroll
         for (int l = 0; l < NC; l++) if (mask >> (QB_FR + l) & 1u) W[tri(l, l)] += qd.K(3 * (6 * w + l));
 #pragma unroll
@@ -310,8 +312,9 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
             const double D = qd.P(QP_WC);
             const double a0 = (mask >> QB_WC & 1u) ? 1.0 : 0.0, a1 = (mask >> (QB_WC + 1) & 1u) ? 1.0 : 0.0,
                          a2 = (mask >> (QB_WC + 2) & 1u) ? 1.0 : 0.0, a3 = (mask >> (QB_WC + 3) & 1u) ? 1.0 : 0.0;
-            const double k00 = D * (a0 + a1 + a2 + a3), k01 = D * WC_MU * (a0 - a1), k02 = D * WC_MU * (a2 - a3),
-                         k11 = D * WC_MU * WC_MU * (a0 + a1), k22 = D * WC_MU * WC_MU * (a2 + a3);
+            k00 = D * (a0 + a1 + a2 + a3); k01 = D * WC_MU * (a0 - a1); k02 = D * WC_MU * (a2 - a3);
+            k11 = D * WC_MU * WC_MU * (a0 + a1); k22 = D * WC_MU * WC_MU * (a2 + a3);
+            wcon = true;
             double J[3][9], T[3][9];
             J[0][0] = 0; J[0][1] = 0; J[0][2] = 1; J[1][0] = 0; J[1][1] = 1; J[1][2] = 0; J[2][0] = -1; J[2][1] = 0; J[2][2] = 0;
 #pragma unroll
@@ -433,13 +436,35 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
         for (int k = i + 1; k < NR; k++) s -= R[tri(k, i)] * xr[k];
         xr[i] = s * R[tri(i, i)];
     }
-    // back substitution of the chain: x_c = L^-T (z - Y x_r)
+    // chain: x_c = W^-1 (b_c - B x_r) with the ORIGINAL border B, rebuilt from shared memory (keeping Y = L^-1 B
+    // alive across the root factorisation costs 84 registers and spills; rebuilding B x_r costs ~90 DFMA)
+    {
+        double t[NC];
 #pragma unroll
-    for (int l = 0; l < NC; l++) {
-        double s = 0;
+        for (int l = 0; l < NC; l++) {
+            double sacc = qd.P(V.p + l);
 #pragma unroll
-        for (int j = 0; j < NR; j++) s += B[l][j] * xr[j];
-        z[l] -= s;
+            for (int j = 0; j < 6; j++) sacc -= qd.P(QP_MB + 6 * l + j) * xr[j];
+            t[l] = sacc;
+        }
+        t[1] -= eqb * xr[6];
+        if (wcon) {
+            double v3[3] = {xr[2], xr[1], -xr[0]}, u[3];
+#pragma unroll
+            for (int a = 0; a < 3; a++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) v3[a] += qd.P(QP_CJ + 6 * a + k) * xr[3 + k];
+            u[0] = k00 * v3[0] + k01 * v3[1] + k02 * v3[2]; u[1] = k01 * v3[0] + k11 * v3[1]; u[2] = k02 * v3[0] + k22 * v3[2];
+#pragma unroll
+            for (int l = 0; l < 3; l++) t[l] -= qd.P(QP_CJ + 3 + l) * u[0] + qd.P(QP_CJ + 9 + l) * u[1] + qd.P(QP_CJ + 15 + l) * u[2];
+        }
+#pragma unroll
+        for (int l = 0; l < NC; l++) {
+            double sacc = t[l];
+#pragma unroll
+            for (int k = 0; k < l; k++) sacc -= W[tri(l, k)] * z[k];
+            z[l] = sacc * W[tri(l, l)];
+        }
     }
 #pragma unroll
     for (int l = NC - 1; l >= 0; l--) {
