@@ -292,7 +292,7 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     if (impl == 2) {
         static int qt = 0, lock = 1;
         if (!qt) {
-            const char* e = getenv("FTGP_STEP_QT"); qt = e ? atoi(e) : 192; if (qt != 64 && qt != 128 && qt != 160 && qt != 192) qt = 192;
+            const char* e = getenv("FTGP_STEP_QT"); qt = e ? atoi(e) : 192; if (qt != 128 && qt != 192) qt = 192;
             const char* l = getenv("FTGP_STEP_LOCK"); lock = (l && l[0] == '0') ? 0 : 1;
         }
         const int32_t* perm = nullptr;
@@ -305,10 +305,8 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
             return FTGP_OK;
         };
         int rc2;
-        if (qt == 64) rc2 = lock ? launch(step_quad_kernel<64, true>, quad_smem_bytes<64>()) : launch(step_quad_kernel<64, false>, quad_smem_bytes<64>());
-        else if (qt == 128) rc2 = lock ? launch(step_quad_kernel<128, true>, quad_smem_bytes<128>()) : launch(step_quad_kernel<128, false>, quad_smem_bytes<128>());
-        else if (qt == 192) rc2 = lock ? launch(step_quad_kernel<192, true>, quad_smem_bytes<192>()) : launch(step_quad_kernel<192, false>, quad_smem_bytes<192>());
-        else rc2 = lock ? launch(step_quad_kernel<160, true>, quad_smem_bytes<160>()) : launch(step_quad_kernel<160, false>, quad_smem_bytes<160>());
+        if (qt == 128) rc2 = launch(step_quad_kernel<128, true>, quad_smem_bytes<128>());
+        else rc2 = lock ? launch(step_quad_kernel<192, true>, quad_smem_bytes<192>()) : launch(step_quad_kernel<192, false>, quad_smem_bytes<192>());
         if (rc2) return rc2;
     } else if (impl == 1) {
         static int threads = 0;
