@@ -10,6 +10,8 @@ One "step" = one pass of the hot path over the whole fleet:
                  (rays/s = 90 x car-steps/s is reported beside it)
   workload lidar (BASELINE config 2): 90-beam scan of 4,096 cars at random poses -> rays/s
   workload step  : vehicle step only, 65,536 cars
+  workload episode (BASELINE config 4): 1,048,576 cars IN TOTAL over the N ranks (strong scaling) on circle /
+                 small-circle alternating by world index, full tick, lap statistics gathered once at the end
 Cars are sharded over the N ranks with no collective on the step path (weak scaling: the per-GPU
 fleet is fixed); only the final timing / stats are gathered.
 """
@@ -378,20 +380,127 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- BASELINE config 4: one sharded episode
+def run_episode(args):
+    """1,048,576 independent cars (total, strong scaling) on circle / small-circle alternating by GLOBAL world index,
+    contiguous blocks of worlds per rank, no collective on the step path; the episode's lap statistics are gathered
+    once at the end (NCCL all_gather, ft_grandprix_b200.sharding)."""
+    import torch
+    import torch.distributed as dist
+    import ft_grandprix_b200 as ft
+    from ft_grandprix_b200.sharding import STAT_FIELDS, ShardedRace
+    from ft_grandprix_b200.track import Geometry
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = ft._lib.load()
+    tracks = [ft.Track.bundled("circle"), ft.Track.bundled("small-circle")]
+    nworlds = args.cars
+    race = ShardedRace(nworlds, 1, 2, lambda n, tid, first: ft.Fleet(Geometry(tracks, device=local), n, device=local, track_id=tid, driver="nidc"))
+    fleet = race.fleet
+    n = fleet.ncars
+    xy = np.zeros((n, 2)); yaw = np.zeros(n)
+    for t in range(2):
+        sel = np.nonzero(race.track_id == t)[0]
+        a, b, _ = make_poses(tracks[t].path, len(sel), seed=2 + 1000 * rank + t, level=True)
+        xy[sel] = a; yaw[sel] = b
+    fleet.reset(xy, yaw)
+    stream = fleet.stream
+    sampler = ClockSampler(local); sampler.start()
+    with torch.cuda.stream(stream):
+        for _ in range(args.settle):
+            fleet.tick(1)
+        for _ in range(args.warmup):
+            fleet.tick(1)
+    stream.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = lib.ftgp_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            fleet.tick(1)
+        e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.ftgp_launch_count() - launches0
+    dev_ms = e0.elapsed_time(e1)
+    t0 = time.perf_counter()
+    stats = race.episode_stats()                     # the only collective of the episode
+    torch.cuda.synchronize()
+    gather_ms = (time.perf_counter() - t0) * 1e3
+    # e2e: ticks through the public API with the episode statistics read back to the host every step
+    lap_h = torch.empty_like(fleet.lap, device="cpu").pin_memory()
+    ranges_h = torch.empty(n, 90, dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        with torch.cuda.stream(stream):
+            fleet.tick(1)
+            ranges_h.copy_(fleet.ranges, non_blocking=True); lap_h.copy_(fleet.lap, non_blocking=True)
+        stream.synchronize()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    tt = torch.tensor([dev_ms, e2e_ms, float(launches), gather_ms], dtype=torch.float64, device=fleet.device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, launches, gather_ms = float(tt[0]), float(tt[1]), int(tt[2]), float(tt[3])
+    value = nworlds * args.steps / (dev_ms * 1e-3)
+    peak, peak_src = peaks()
+    achieved = value * BYTES["tick"] / 1e9
+    laps = stats[:, STAT_FIELDS.index("laps")]
+    line = {"metric": "car-steps/s", "value": value, "unit": "car-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"sharded episode, {nworlds} cars in total on circle/small-circle alternating by world index, "
+                                   f"full tick, stats gathered once (BASELINE config 4)", "cars_total": nworlds,
+                       "cars_per_gpu": n, "beams": 90, "driver": "nidc (device)",
+                       "l2": "fleet state per GPU (>= 190 MB at 8 GPUs) exceeds the 126 MB L2", "timing": "CUDA events around the K ticks; max over ranks",
+                       "sharding": f"{world} contiguous blocks of worlds, no collective on the step path"},
+            "roofline": {"bound": "hbm", "achieved": achieved / world, "peak": peak, "unit": "GB/s", "frac": achieved / world / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "whole tick (per GPU)",
+                         "algorithmic_bytes_per_unit": BYTES["tick"],
+                         "note": "latency/issue-bound path: algorithmic HBM traffic is far below peak by construction (SURVEY 8d)"},
+            "e2e": {"value": nworlds * e2e_steps / (e2e_ms * 1e-3), "unit": "car-steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": n * 90 * 4 + fleet.lap.numel() * 4, "steps": e2e_steps,
+                    "how": "fleet.tick + ranges and lap state to pinned host memory every step, wall clock"},
+            "gpu_launches": launches, "clocks": clocks, "rays_per_s": value * 90,
+            "episode": {"gather_ms": gather_ms, "stats_rows": int(stats.shape[0]), "stats_bytes": int(stats.numel() * 4),
+                        "laps_max": int(laps.max()), "cars_moved": int((stats[:, STAT_FIELDS.index("completion")] != 0).sum())}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("FTGP_WORKLOAD", "tick"), choices=["tick", "lidar", "step"])
+    ap.add_argument("--workload", default=os.environ.get("FTGP_WORKLOAD", "tick"), choices=["tick", "lidar", "step", "episode"])
     ap.add_argument("--cars", type=int, default=None)
     ap.add_argument("--settle", type=int, default=200, help="untimed ticks before timing (tick/step workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused-check", action="store_true", help="assert that ftgp_tick == the four separate calls, bit for bit")
     args = ap.parse_args()
     if args.cars is None:
-        args.cars = 4096 if args.workload == "lidar" else 65536
+        args.cars = {"lidar": 4096, "episode": 1048576}.get(args.workload, 65536)
+    if args.workload == "episode" and args.impl != "reference":
+        return run_episode(args)
     if args.impl == "reference":
         run_reference(args)
     else:
