@@ -196,10 +196,11 @@ __device__ __forceinline__ double ray_cylinder(double px, double py, double pz, 
 // Traversal as a per-lane state machine.  A warp owns a batch of cars (whole worlds) and a pool of
 // 90 x ncars rays; every lane runs IDLE -> CHUNK (one Amanatides-Woo step over the 0.5 m chunk grid)
 // -> SWEEP (one major-axis column of 19x19 cells inside a non-empty chunk) -> ... -> IDLE, and an idle
-// lane pulls the next ray of the pool.  Each loop iteration executes each of the three short code
-// blocks at most once for the whole warp, so lanes never wait for another lane's inner loop
+// lane pulls the next ray of the pool.  Each loop iteration executes ONE of the code blocks for the whole warp: the
+// one most lanes are waiting for (a warp-uniform vote), so that lanes in the same state are served together and the
+// other blocks' instructions are not issued at all for a handful of lanes
 // (the first version traced beams l, l+32, l+64 per lane with nested loops: 6.5 of 32 lanes active).
-enum { ST_IDLE = 0, ST_CHUNK = 1, ST_SWEEP = 2 };
+enum { ST_IDLE = 0, ST_CHUNK = 1, ST_SWEEP = 2, ST_ADV = 3 };
 constexpr int BATCH = 8;              // max cars per warp batch (a batch holds whole worlds: cars_per_world 1, 2, 4 or 8)
 constexpr int FRAME_DOUBLES = 12;     // p[3], R[9]
 
@@ -215,7 +216,7 @@ struct Lane {
     // sweep
     float ta, span, xa, ya, za, dM, dm, Ma, ma, inv_dM; int nM, nm, sg, c, cend; bool floor_reach, major_x;
     // bookkeeping
-    int rid, state; bool need_advance;
+    int rid, state;
     const TrackHeader* th;
 };
 
@@ -224,7 +225,7 @@ __device__ __forceinline__ void finish(Lane& L, float val, float* __restrict__ r
     const int car = L.rid / FTGP_NBEAMS, beam = L.rid - car * FTGP_NBEAMS;
     ranges[(base_car + car) * FTGP_NBEAMS + beam] = val;
     if (min_range && val >= 0.f) atomicMin(reinterpret_cast<unsigned int*>(min_range + base_car + car), __float_as_uint(val));
-    L.state = ST_IDLE; L.need_advance = false;
+    L.state = ST_IDLE;
 }
 
 __global__ void __launch_bounds__(512)
@@ -283,7 +284,7 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
         const int nrays = nb * FTGP_NBEAMS;
         int next = 0;
         Lane L;
-        L.state = ST_IDLE; L.need_advance = false;
+        L.state = ST_IDLE;
         for (;;) {
             const unsigned idle = __ballot_sync(0xffffffffu, L.state == ST_IDLE);
             const bool refill = next < nrays && (__popc(idle) >= 8 || idle == 0xffffffffu);
@@ -389,8 +390,13 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                     }
                 }
             }
+            // ---------------- which block runs this round: the state with the most lanes
+            const int n_chunk = __popc(__ballot_sync(0xffffffffu, L.state == ST_CHUNK));
+            const int n_sweep = __popc(__ballot_sync(0xffffffffu, L.state == ST_SWEEP));
+            const int n_adv = __popc(__ballot_sync(0xffffffffu, L.state == ST_ADV));
+            const int pick = (n_chunk >= n_sweep && n_chunk >= n_adv) ? ST_CHUNK : (n_sweep >= n_adv ? ST_SWEEP : ST_ADV);
             // ---------------- over the chunk grid to the next non-empty chunk (empty chunks: one shared-memory load each)
-            if (L.state == ST_CHUNK) {
+            if (pick == ST_CHUNK && L.state == ST_CHUNK) {
                 const TrackHeader* th = L.th;
                 const int hc = th->hc, vc = th->vc;
                 const uint16_t* index = reinterpret_cast<const uint16_t*>(geo + th->index_off);
@@ -409,7 +415,7 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                     L.t0 = L.t1; L.entry_axis = L.exit_axis;
                 }
                 L.nonempty = L.state == ST_CHUNK;
-                L.need_advance = L.nonempty;
+                if (L.nonempty) L.state = ST_ADV;           // unless the sweep below takes over (or a face ends the ray)
                 if (L.nonempty) {
                     const uint32_t* m = geo + th->chunks_off + cid * CHUNK_WORDS;
                     L.m = m;
@@ -461,14 +467,14 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                                 const float Mb = L.Ma + L.span * L.dM;
                                 int c = (int)floorf(L.Ma - (float)L.sg * 1e-3f), cend = (int)floorf(Mb + (float)L.sg * 1e-3f);
                                 L.c = min(max(c, 0), L.nM - 1); L.cend = min(max(cend, 0), L.nM - 1);
-                                L.state = ST_SWEEP; L.need_advance = false;
+                                L.state = ST_SWEEP;
                             }
                         }
                     }
                 }
             }
             // ---------------- inside the current chunk: on to the next line of cells with a candidate, then test them
-            if (L.state == ST_SWEEP) {
+            if (pick == ST_SWEEP && L.state == ST_SWEEP) {
                 uint32_t cand, lineA, lineB;
                 const uint32_t* mk = L.major_x ? L.m + 15 : L.m;        // row-major masks for rows, transposed for columns
                 const int nline = L.major_x ? L.nrow : L.ncol;          // vertices per line
@@ -510,14 +516,13 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                     if (s <= L.span + 1e-4f) found = fminf(found, s);
                 }
                 if (found < BIG) finish(L, fminf(L.best, fmaxf(L.ta + found, 0.f)), ranges, min_range, base_car);
-                else if (L.c == L.cend) { L.state = ST_CHUNK; L.need_advance = true; }
+                else if (L.c == L.cend) L.state = ST_ADV;
                 else L.c += L.sg;
             }
             // ---------------- leave the current chunk
-            if (L.need_advance) {
-                L.need_advance = false;
+            if (pick == ST_ADV && L.state == ST_ADV) {
                 bool done = false;
-                if (L.nonempty && L.t1 <= L.tend) {                  // exit side face
+                if (L.t1 <= L.tend) {                                // exit side face
                     const bool far_side = L.exit_axis == 0 ? L.stepx > 0 : L.stepy > 0;
                     const float along = L.exit_axis == 0 ? L.fyo + L.t1 * L.dfy : L.fxo + L.t1 * L.dfx;
                     if (face_hit(L.m, L.ncol, L.nrow, L.exit_axis, far_side, along, (L.lz + L.t1 * L.dz) * (1.f / HF_RANGE))) {
