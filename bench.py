@@ -370,11 +370,12 @@ def run_gpu(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = 1
-            sc = {"lidar": 256, "tick": 32, "step": 32}[wl]
-            v, dt = cpu_units_per_s(wl, sc, 1 if wl == "lidar" else 20, threads)
+            sc = {"lidar": 4096, "tick": 128, "step": 128}[wl]          # ~10-20 s of single-thread CPU work
+            nt = 1 if wl == "lidar" else 60
+            v, dt = cpu_units_per_s(wl, sc, nt, threads)
             line["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
                                     "host_cores_available": os.cpu_count(),
-                                    "sample": f"{sc} cars x {1 if wl == 'lidar' else 20} tick(s), C oracle single thread ({dt:.1f} s)"}
+                                    "sample": f"{sc} cars x {nt} tick(s), C oracle single thread ({dt:.1f} s)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
