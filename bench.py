@@ -12,6 +12,8 @@ One "step" = one pass of the hot path over the whole fleet:
   workload step  : vehicle step only, 65,536 cars
   workload episode (BASELINE config 4): 1,048,576 cars IN TOTAL over the N ranks (strong scaling) on circle /
                  small-circle alternating by world index, full tick, lap statistics gathered once at the end
+  workload race  (BASELINE config 5, partial): 32,768 worlds x 8 cars IN TOTAL on track.png's start grid, the cars
+                 see each other's lidar cylinders and are ranked per world; car-car contacts are NOT generated
 Cars are sharded over the N ranks with no collective on the step path (weak scaling: the per-GPU
 fleet is fixed); only the final timing / stats are gathered.
 """
@@ -382,7 +384,7 @@ def run_gpu(args):
 
 
 # ----------------------------------------------------------------------------- BASELINE config 4: one sharded episode
-def run_episode(args):
+def run_episode(args, kind="episode"):
     """1,048,576 independent cars (total, strong scaling) on circle / small-circle alternating by GLOBAL world index,
     contiguous blocks of worlds per rank, no collective on the step path; the episode's lap statistics are gathered
     once at the end (NCCL all_gather, ft_grandprix_b200.sharding)."""
@@ -399,17 +401,35 @@ def run_episode(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = ft._lib.load()
-    tracks = [ft.Track.bundled("circle"), ft.Track.bundled("small-circle")]
-    nworlds = args.cars
-    race = ShardedRace(nworlds, 1, 2, lambda n, tid, first: ft.Fleet(Geometry(tracks, device=local), n, device=local, track_id=tid, driver="nidc"))
-    fleet = race.fleet
-    n = fleet.ncars
-    xy = np.zeros((n, 2)); yaw = np.zeros(n)
-    for t in range(2):
-        sel = np.nonzero(race.track_id == t)[0]
-        a, b, _ = make_poses(tracks[t].path, len(sel), seed=2 + 1000 * rank + t, level=True)
-        xy[sel] = a; yaw[sel] = b
+    if kind == "race":
+        # BASELINE config 5 (without car-car contacts, which this round does not generate): worlds of 8 cars on the
+        # reference start grid of track.png (custom.py:1232-1245), drivers alternating nidc / fast as in
+        # template/cars/cars.json; the cars see each other's lidar cylinders and are ranked per world
+        cpw, tracks = 8, [ft.Track.bundled("track")]
+        nworlds = args.cars // cpw
+        race = ShardedRace(nworlds, cpw, 1, lambda n, tid, first: ft.Fleet(Geometry(tracks, device=local), n, cars_per_world=cpw,
+                                                                           device=local, driver="nidc"))
+        fleet = race.fleet
+        n = fleet.ncars
+        grid = np.array([tracks[0].start_pose(c) for c in range(cpw)])
+        rng = np.random.default_rng(3 + 1000 * rank)
+        xy = np.tile(grid[:, :2], (n // cpw, 1)) + rng.normal(0, 0.01, (n, 2))
+        yaw = np.tile(grid[:, 2], n // cpw) + rng.normal(0, 0.02, n)
+        fleet.set_driver_kinds(["nidc" if c % 2 == 0 else "fast" for c in range(cpw)] * (n // cpw))
+    else:
+        cpw, tracks = 1, [ft.Track.bundled("circle"), ft.Track.bundled("small-circle")]
+        nworlds = args.cars
+        race = ShardedRace(nworlds, 1, 2, lambda n, tid, first: ft.Fleet(Geometry(tracks, device=local), n, device=local, track_id=tid, driver="nidc"))
+        fleet = race.fleet
+        n = fleet.ncars
+        xy = np.zeros((n, 2)); yaw = np.zeros(n)
+        for t in range(2):
+            sel = np.nonzero(race.track_id == t)[0]
+            a, b, _ = make_poses(tracks[t].path, len(sel), seed=2 + 1000 * rank + t, level=True)
+            xy[sel] = a; yaw[sel] = b
     fleet.reset(xy, yaw)
+    xy0 = fleet.qpos[:, :2].clone()
+    ncars_total = nworlds * cpw
     stream = fleet.stream
     sampler = ClockSampler(local); sampler.start()
     with torch.cuda.stream(stream):
@@ -458,15 +478,18 @@ def run_episode(args):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, launches, gather_ms = float(tt[0]), float(tt[1]), int(tt[2]), float(tt[3])
-    value = nworlds * args.steps / (dev_ms * 1e-3)
+    value = ncars_total * args.steps / (dev_ms * 1e-3)
     peak, peak_src = peaks()
     achieved = value * BYTES["tick"] / 1e9
     laps = stats[:, STAT_FIELDS.index("laps")]
     line = {"metric": "car-steps/s", "value": value, "unit": "car-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"sharded episode, {nworlds} cars in total on circle/small-circle alternating by world index, "
-                                   f"full tick, stats gathered once (BASELINE config 4)", "cars_total": nworlds,
+            "config": {"workload": (f"sharded episode, {nworlds} cars in total on circle/small-circle alternating by world index, "
+                                    f"full tick, stats gathered once (BASELINE config 4)") if kind == "episode" else
+                                   (f"race worlds, {nworlds} worlds x 8 cars in total on track.png, start grid, nidc/fast alternating, cars see "
+                                    f"each other's lidar cylinders, per-world ranking; NO car-car contacts (BASELINE config 5, partial)"),
+                       "cars_total": ncars_total,
                        "cars_per_gpu": n, "beams": 90, "driver": "nidc (device)",
                        "l2": "fleet state per GPU (>= 190 MB at 8 GPUs) exceeds the 126 MB L2", "timing": "CUDA events around the K ticks; max over ranks",
                        "sharding": f"{world} contiguous blocks of worlds, no collective on the step path"},
@@ -474,12 +497,13 @@ def run_episode(args):
                          "traffic": None, "peak_source": peak_src, "kernel": "whole tick (per GPU)",
                          "algorithmic_bytes_per_unit": BYTES["tick"],
                          "note": "latency/issue-bound path: algorithmic HBM traffic is far below peak by construction (SURVEY 8d)"},
-            "e2e": {"value": nworlds * e2e_steps / (e2e_ms * 1e-3), "unit": "car-steps/s", "h2d_bytes_per_step": 0,
+            "e2e": {"value": ncars_total * e2e_steps / (e2e_ms * 1e-3), "unit": "car-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": n * 90 * 4 + fleet.lap.numel() * 4, "steps": e2e_steps,
                     "how": "fleet.tick + ranges and lap state to pinned host memory every step, wall clock"},
             "gpu_launches": launches, "clocks": clocks, "rays_per_s": value * 90,
             "episode": {"gather_ms": gather_ms, "stats_rows": int(stats.shape[0]), "stats_bytes": int(stats.numel() * 4),
-                        "laps_max": int(laps.max()), "cars_moved": int((stats[:, STAT_FIELDS.index("completion")] != 0).sum())}}
+                        "laps_max": int(laps.max()),
+                        "cars_moved_5cm_this_rank": int(((fleet.qpos[:, :2] - xy0).norm(dim=1) > 0.05).sum())}}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -492,16 +516,16 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("FTGP_WORKLOAD", "tick"), choices=["tick", "lidar", "step", "episode"])
+    ap.add_argument("--workload", default=os.environ.get("FTGP_WORKLOAD", "tick"), choices=["tick", "lidar", "step", "episode", "race"])
     ap.add_argument("--cars", type=int, default=None)
     ap.add_argument("--settle", type=int, default=200, help="untimed ticks before timing (tick/step workloads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused-check", action="store_true", help="assert that ftgp_tick == the four separate calls, bit for bit")
     args = ap.parse_args()
     if args.cars is None:
-        args.cars = {"lidar": 4096, "episode": 1048576}.get(args.workload, 65536)
-    if args.workload == "episode" and args.impl != "reference":
-        return run_episode(args)
+        args.cars = {"lidar": 4096, "episode": 1048576, "race": 262144}.get(args.workload, 65536)
+    if args.workload in ("episode", "race") and args.impl != "reference":
+        return run_episode(args, args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:
