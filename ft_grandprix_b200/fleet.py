@@ -205,6 +205,23 @@ class Fleet:
                                             time=self.steps / TIMESTEP))          # custom.py:1397 (sic)
         return out
 
+    def snapshot_tensors(self):
+        """The fields of VehicleStateSnapshot (ft_grandprix/vehicle.py:3-12, custom.py:132-160) for the whole fleet as
+        device tensors, for batched v2 drivers `process_lidar(ranges, state)`: nothing leaves the GPU.  `velocity`
+        aliases fleet.qvel like the reference's view of `joint.qvel[0:3]`."""
+        with torch.cuda.stream(self.stream):
+            w, x, y, z = (self.qpos[:, 3], self.qpos[:, 4], self.qpos[:, 5], self.qpos[:, 6])
+            # quaternion_to_euler (custom.py:62-76): ZYX, asin clamped to +-1
+            roll = torch.atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y))
+            pitch = torch.asin(torch.clamp(2 * (w * y - z * x), -1.0, 1.0))
+            yaw = torch.atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))
+            comp = self.lap[:, LAP["completion"]]
+            lap_completion = torch.where(self.lap[:, LAP["good_start"]] != 0, comp, comp - 100)   # custom.py:132-140
+            laps = self.lap[:, LAP["laps"]]
+            return {"laps": laps, "velocity": self.qvel[:, 0:3], "yaw": yaw, "pitch": pitch, "roll": roll,
+                    "lap_completion": lap_completion, "absolute_completion": laps * 100 + lap_completion,
+                    "time": self.steps / TIMESTEP}                                            # custom.py:1397 (sic)
+
     def state_dict(self):
         self.sync()
         return {k: getattr(self, k).cpu() for k in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "times",

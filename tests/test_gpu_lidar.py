@@ -219,3 +219,30 @@ def test_lidar_four_tracks_geometry_read_from_global_memory(ft, otracks):
     for k, nm in enumerate(names):
         want[tid == k] = otracks[nm].scan(poses[tid == k])
     _check(got, want)
+
+
+def test_snapshot_tensors_match_host_snapshots(ft):
+    """v2 driver input on device == the per-car VehicleStateSnapshot objects of the host shim."""
+    t = ft.Track.bundled("track")
+    n = 64
+    fleet = ft.Fleet(t, n)
+    fleet.reset_grid() if n <= 40 else None
+    rng = np.random.default_rng(5)
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    fleet.qpos[:, 3:7] = torch.from_numpy(q).to(fleet.device)
+    fleet.qvel[:, :3] = torch.from_numpy(rng.normal(size=(n, 3))).to(fleet.device)
+    from ft_grandprix_b200.fleet import LAP
+    fleet.lap[:, LAP["laps"]] = torch.from_numpy(rng.integers(0, 5, n).astype(np.int32)).to(fleet.device)
+    fleet.lap[:, LAP["completion"]] = torch.from_numpy(rng.integers(0, 100, n).astype(np.int32)).to(fleet.device)
+    fleet.lap[:, LAP["good_start"]] = torch.from_numpy(rng.integers(0, 2, n).astype(np.int32)).to(fleet.device)
+    fleet.steps = 123
+    torch.cuda.synchronize()
+    d = fleet.snapshot_tensors(); fleet.sync()
+    host = fleet.snapshots()
+    for i, sn in enumerate(host):
+        assert int(d["laps"][i]) == sn.laps and int(d["lap_completion"][i]) == sn.lap_completion
+        assert int(d["absolute_completion"][i]) == sn.absolute_completion
+        for k in ("yaw", "pitch", "roll"):
+            assert abs(float(d[k][i]) - getattr(sn, k)) < 1e-12
+        assert np.array_equal(d["velocity"][i].cpu().numpy(), sn.velocity)
+    assert d["time"] == host[0].time
