@@ -304,9 +304,14 @@ def run_gpu(args):
         ranges_h = torch.empty(cars, 90, dtype=torch.float32).pin_memory()
         lap_h = torch.empty_like(fleet.lap, device="cpu").pin_memory()
         def e2e_step():
+            if wl == "tick":
+                # the public per-tick call with host delivery: copies overlap the kernels that do not touch the arrays;
+                # the host waits for THIS tick's ranges and lap state before the next tick is issued
+                fleet.tick_readback(ranges_h, lap_h)
+                fleet.sync_readback()
+                return
             with torch.cuda.stream(stream):
-                if wl == "step":
-                    fleet.ctrl.copy_(ctrl_h, non_blocking=True)
+                fleet.ctrl.copy_(ctrl_h, non_blocking=True)
                 one_step()
                 ranges_h.copy_(fleet.ranges, non_blocking=True)
                 lap_h.copy_(fleet.lap, non_blocking=True)
@@ -365,7 +370,7 @@ def run_gpu(args):
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/)" if traffic else None,
                          "note": "latency/issue-bound path: algorithmic HBM traffic is far below peak by construction (SURVEY §8 d)"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "how": "C ABI with pinned host buffers, wall clock around H2D + kernels + D2H"},
+                    "steps": e2e_steps, "how": "public API with pinned host buffers, wall clock around H2D + kernels + D2H; the host waits for every tick's ranges and lap state"},
             "gpu_launches": launches, "clocks": clocks, "kernels": kernels}
     if wl != "lidar":
         line["rays_per_s"] = value * 90 if wl == "tick" else 0.0

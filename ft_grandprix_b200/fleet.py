@@ -184,6 +184,40 @@ class Fleet:
         _lib.check(self.lib.ftgp_tick(C.byref(a), int(nticks), self._s), "ftgp_tick")
         self.steps += int(nticks)
 
+    def tick_readback(self, ranges_host, lap_host):
+        """One iteration of the physics loop with this tick's ranges and lap state delivered to pinned host buffers,
+        the copies overlapped with the kernels that do not touch those arrays: the lap state leaves right after the
+        lap kernel, the ranges right after the lidar kernel (the vehicle step runs meanwhile), and only the NEXT
+        tick's lidar / lap kernels wait for the copies.  Call sync_readback() before reading the host buffers."""
+        if not hasattr(self, "_copy_stream"):
+            with torch.cuda.device(self.device):
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._ev = [torch.cuda.Event() for _ in range(4)]      # lap ready, ranges ready, lap copied, ranges copied
+            self._ev[2].record(self._copy_stream); self._ev[3].record(self._copy_stream)
+        s, c = self.stream, self._copy_stream
+        lap_ready, ranges_ready, lap_copied, ranges_copied = self._ev
+        with torch.cuda.stream(s):
+            s.wait_event(lap_copied)                 # the previous copy of the lap state has left
+            self.lap_update()
+            lap_ready.record(s)
+            self.drive()
+            s.wait_event(ranges_copied)              # ... and of the ranges
+            self.lidar()
+            ranges_ready.record(s)
+            self.step(1)
+        with torch.cuda.stream(c):
+            c.wait_event(lap_ready)
+            lap_host.copy_(self.lap, non_blocking=True)
+            lap_copied.record(c)
+            c.wait_event(ranges_ready)
+            ranges_host.copy_(self.ranges, non_blocking=True)
+            ranges_copied.record(c)
+
+    def sync_readback(self):
+        self.stream.synchronize()
+        if hasattr(self, "_copy_stream"):
+            self._copy_stream.synchronize()
+
     # ------------------------------------------------------------------ v2 driver input (custom.py:149-160)
     def snapshots(self):
         self.sync()

@@ -216,3 +216,27 @@ def test_config1_single_car_nidc_on_track(ft, oracle, otracks):
     for f in ("completion", "laps", "start", "good_start", "finished", "ntimes", "off_track"):
         assert got[L[f]] == getattr(lap.s, f), f
     assert np.hypot(*(Q[0, :2] - np.array([x, y]))) > 5.0         # it drove away from the grid
+
+
+def test_tick_readback_equals_tick_and_delivers_host_copies(ft):
+    """Fleet.tick_readback (copies overlapped with the kernels) == Fleet.tick bit for bit; the pinned host buffers hold
+    this tick's ranges and lap state."""
+    t = ft.Track.bundled("track")
+    n = 2048
+    rng = np.random.default_rng(7)
+    idx = rng.integers(0, 100, n)
+    xy = t.path[idx] + rng.normal(0, 0.1, (n, 2))
+    yaw = rng.uniform(-3, 3, n)
+    a = ft.Fleet(t, n); b = ft.Fleet(t, n)
+    a.reset(xy, yaw); b.reset(xy, yaw)
+    ranges_h = torch.empty(n, 90, dtype=torch.float32).pin_memory()
+    lap_h = torch.empty_like(b.lap, device="cpu").pin_memory()
+    for k in range(12):
+        a.tick(1)
+        b.tick_readback(ranges_h, lap_h)
+        b.sync_readback()
+        assert torch.equal(ranges_h, b.ranges.cpu())
+    a.sync()
+    assert torch.equal(lap_h, a.lap.cpu())               # the lap state of the last tick (written by its lap kernel only)
+    for k in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "times", "status"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
