@@ -1,15 +1,14 @@
 // step.cu -- vehicle-step kernel and the fused per-tick entry point.
 //
 // ftgp_step replaces mujoco.mj_step(model, data) (ft_grandprix/custom.py:1425) for a fleet of
-// independent cars of template/mushr.em.xml; the arithmetic is csrc/mushr_step.cuh (block-arrow
-// Newton solver specialised for the car's fixed topology).  One thread advances one car in fp64;
-// cars never interact on this path, so there is no inter-thread communication at all.
+// independent cars of template/mushr.em.xml; the arithmetic is the block-arrow Newton solver specialised
+// for the car's fixed topology (csrc/mushr_step.cuh), mapped four lanes per car, one per wheel chain
+// (csrc/mushr_step_quad.cuh), in fp64; cars never interact on this path, so nothing crosses a quad.
 // ftgp_tick runs whole iterations of physics_thread (custom.py:1337-1426) without leaving the
 // device: lap update -> built-in driver on last tick's ranges -> ctrl -> rangefinders from the
 // pre-step pose -> mj_step (the reference's one-tick sensor lag is kept).
 #include "common.h"
 #include "mushr_consts.h"
-#include "mushr_step_warp.cuh"
 #include "mushr_step_quad.cuh"
 #include <cstdlib>
 
@@ -96,55 +95,6 @@ struct Walls {                                  // thread-per-car flavour
     }
 };
 
-struct WallsWarp {                              // warp-per-car flavour: lane v probes hull vertex v
-    const uint32_t* blob; const TrackHeader* th;
-    __device__ int operator()(const ModelConsts& mc, WarpShared& S, const double* com, int T, int ncon) const {
-        if (!blob) return ncon;
-        WallHit h;
-        const bool hit = T < MUSHR_CHASSIS_NHULL && wall_probe(blob, th, S.R1, S.p1, T, h);
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        const int slot = ncon + __popc(m & ((1u << T) - 1));
-        if (hit && slot < MAXCON) {
-            S.cdist[slot] = h.dist; S.cmu[slot] = 1.0; S.cdmin[slot] = 0.9; S.ctran[slot] = mc.chassis_invweight0; S.cwheel[slot] = -1;
-            for (int a = 0; a < 3; a++) { S.cpnt[slot][a] = h.pnt[a]; S.cframe[slot][a] = h.nrm[a]; S.cframe[slot][3 + a] = h.t1[a]; S.cframe[slot][6 + a] = h.t2[a]; }
-        }
-        const int n = ncon + __popc(m);
-        return n > MAXCON ? MAXCON : n;
-    }
-};
-
-template <int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
-step_warp_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
-                 double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
-                 const int32_t* __restrict__ lap, const int32_t* __restrict__ perm, int64_t ncars, int nsteps,
-                 int32_t* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    WarpShared* SS = reinterpret_cast<WarpShared*>(smraw);
-    const int T = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    int64_t car = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    const bool live = car < ncars;
-    if (!live) car = ncars - 1;                     // padding warp: same barriers, no stores
-    if (perm) car = perm[car];                      // cars grouped by their last Newton iteration count
-    WarpShared& S = SS[wib];
-    WallsWarp walls{nullptr, nullptr};
-    const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
-    if (blob && !shadowed) {
-        const GeomHeader* gh = reinterpret_cast<const GeomHeader*>(blob);
-        int tid = track_id ? track_id[car] : 0;
-        if (tid < 0 || tid >= gh->ntracks) tid = 0;
-        walls.blob = blob; walls.th = reinterpret_cast<const TrackHeader*>(blob + gh->track_off[tid]);
-    }
-    int st = 0;
-    for (int s = 0; s < nsteps; s++) {
-        StepInfo info;
-        step_car_warp(S, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, T, live, info);
-        __syncthreads();
-        st = (info.iters & 0xFF) | (info.reset ? 0x100 : (st & 0x100)) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24);
-    }
-    if (status && T == 0 && live) status[car] = st;
-}
-
 __global__ void __launch_bounds__(64)
 step_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
             double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
@@ -219,7 +169,7 @@ step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
     if (status && qd.w == 0 && live) status[car] = st;
 }
 
-// The warp-per-car kernel runs the cars of a CTA in lock-step, so a CTA takes as many Newton rounds as its slowest
+// The quad-per-car kernel runs the cars of a CTA in lock-step, so a CTA takes as many Newton rounds as its slowest
 // car.  The iteration count is strongly correlated from one step to the next (measured: mean 2, max over 8 random
 // cars 3.6), so cars are grouped by (last iteration count, in wall contact or not) with a counting sort.
 constexpr int NBIN = 16;
@@ -282,12 +232,13 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     int dev = 0;
     FTGP_CUDA(cudaGetDevice(&dev));
     int rc = ensure_model(dev); if (rc) return rc;
-    // Three implementations of the same arithmetic (all parity-tested), FTGP_STEP_IMPL = quad (default) | thread | warp:
-    //   quad   four lanes per car, one per wheel chain (mushr_step_quad.cuh): factorisations in registers
-    //   thread one thread per car (mushr_step.cuh): fewest instructions, 16.7 KB local frame per thread, DRAM-latency bound
-    //   warp   one warp per car (mushr_step_warp.cuh): state in shared memory, 5.4x the instructions
+    // Two implementations of the same arithmetic (both parity-tested), FTGP_STEP_IMPL = quad (default) | thread:
+    //   quad   four lanes per car, one per wheel chain (mushr_step_quad.cuh): 1.47 ms per 65,536 cars
+    //   thread one thread per car (mushr_step.cuh): 16.7 KB local frame per thread, DRAM-latency bound, 5.3 ms; kept as the
+    //          A/B reference (it is also the source the CPU tests compile for the host)
+    // (a third mapping, one warp per car with the state in shared memory, measured 5.2 ms and was removed: DESIGN.md 3.2)
     static int impl = -1;
-    if (impl < 0) { const char* e = getenv("FTGP_STEP_IMPL"); impl = !e ? 2 : (e[0] == 'w' ? 0 : (e[0] == 't' ? 1 : 2)); }
+    if (impl < 0) { const char* e = getenv("FTGP_STEP_IMPL"); impl = (e && e[0] == 't') ? 1 : 2; }
     const uint32_t* blob = g ? g->d_blob : nullptr;
     if (impl == 2) {
         static int qt = 0, lock = 1;
@@ -313,28 +264,6 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
         if (!threads) { const char* e = getenv("FTGP_STEP_BLOCK"); threads = e ? atoi(e) : 64; if (threads < 32 || threads > 64) threads = 64; }
         step_kernel<<<(unsigned)((ncars + threads - 1) / threads), threads, 0, stream>>>(
             blob, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status);
-    } else {
-        // CTA shape: `warps` cars per CTA (the CTA runs its cars in lock-step phases), register budget by variant
-        static int warps = 0, variant = 0;
-        if (!warps) {
-            const char* e = getenv("FTGP_STEP_WARPS"); warps = e ? atoi(e) : 8; if (warps < 1 || warps > 16) warps = 8;
-            const char* v = getenv("FTGP_STEP_VARIANT"); variant = v ? atoi(v) : 0;
-        }
-        const size_t smem = warps * sizeof(WarpShared);
-        const int32_t* perm = nullptr;
-        if ((rc = order_cars(status, ncars, dev, stream, &perm))) return rc;
-        auto launch = [&](auto kern) -> int {
-            FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            kern<<<(unsigned)((ncars + warps - 1) / warps), warps * 32, smem, stream>>>(
-                blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status);
-            return FTGP_OK;
-        };
-        int rc2;
-        if (variant == 1 && warps <= 8) rc2 = launch(step_warp_kernel<256, 1>);          // 255 registers, no spills
-        else if (variant == 2 && warps <= 12) rc2 = launch(step_warp_kernel<384, 1>);     // 168 registers
-        else rc2 = launch(step_warp_kernel<512, 1>);                                      // 128 registers
-        if (rc2) return rc2;
     }
     count_launch();
     FTGP_CUDA(cudaGetLastError());
