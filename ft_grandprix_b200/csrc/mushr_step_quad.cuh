@@ -53,19 +53,21 @@ constexpr int QP_FRA = 75;           // 6   aref of the friction-loss rows of th
 constexpr int QP_EQ = 81;            // 3   Ackermann equality of a front chain: D (0: none), aref, dP/dx
 constexpr int QP_LIM = 84;           // 6   suspension / front steering limit: D[2] (0: inactive), aref[2], sign[2]
 constexpr int QP_WC = 90;            // 5   wheel-ground contact: D (0: none), aref[4]
-constexpr int QP_VEC = 95;           // 6 x 6 chain parts of the dof vectors below
-constexpr int QP_N = 131;
+constexpr int QP_VEC = 95;           // 4 x 6 chain parts of the dof vectors below
+constexpr int QP_N = 119;
 constexpr int QC_MR = 0;             // 28  root block of M, lower triangle
 constexpr int QC_R6 = 28;            // 4   rows of root dof 6 (steering wheel): friction aref, limit D, aref, sign
-constexpr int QC_VEC = 32;           // 6 x 7 root parts of the dof vectors
-constexpr int QC_N = 74;
+constexpr int QC_VEC = 32;           // 4 x 7 root parts of the dof vectors
+constexpr int QC_N = 60;
 struct QVec { int p, c; };           // dof vector: chain part at P(p + l), root part at C(c + i)
+// qfrc_smooth, the iterate x = qacc, M x, and S = right-hand side / solution of the factor-solve (qacc_smooth, then the
+// gradient / search direction, then the Euler acceleration).  qacc_smooth itself is not kept: the Gauss term
+// (x - qacc_smooth)' M (x - qacc_smooth) / 2 is evaluated as x' (M x / 2 - qfrc_smooth) + qacc_smooth' qfrc_smooth / 2;
+// M s lives in registers between the line search and the update of M x.
 #define VQFS (QVec{QP_VEC, QC_VEC})
-#define VQAS (QVec{QP_VEC + 6, QC_VEC + 7})
-#define VX (QVec{QP_VEC + 12, QC_VEC + 14})
-#define VMA (QVec{QP_VEC + 18, QC_VEC + 21})
-#define VS (QVec{QP_VEC + 24, QC_VEC + 28})
-#define VMV (QVec{QP_VEC + 30, QC_VEC + 35})
+#define VX (QVec{QP_VEC + 6, QC_VEC + 7})
+#define VMA (QVec{QP_VEC + 12, QC_VEC + 14})
+#define VS (QVec{QP_VEC + 18, QC_VEC + 21})
 // model constants of the friction-loss rows (pos = 0, so impedance and regulariser never change): (D, R f, f) for
 // chain slot (w, l) at 3 (6 w + l), root dof 6 at 72
 constexpr int QK_N = 75;
@@ -115,7 +117,7 @@ FT_HDN void quad_const_entry(const ModelConsts& mc, int g, double* t) {      // 
 // chassis (wall) contacts owned by the lane: rare, kept in the lane's frame and only touched when nch > 0
 constexpr int QMAXCH = 2;            // MAXCON = 8 contacts over four lanes
 struct QChassis { double D[QMAXCH], aref[QMAXCH][4], J[QMAXCH][3][6], dx[QMAXCH][3], ds[QMAXCH][3]; };
-struct QState { double cost, gauss; unsigned mask; int nch; };
+struct QState { double cost, gauss, c0; unsigned mask; int nch; };     // c0 = qacc_smooth' qfrc_smooth / 2
 constexpr int QB_FR = 0, QB_FR6 = 6, QB_LIM = 7, QB_LIM6 = 9, QB_WC = 10, QB_CH = 14;
 constexpr double WC_MU = 0.5, CH_MU = 1.0;
 constexpr double REF_B = 2 / (0.95 * 0.02);          // kbi(): B of the default solref with dmax 0.95
@@ -225,10 +227,10 @@ FT_QN double rows_eval(const Q& qd, const QChassis& ch, int nch, QVec X, double*
     return cost;
 }
 
-// Y = M X with M in shared memory
+// y = M X with M in shared memory, result in registers (root part replicated)
 template <class Q>
-FT_QN void quad_mul(const Q& qd, QVec X, QVec Y, bool on) {
-    double xr[NR], xc[NC], yr[NR], yc[NC], part[6];
+FT_QN void quad_mul(const Q& qd, QVec X, double* yr, double* yc) {
+    double xr[NR], xc[NC], part[6];
     vec_load(qd, X, xr, xc);
 #pragma unroll
     for (int j = 0; j < 6; j++) part[j] = 0;
@@ -249,8 +251,6 @@ FT_QN void quad_mul(const Q& qd, QVec X, QVec Y, bool on) {
         if (i < 6) s += qd.sum(part[i]);
         yr[i] = s;
     }
-    qd.sync();
-    vec_store(qd, Y, yr, yc, on);
 }
 
 // cost, Gauss term and gradient (into S) at X (needs MA = M X)
@@ -262,18 +262,19 @@ FT_QN void quad_evaluate(const Q& qd, const QChassis& ch, QState& st, bool on) {
     double g = 0;
 #pragma unroll
     for (int l = 0; l < NC; l++) {
-        const double d = qd.P(VMA.p + l) - qd.P(VQFS.p + l);
-        g += d * (qd.P(VX.p + l) - qd.P(VQAS.p + l));
-        g_c[l] = d - fc[l];
+        const double ma = qd.P(VMA.p + l), qf = qd.P(VQFS.p + l);
+        g += qd.P(VX.p + l) * (0.5 * ma - qf);
+        g_c[l] = (ma - qf) - fc[l];
     }
     cc = qd.sum(cc); g = qd.sum(g);
 #pragma unroll
     for (int i = 0; i < NR; i++) {
-        const double d = qd.C(VMA.c + i) - qd.C(VQFS.c + i);
-        g += d * (qd.C(VX.c + i) - qd.C(VQAS.c + i));
-        g_r[i] = d - qd.sum(fr[i]);
+        const double ma = qd.C(VMA.c + i), qf = qd.C(VQFS.c + i);
+        g += qd.C(VX.c + i) * (0.5 * ma - qf);
+        g_r[i] = (ma - qf) - qd.sum(fr[i]);
     }
-    if (on) { st.mask = mask; st.gauss = 0.5 * g; st.cost = cc + st.gauss; }
+    g += st.c0;
+    if (on) { st.mask = mask; st.gauss = g; st.cost = cc + g; }
     qd.sync();
     vec_store(qd, VS, g_r, g_c, on);
 }
@@ -548,7 +549,7 @@ FT_HD void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, const QLs& L, 
 // MuJoCo's PrimalSearch as a state machine: every tick of the warp-uniform loop evaluates the cost once, at the
 // point each quad asked for, then each quad moves on by itself (no collectives in the transitions).
 template <class Q>
-FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, double scale, bool on) {
+FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, double scale, bool on, double* mv_r, double* mv_c) {
     QLs L;
     double snorm;
     {
@@ -561,13 +562,13 @@ FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, doubl
 #pragma unroll
         for (int i = 0; i < NR; i++) sn += sr[i] * sr[i];
         snorm = sqrt(sn);
-        quad_mul(qd, VS, VMV, on);
+        quad_mul(qd, VS, mv_r, mv_c);
         double g1 = 0, g2 = 0;
 #pragma unroll
-        for (int l = 0; l < NC; l++) { g1 += sc[l] * (qd.P(VMA.p + l) - qd.P(VQFS.p + l)); g2 += 0.5 * sc[l] * qd.P(VMV.p + l); }
+        for (int l = 0; l < NC; l++) { g1 += sc[l] * (qd.P(VMA.p + l) - qd.P(VQFS.p + l)); g2 += 0.5 * sc[l] * mv_c[l]; }
         g1 = qd.sum(g1); g2 = qd.sum(g2);
 #pragma unroll
-        for (int i = 0; i < NR; i++) { g1 += sr[i] * (qd.C(VMA.c + i) - qd.C(VQFS.c + i)); g2 += 0.5 * sr[i] * qd.C(VMV.c + i); }
+        for (int i = 0; i < NR; i++) { g1 += sr[i] * (qd.C(VMA.c + i) - qd.C(VQFS.c + i)); g2 += 0.5 * sr[i] * mv_r[i]; }
         L.g0 = st.gauss; L.g1 = g1; L.g2 = g2;
         vec_load(qd, VX, xr, xc);
         const int w = qd.lane();
@@ -859,7 +860,7 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
         f = f > 500.0 ? 500.0 : (f < -500.0 ? -500.0 : f);
         fs_c[2] += 0.04 * 0.25 * f;
         vec_store(qd, VQFS, fs_r, fs_c);
-        vec_store(qd, VQAS, fs_r, fs_c);             // right-hand side of qacc_smooth = M^-1 qfrc_smooth
+        vec_store(qd, VS, fs_r, fs_c);               // right-hand side of qacc_smooth = M^-1 qfrc_smooth
     }
     // ---- rows
     double K, B, imp, R;
@@ -1048,7 +1049,7 @@ FT_HDN void step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, doub
     int mode = 0;
     bool first = true;
     for (;;) {
-        quad_factor_solve(qd, ch, st, mode == 3 ? 2 : mode, mode == 0 ? VQAS : VS, mode == 1 ? -1.0 : 1.0, mode < 3);
+        quad_factor_solve(qd, ch, st, mode == 3 ? 2 : mode, VS, mode == 1 ? -1.0 : 1.0, mode < 3);
         if (mode == 2) mode = 3;
         if (!first && !qd.cany(mode == 1)) break;
         bool upd = false;
@@ -1064,24 +1065,31 @@ FT_HDN void step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, doub
                 qd.sync();
                 vec_store(qd, VX, wr, wc);
             }
-            quad_mul(qd, VX, VMA, true);
             double fr_[NR], fc_[NC]; unsigned m_;
-            double cw = rows_eval(qd, ch, st.nch, VX, fr_, fc_, m_), gw = 0;
-            for (int l = 0; l < NC; l++) gw += (qd.P(VMA.p + l) - qd.P(VQFS.p + l)) * (qd.P(VX.p + l) - qd.P(VQAS.p + l));
-            cw = qd.sum(cw); gw = qd.sum(gw);
-            for (int i = 0; i < NR; i++) gw += (qd.C(VMA.c + i) - qd.C(VQFS.c + i)) * (qd.C(VX.c + i) - qd.C(VQAS.c + i));
-            cw += 0.5 * gw;
-            const double cs = qd.sum(rows_eval(qd, ch, st.nch, VQAS, fr_, fc_, m_));
+            {
+                double mr[NR], mcn[NC];
+                quad_mul(qd, VX, mr, mcn);
+                qd.sync();
+                vec_store(qd, VMA, mr, mcn);
+            }
+            // S holds qacc_smooth: c0 = qacc_smooth' qfrc_smooth / 2, cost of the warm start and of qacc_smooth
+            double c0 = 0, gw = 0;
+            for (int l = 0; l < NC; l++) { c0 += qd.P(VS.p + l) * qd.P(VQFS.p + l); gw += qd.P(VX.p + l) * (0.5 * qd.P(VMA.p + l) - qd.P(VQFS.p + l)); }
+            c0 = qd.sum(c0); gw = qd.sum(gw);
+            for (int i = 0; i < NR; i++) { c0 += qd.C(VS.c + i) * qd.C(VQFS.c + i); gw += qd.C(VX.c + i) * (0.5 * qd.C(VMA.c + i) - qd.C(VQFS.c + i)); }
+            st.c0 = 0.5 * c0;
+            const double cw = qd.sum(rows_eval(qd, ch, st.nch, VX, fr_, fc_, m_)) + (gw + st.c0);
+            const double cs = qd.sum(rows_eval(qd, ch, st.nch, VS, fr_, fc_, m_));
             double r[NR], c[NC], r2[NR], c2[NC];
-            vec_load(qd, VQAS, r, c); vec_load(qd, VQFS, r2, c2);
+            vec_load(qd, VS, r, c); vec_load(qd, VQFS, r2, c2);
             qd.sync();
             vec_store(qd, VX, r, c, cw > cs); vec_store(qd, VMA, r2, c2, cw > cs);
             mode = live ? 1 : 3; first = false;
         } else {
-            const double alpha = quad_line_search(qd, ch, st, scale, mode == 1);
             double xr[NR], xc[NC], mr[NR], mcn[NC];
-            for (int i = 0; i < NR; i++) { xr[i] = qd.C(VX.c + i) + alpha * qd.C(VS.c + i); mr[i] = qd.C(VMA.c + i) + alpha * qd.C(VMV.c + i); }
-            for (int l = 0; l < NC; l++) { xc[l] = qd.P(VX.p + l) + alpha * qd.P(VS.p + l); mcn[l] = qd.P(VMA.p + l) + alpha * qd.P(VMV.p + l); }
+            const double alpha = quad_line_search(qd, ch, st, scale, mode == 1, mr, mcn);      // mr, mcn: M s
+            for (int i = 0; i < NR; i++) { xr[i] = qd.C(VX.c + i) + alpha * qd.C(VS.c + i); mr[i] = qd.C(VMA.c + i) + alpha * mr[i]; }
+            for (int l = 0; l < NC; l++) { xc[l] = qd.P(VX.p + l) + alpha * qd.P(VS.p + l); mcn[l] = qd.P(VMA.p + l) + alpha * mcn[l]; }
             upd = mode == 1 && alpha != 0;
             qd.sync();
             vec_store(qd, VX, xr, xc, upd); vec_store(qd, VMA, mr, mcn, upd);

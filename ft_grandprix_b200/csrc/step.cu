@@ -133,7 +133,7 @@ struct WallsQuad {                              // quad-per-car flavour: probe o
 
 // Quad-per-car: four lanes (one per wheel chain) advance one car, 8 cars per warp; see mushr_step_quad.cuh.
 // Shared memory: [slot][thread] for the lane-private slots, [slot][car] for the per-car slots, then the table of
-// friction-loss row constants.  1 250 B per lane: five 32-thread CTAs (40 cars) per SM.
+// friction-loss row constants.  1 072 B per lane: one 216-thread CTA (54 cars) per SM.
 template <int NT> constexpr size_t quad_smem_bytes() { return (size_t)(NT * QP_N + NT / 4 * QC_N + QK_N + 1) * sizeof(double); }
 
 template <int NT, bool LOCK>
@@ -243,7 +243,7 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     if (impl == 2) {
         static int qt = 0, lock = 1;
         if (!qt) {
-            const char* e = getenv("FTGP_STEP_QT"); qt = e ? atoi(e) : 192; if (qt != 128 && qt != 192) qt = 192;
+            const char* e = getenv("FTGP_STEP_QT"); qt = e ? atoi(e) : 216; if (qt != 128 && qt != 192 && qt != 216) qt = 216;
             const char* l = getenv("FTGP_STEP_LOCK"); lock = (l && l[0] == '0') ? 0 : 1;
         }
         const int32_t* perm = nullptr;
@@ -257,6 +257,7 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
         };
         int rc2;
         if (qt == 128) rc2 = launch(step_quad_kernel<128, true>, quad_smem_bytes<128>());
+        else if (qt == 216) rc2 = launch(step_quad_kernel<216, true>, quad_smem_bytes<216>());   // 54 cars: 6 warps + 24 lanes
         else rc2 = lock ? launch(step_quad_kernel<192, true>, quad_smem_bytes<192>()) : launch(step_quad_kernel<192, false>, quad_smem_bytes<192>());
         if (rc2) return rc2;
     } else if (impl == 1) {
