@@ -1,0 +1,97 @@
+"""CPU: the oracle's mj_ray restatement (oracle/ray.c: per-hfield top-box clipping, cell-range traversal, side faces)
+against an INDEPENDENT brute-force ray caster: every height-field triangle and every side-face trapezoid of every
+chunk is built explicitly from the wall mask with the pixel -> world mapping of SURVEY C.2 / B.10 (chunk.py:49-64,
+mushr.em.xml:19-20,55,92), and each ray is intersected with all ~400,000 triangles (Moeller-Trumbore, two-sided,
+numpy).  Same specification, entirely different algorithm and code: it pins the traversal logic of ray.c (and
+therefore of the CUDA lidar kernel that is tested against ray.c), not MuJoCo's own reading of the model."""
+import numpy as np
+import pytest
+
+from conftest import random_poses
+
+HF_RANGE, HF_Z0, PLANE_Z = 0.3, -0.1, 0.01
+
+
+def chunk_mesh(wall, scale=2.0, px=20):
+    """All triangles of all non-empty chunks: [n, 3, 3] world coordinates."""
+    H, W = wall.shape
+    hc, vc = -(-W // px), -(-H // px)
+    size_x, size_y = 20.0 * scale / hc, 20.0 * scale / vc
+    tris = []
+    for i in range(hc):
+        for j in range(vc):
+            blk = wall[j * px:(j + 1) * px, i * px:(i + 1) * px]
+            if not blk.any():
+                continue
+            nrow, ncol = blk.shape
+            if nrow < 2 or ncol < 2:
+                continue
+            # hfield rows are flipped: row r = nrow-1-k is PNG row k; elevation normalised to [0, 1] (constant chunk -> 0)
+            e = blk[::-1].astype(np.float64)
+            e = (e - e.min()) / (e.max() - e.min()) if e.max() > e.min() else np.zeros_like(e)
+            z = HF_Z0 + HF_RANGE * e
+            xs = size_x * i - size_x / 2 + np.arange(ncol) * size_x / (ncol - 1)
+            ys = -size_y * j - size_y / 2 + np.arange(nrow) * size_y / (nrow - 1)
+            P = np.stack([np.broadcast_to(xs[None, :], (nrow, ncol)), np.broadcast_to(ys[:, None], (nrow, ncol)), z], -1)
+            a, b, c, d = P[:-1, :-1], P[:-1, 1:], P[1:, :-1], P[1:, 1:]          # (c,r) (c+1,r) (c,r+1) (c+1,r+1)
+            keep = (e[:-1, :-1] + e[:-1, 1:] + e[1:, :-1] + e[1:, 1:]) > 0     # flat cells at the base are below the ground plane
+            tris.append(np.stack([a, d, b], -2)[keep]); tris.append(np.stack([a, d, c], -2)[keep])
+            # vertical side faces of the top box: from the base (z = HF_Z0) up to the boundary elevation profile
+            for border in (P[:, 0], P[:, -1], P[0, :], P[-1, :]):
+                p0, p1 = border[:-1], border[1:]
+                use = (p0[:, 2] > HF_Z0) | (p1[:, 2] > HF_Z0)
+                b0, b1 = p0.copy(), p1.copy(); b0[:, 2] = HF_Z0; b1[:, 2] = HF_Z0
+                tris.append(np.stack([b0, b1, p1], -2)[use]); tris.append(np.stack([b0, p1, p0], -2)[use])
+    return np.concatenate(tris, 0)
+
+
+def brute_ray(tris, o, d):
+    """Nearest non-negative hit of ray o + s d with the triangles and the ground plane, or -1."""
+    v0, e1, e2 = tris[:, 0], tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0]
+    p = np.cross(d, e2)
+    det = (e1 * p).sum(1)
+    ok = np.abs(det) > 1e-300
+    inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+    t = o - v0
+    u = (t * p).sum(1) * inv
+    q = np.cross(t, e1)
+    v = (q * d).sum(1) * inv
+    s = (e2 * q).sum(1) * inv
+    hit = ok & (u >= 0) & (v >= 0) & (u + v <= 1) & (s >= 0)
+    best = s[hit].min() if hit.any() else np.inf
+    if d[2] < 0:                                                     # ground plane z = 0.01, front side, 300 m half-size
+        sp = (PLANE_Z - o[2]) / d[2]
+        h = o + sp * d
+        if sp >= 0 and abs(h[0]) <= 300 and abs(h[1]) <= 300:
+            best = min(best, sp)
+    return best if np.isfinite(best) else -1.0
+
+
+@pytest.mark.parametrize("name,nposes", [("track", 5), ("small-circle", 3)])
+def test_oracle_scan_matches_bruteforce_triangle_mesh(name, nposes, otracks, walls):
+    wall, svg = walls[name]
+    t = otracks[name]
+    path = t.centreline(svg)
+    tris = chunk_mesh(wall)
+    assert len(tris) > 50000
+    poses = random_poses(path, nposes, seed=77)
+    got = t.scan(poses)                                              # oracle/ray.c, 90 beams per pose
+    rx, rz, lr = -0.0525, 0.065, 0.03                                # mushr.em.xml:101-103,114-116
+    worst, edge = 0.0, 0
+    for k, ps in enumerate(poses):
+        w, x, y, z = ps[3:7] / np.linalg.norm(ps[3:7])
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        for j in range(90):
+            b = np.radians(4 * j - 90)
+            d = R @ np.array([np.sin(b), -np.cos(b), 0.0])
+            o = ps[:3] + R @ np.array([rx - lr * np.sin(b), lr * np.cos(b), rz])
+            want = brute_ray(tris, o, d)
+            if (want < 0) != (got[k, j] < 0) or abs(want - got[k, j]) > 1e-9:
+                # a ray through a shared triangle edge / vertex may legitimately pick either facet: tolerate a few
+                edge += 1
+                assert abs(want - got[k, j]) < 5e-3, (k, j, want, got[k, j])
+            else:
+                worst = max(worst, abs(want - got[k, j]))
+    assert edge <= 2 and worst < 1e-9, (edge, worst)
