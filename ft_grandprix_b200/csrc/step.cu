@@ -11,6 +11,7 @@
 #include "mushr_consts.h"
 #include "mushr_step_quad.cuh"
 #include <cstdlib>
+#include <mutex>
 
 namespace ftgp {
 using namespace mushr;
@@ -200,8 +201,30 @@ __global__ void order_scatter_kernel(const int32_t* __restrict__ status, int64_t
     __syncthreads();
     if (i < ncars) perm[base[bin] + rank] = (int32_t)i;
 }
-struct OrderScratch { int32_t* perm = nullptr; int32_t* counters = nullptr; int64_t cap = 0; };
-static OrderScratch g_order[16];
+// one scratch per (device, stream): fleets stepped concurrently on different streams must not share it
+struct OrderScratch { int dev = -1; cudaStream_t stream = nullptr; int32_t* perm = nullptr; int32_t* counters = nullptr; int64_t cap = 0; uint64_t used = 0; };
+static OrderScratch g_order[64];
+static std::mutex g_order_mutex;
+static uint64_t g_order_clock = 0;
+static OrderScratch* order_scratch(int dev, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_order_mutex);
+    OrderScratch* lru = &g_order[0];
+    for (auto& o : g_order) {
+        if (o.dev == dev && o.stream == stream) { o.used = ++g_order_clock; return &o; }
+        if (o.used < lru->used) lru = &o;
+    }
+    // not found: take a free slot, else recycle the least recently used one (cudaFree waits for work that uses it)
+    if (lru->dev >= 0) {
+        int cur = 0;
+        cudaGetDevice(&cur); cudaSetDevice(lru->dev);
+        if (lru->perm) cudaFree(lru->perm);
+        if (lru->counters) cudaFree(lru->counters);
+        cudaSetDevice(cur);
+    }
+    *lru = OrderScratch();
+    lru->dev = dev; lru->stream = stream; lru->used = ++g_order_clock;
+    return lru;
+}
 
 // cars grouped by (last Newton iteration count, wall contact) for the kernels that run several cars in lock-step
 static int order_cars(const int32_t* status, int64_t ncars, int dev, cudaStream_t stream, const int32_t** perm) {
@@ -209,7 +232,9 @@ static int order_cars(const int32_t* status, int64_t ncars, int dev, cudaStream_
     static int use_order = -1;
     if (use_order < 0) { const char* e = getenv("FTGP_STEP_ORDER"); use_order = (e && e[0] == '0') ? 0 : 1; }
     if (!use_order || !status || ncars < 1024 || ncars >= (int64_t)1 << 31 || dev >= 16) return FTGP_OK;
-    OrderScratch& o = g_order[dev];
+    OrderScratch* op = order_scratch(dev, stream);
+    if (!op) return FTGP_OK;
+    OrderScratch& o = *op;
     if (o.cap < ncars) {
         if (o.perm) cudaFree(o.perm);
         if (!o.counters) FTGP_CUDA(cudaMalloc(&o.counters, 2 * NBIN * sizeof(int32_t)));

@@ -240,3 +240,31 @@ def test_tick_readback_equals_tick_and_delivers_host_copies(ft):
     assert torch.equal(lap_h, a.lap.cpu())               # the lap state of the last tick (written by its lap kernel only)
     for k in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "times", "status"):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_two_fleets_on_two_streams_do_not_share_scratch(ft):
+    """Fleets stepped concurrently on their own streams (interleaved launches, no sync in between) give what each gives
+    alone: the step kernel's car-regrouping scratch is per (device, stream)."""
+    t = ft.Track.bundled("track")
+    from conftest import random_poses
+    res = {}
+    for mode in ("alone", "interleaved"):
+        fleets = []
+        for n, seed in ((4096, 51), (6144, 52)):
+            poses = random_poses(t.path, n, seed=seed, level=True)
+            f = ft.Fleet(t, n)
+            f.reset(poses[:, :2], 2 * np.arctan2(poses[:, 6], poses[:, 3]))
+            fleets.append(f)
+        if mode == "alone":
+            for f in fleets:
+                f.tick(30); f.sync()
+        else:
+            for _ in range(30):
+                for f in fleets:
+                    f.tick(1)
+            for f in fleets:
+                f.sync()
+        res[mode] = [{k: getattr(f, k).clone() for k in ("qpos", "qvel", "warm", "ranges", "lap", "status")} for f in fleets]
+    for a, b in zip(res["alone"], res["interleaved"]):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
