@@ -201,7 +201,7 @@ __device__ __forceinline__ double ray_cylinder(double px, double py, double pz, 
 // other blocks' instructions are not issued at all for a handful of lanes
 // (the first version traced beams l, l+32, l+64 per lane with nested loops: 6.5 of 32 lanes active).
 enum { ST_IDLE = 0, ST_CHUNK = 1, ST_SWEEP = 2, ST_ADV = 3 };
-constexpr int BATCH = 8;              // max cars per warp batch (a batch holds whole worlds: cars_per_world 1, 2, 4 or 8)
+constexpr int BATCH = 8;              // max cars per warp batch (a batch holds whole worlds of 1..8 cars)
 constexpr int FRAME_DOUBLES = 12;     // p[3], R[9]
 
 struct Lane {
@@ -559,7 +559,7 @@ static int ensure_beams(int device) {
 int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const int32_t* track_id,
                  const uint8_t* visible, const int32_t* lap, int64_t ncars, int cpw, float* ranges, float* min_range,
                  cudaStream_t stream) {
-    if (cpw > BATCH || BATCH % cpw) { set_error("ftgp_lidar: cars_per_world must be 1, 2, 4 or 8"); return FTGP_ERR_UNSUPPORTED; }
+    if (cpw < 1 || cpw > BATCH) { set_error("ftgp_lidar: cars_per_world must be 1..8"); return FTGP_ERR_UNSUPPORTED; }
     GeomHeader gh; memcpy(&gh, g->h_blob.data(), sizeof gh);
     const int threads = 512;
     const size_t scratch = (size_t)(threads / 32) * BATCH * (FRAME_DOUBLES * 8 + 4);
@@ -577,8 +577,9 @@ int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const i
     if (per_sm < 1) per_sm = 1;
     int nsm = dev < 16 ? sm_count[dev] : 148;
     // cars per warp batch: 8 for big fleets (best lane utilisation), fewer when the fleet would not fill the GPU
-    int bsz = BATCH;
-    while (bsz > cpw && (ncars + bsz - 1) / bsz < (int64_t)nsm * per_sm * (threads / 32) * 2) bsz >>= 1;
+    int wpb = BATCH / cpw;                                      // whole worlds per batch
+    while (wpb > 1 && (ncars + wpb * cpw - 1) / (wpb * cpw) < (int64_t)nsm * per_sm * (threads / 32) * 2) wpb >>= 1;
+    const int bsz = wpb * cpw;
     int64_t need = ((ncars + bsz - 1) / bsz + (threads / 32) - 1) / (threads / 32);
     int grid = (int)std::min<int64_t>(need, (int64_t)nsm * per_sm);
     if (grid < 1) return FTGP_OK;

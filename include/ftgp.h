@@ -86,7 +86,7 @@ int64_t ftgp_geom_bytes(const ftgp_geom* g);
 /* Replaces data.sensordata[vehicle_state.sensors] (custom.py:1395): the 90 rangefinder
  * sensors of mushr.em.xml:112-117,204-206 evaluated by mj_ray from the pose in qpos.
  * qpos: device double[ncars][qpos_stride] (first 7 = free joint).  track_id: device
- * int32[ncars] or NULL (all on track 0).  cars_per_world > 1: consecutive cars share a
+ * int32[ncars] or NULL (all on track 0).  cars_per_world in 2..8: consecutive cars share a
  * world and see each other's lidar cylinder (mushr.em.xml:108); visible: device
  * uint8[ncars] or NULL (0 = shadowed car, custom.py:1455-1464).
  * lap: device lap state (FTGP_LAP_* rows, see below) or NULL; a car whose FTGP_LAP_FINISHED field

@@ -268,3 +268,32 @@ def test_two_fleets_on_two_streams_do_not_share_scratch(ft):
     for a, b in zip(res["alone"], res["interleaved"]):
         for k in a:
             assert torch.equal(a[k], b[k]), k
+
+
+def test_headless_runner_with_device_and_host_drivers(ft, capsys):
+    """python -m ft_grandprix_b200.run: a cars.json with the two bundled drivers (device), a file:// v1 driver that
+    raises now and then, a v2 driver module and a driver that cannot be imported (inert), two identical worlds."""
+    import os
+    from ft_grandprix_b200 import run as runner
+    from ft_grandprix_b200.fleet import LAP
+    from conftest import ROOT
+    sys_path_added = os.path.join(ROOT, "tests")
+    import sys
+    if sys_path_added not in sys.path:
+        sys.path.insert(0, sys_path_added)
+    cars = [{"driver": "ft_grandprix.nidc", "name": "red car"},
+            {"driver": "ft_grandprix.fast", "name": "orange car"},
+            {"driver": "file://" + os.path.join(ROOT, "tests", "drivers", "slowpoke.py"), "name": "slowpoke"},
+            {"driver": "drivers.v2driver", "name": "v2"},
+            {"driver": "no.such.module", "name": "ghost"}]
+    lines = []
+    fleet = runner.run(cars, "track", lap_target=1, max_seconds=2.0, worlds=2, report_every=1.0, out=lines.append)
+    assert fleet.steps == 500 and fleet.cars_per_world == 5
+    text = "\n".join(lines)
+    assert "t = 1.0 s" in text and "t = 2.0 s" in text and "Car #0 - red car" in text and "Completion:" in text and "1st" in text
+    assert "Error in vehicle" in capsys.readouterr().out                      # the flaky driver's exceptions were swallowed
+    q = fleet.qpos.cpu().numpy(); lap = fleet.lap.cpu().numpy()
+    assert np.array_equal(q[:5], q[5:])                                       # the two worlds are identical
+    start = np.array([fleet.geom.tracks[0].start_pose(i)[:2] for i in range(5)])
+    moved = np.linalg.norm(q[:5, :2] - start, axis=1)
+    assert (moved[:4] > 0.3).all() and moved[4] < 0.05                        # everyone drives except the inert car
