@@ -59,7 +59,7 @@ extern "C" int hq_step_ghost(double* qpos, double* qvel, double* warm, const dou
                 for (int k = 0; k < nsteps; k++) {
                     StepInfo si;
                     q.ghost_w = ghost_w; q.ghost_c = ghost_c;
-                    step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), true, si);
+                    step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), true, si, QStage{0, false, nullptr});
                     q.sync();
                     if (info4 && w == 0) { info4[4 * i] = si.iters; info4[4 * i + 1] = si.ncon_wheel; info4[4 * i + 2] = si.ncon_wall; info4[4 * i + 3] = si.reset; }
                 }
@@ -69,4 +69,38 @@ extern "C" int hq_step_ghost(double* qpos, double* qvel, double* warm, const dou
 }
 extern "C" int hq_step(double* qpos, double* qvel, double* warm, const double* ctrl, long n, int nsteps, int* info4) {
     return hq_step_ghost(qpos, qvel, warm, ctrl, n, nsteps, info4, 0, 0);
+}
+
+// staged solve: at most k1 Newton rounds, then (suspended cars) k2 more, then to convergence -- the records live on the host
+extern "C" int hq_step_staged(double* qpos, double* qvel, double* warm, const double* ctrl, long n, int* info4, int k1, int k2, int* nsuspended) {
+    if (!g_ready) { g_mc = model_constants(); g_ready = true; }
+    QuadHostShared sh;
+    for (int g = 0; g < 25; g++) quad_const_entry(g_mc, g, sh.ktab);
+    std::vector<double> rec(QREC_DOUBLES);
+    std::vector<std::thread> th;
+    int nsus[4] = {0, 0, 0, 0};
+    for (int w = 0; w < 4; w++)
+        th.emplace_back([&, w]() {
+            QuadHost q; q.s = &sh; q.w = w; q.priv = sh.priv + w; q.shr = sh.shr; q.ktab = sh.ktab;
+            for (long i = 0; i < n; i++) {
+                StepInfo si;
+                const int budget[3] = {k1, k2, 0};
+                bool sus = false;
+                for (int stage = 0; stage < 3; stage++) {
+                    sus = step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), true, si,
+                                        QStage{budget[stage], stage > 0, rec.data()});
+                    q.sync();
+                    if (!sus) break;
+                    nsus[w]++;
+                    // scribble over the shared slots: the next stage must rely on the record alone
+                    for (int k = w; k < QP_N * 4; k += 4) sh.priv[k] = -7e77;
+                    if (w == 0) for (int k = 0; k < QC_N; k++) sh.shr[k] = 3e99;
+                    q.sync();
+                }
+                if (info4 && w == 0) { info4[4 * i] = si.iters; info4[4 * i + 1] = si.ncon_wheel; info4[4 * i + 2] = si.ncon_wall; info4[4 * i + 3] = si.reset; }
+            }
+        });
+    for (auto& t2 : th) t2.join();
+    if (nsuspended) *nsuspended = nsus[0];
+    return 0;
 }
