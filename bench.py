@@ -156,7 +156,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = args.workload
+    wl = args.workload if args.workload in ("lidar", "step") else "tick"      # episode / race: the CPU arm is the full tick
     threads = os.cpu_count() or 1
     sample_cars = {"lidar": 64 * threads, "tick": 16 * threads, "step": 16 * threads}[wl]
     ticks = 1 if wl == "lidar" else 10
