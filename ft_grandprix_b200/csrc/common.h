@@ -42,6 +42,7 @@ struct TrackHeader {
     int32_t path_off;              // word offset of double[100][2], or -1
     int32_t pad;
     double dsize_x, dsize_y;       // fp64 copies for the step kernel
+    double dinv_size_x, dinv_size_y;   // 1 / dsize (the lidar's ray set-up divides by the chunk pitch for every ray)
 };
 
 struct GeomHeader {

@@ -308,7 +308,7 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                         const double owx = F[0] + F[3] * lx + F[4] * ly + F[5] * rz;
                         const double owy = F[1] + F[6] * lx + F[7] * ly + F[8] * rz;
                         const double owz = F[2] + F[9] * lx + F[10] * ly + F[11] * rz;
-                        const double inv_sx = 1.0 / th->dsize_x, inv_sy = 1.0 / th->dsize_y;
+                        const double inv_sx = th->dinv_size_x, inv_sy = th->dinv_size_y;
                         const double gxd = owx * inv_sx + 0.5, gyd = owy * inv_sy + 0.5 + (double)(th->vc - 1);
                         const double fgx = floor(gxd), fgy = floor(gyd);
                         L.ix0 = (int)fgx; L.iy0 = (int)fgy;

@@ -221,6 +221,7 @@ extern "C" ftgp_geom* ftgp_geom_create(const ftgp_track* const* tracks, const do
         th.size_x = (float)t->size_x; th.size_y = (float)t->size_y;
         th.inv_size_x = (float)(1.0 / t->size_x); th.inv_size_y = (float)(1.0 / t->size_y);
         th.dsize_x = t->size_x; th.dsize_y = t->size_y;
+        th.dinv_size_x = 1.0 / th.dsize_x; th.dinv_size_y = 1.0 / th.dsize_y;
         th.path_off = -1;
         while (blob.size() % 2) blob.push_back(0);               // 8-byte align the header (doubles inside)
         gh.track_off[k] = thdr_off[k] = (int)blob.size();
