@@ -73,7 +73,7 @@ __device__ __forceinline__ float cell_hit(uint32_t bits, float u, float v, float
         float den = dz - a * du - b * dv;
         float num = z - h00 - a * u - b * v;
         if (fabsf(den) > 1e-15f) {
-            float s = -num / den;
+            float s = __fdividef(-num, den);        // (2 ulp; hits within CELL_EPS of an edge are re-done in fp64 anyway)
             float uu = u + s * du, vv = v + s * dv;
             float m = fminf(fminf(vv, uu - vv), 1.f - uu);          // > 0 inside
             if (s >= smin - 1e-5f && m >= -CELL_EPS) {
@@ -86,7 +86,7 @@ __device__ __forceinline__ float cell_hit(uint32_t bits, float u, float v, float
         float den = dz - a * du - b * dv;
         float num = z - h00 - a * u - b * v;
         if (fabsf(den) > 1e-15f) {
-            float s = -num / den;
+            float s = __fdividef(-num, den);        // (2 ulp; hits within CELL_EPS of an edge are re-done in fp64 anyway)
             float uu = u + s * du, vv = v + s * dv;
             float m = fminf(fminf(uu, vv - uu), 1.f - vv);
             if (s >= smin - 1e-5f && m >= -CELL_EPS) {
