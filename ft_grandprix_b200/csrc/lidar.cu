@@ -444,11 +444,11 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                                 const float xlo = (float)(bb & 0xFF) - 1.01f, xhi = (float)((bb >> 8) & 0xFF) + 1.01f;
                                 const float ylo = (float)((bb >> 16) & 0xFF) - 1.01f, yhi = (float)(bb >> 24) + 1.01f;
                                 if (fabsf(L.dfx) > 1e-20f) {
-                                    const float i = 1.f / L.dfx, a = (xlo - L.fxo) * i, b2 = (xhi - L.fxo) * i;
+                                    const float i = __fdividef(1.f, L.dfx), a = (xlo - L.fxo) * i, b2 = (xhi - L.fxo) * i;
                                     ta = fmaxf(ta, fminf(a, b2)); tb = fminf(tb, fmaxf(a, b2));
                                 } else if (L.fxo < xlo || L.fxo > xhi) tb = -BIG;
                                 if (fabsf(L.dfy) > 1e-20f) {
-                                    const float i = 1.f / L.dfy, a = (ylo - L.fyo) * i, b2 = (yhi - L.fyo) * i;
+                                    const float i = __fdividef(1.f, L.dfy), a = (ylo - L.fyo) * i, b2 = (yhi - L.fyo) * i;
                                     ta = fmaxf(ta, fminf(a, b2)); tb = fminf(tb, fmaxf(a, b2));
                                 } else if (L.fyo < ylo || L.fyo > yhi) tb = -BIG;
                             }
@@ -463,7 +463,7 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                                 L.Ma = L.major_x ? L.xa : L.ya; L.ma = L.major_x ? L.ya : L.xa;
                                 L.nM = L.major_x ? L.ncol - 1 : L.nrow - 1; L.nm = L.major_x ? L.nrow - 1 : L.ncol - 1;
                                 L.sg = L.dM >= 0.f ? 1 : -1;
-                                L.inv_dM = fabsf(L.dM) > 1e-20f ? 1.f / L.dM : 0.f;
+                                L.inv_dM = fabsf(L.dM) > 1e-20f ? __fdividef(1.f, L.dM) : 0.f;      // (the line intervals carry a 1e-3 cell slack)
                                 const float Mb = L.Ma + L.span * L.dM;
                                 int c = (int)floorf(L.Ma - (float)L.sg * 1e-3f), cend = (int)floorf(Mb + (float)L.sg * 1e-3f);
                                 L.c = min(max(c, 0), L.nM - 1); L.cend = min(max(cend, 0), L.nM - 1);
