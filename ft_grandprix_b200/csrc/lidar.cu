@@ -196,9 +196,10 @@ __device__ __forceinline__ double ray_cylinder(double px, double py, double pz, 
 // Traversal as a per-lane state machine.  A warp owns a batch of cars (whole worlds) and a pool of
 // 90 x ncars rays; every lane runs IDLE -> CHUNK (one Amanatides-Woo step over the 0.5 m chunk grid)
 // -> SWEEP (one major-axis column of 19x19 cells inside a non-empty chunk) -> ... -> IDLE, and an idle
-// lane pulls the next ray of the pool.  Each loop iteration executes ONE of the code blocks for the whole warp: the
-// one most lanes are waiting for (a warp-uniform vote), so that lanes in the same state are served together and the
-// other blocks' instructions are not issued at all for a handful of lanes
+// lane pulls the next ray of the pool.  Each loop iteration executes ONE of two code blocks for the whole warp --
+// "leave the previous chunk and walk to the next non-empty one" or "sweep the lines of the current chunk" -- the one
+// most lanes are waiting for (a warp-uniform vote), so that lanes in the same state are served together and the
+// other block's instructions are not issued at all for a handful of lanes
 // (the first version traced beams l, l+32, l+64 per lane with nested loops: 6.5 of 32 lanes active).
 enum { ST_IDLE = 0, ST_CHUNK = 1, ST_SWEEP = 2, ST_ADV = 3 };
 constexpr int BATCH = 8;              // max cars per warp batch (a batch holds whole worlds of 1..8 cars)
@@ -391,11 +392,30 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                 }
             }
             // ---------------- which block runs this round: the state with the most lanes
-            const int n_chunk = __popc(__ballot_sync(0xffffffffu, L.state == ST_CHUNK));
+            const int n_chunk = __popc(__ballot_sync(0xffffffffu, L.state == ST_CHUNK || L.state == ST_ADV));
             const int n_sweep = __popc(__ballot_sync(0xffffffffu, L.state == ST_SWEEP));
-            const int n_adv = __popc(__ballot_sync(0xffffffffu, L.state == ST_ADV));
-            const int pick = (n_chunk >= n_sweep && n_chunk >= n_adv) ? ST_CHUNK : (n_sweep >= n_adv ? ST_SWEEP : ST_ADV);
-            // ---------------- over the chunk grid to the next non-empty chunk (empty chunks: one shared-memory load each)
+            const int pick = n_chunk >= n_sweep ? ST_CHUNK : ST_SWEEP;
+            // ---------------- leave the previous chunk (exit side face, step of the chunk DDA) ...
+            if (pick == ST_CHUNK && L.state == ST_ADV) {
+                bool done = false;
+                if (L.t1 <= L.tend) {                                // exit side face
+                    const bool far_side = L.exit_axis == 0 ? L.stepx > 0 : L.stepy > 0;
+                    const float along = L.exit_axis == 0 ? L.fyo + L.t1 * L.dfy : L.fxo + L.t1 * L.dfx;
+                    if (face_hit(L.m, L.ncol, L.nrow, L.exit_axis, far_side, along, (L.lz + L.t1 * L.dz) * (1.f / HF_RANGE))) {
+                        finish(L, fminf(L.best, L.t1), ranges, min_range, base_car); done = true;
+                    }
+                }
+                if (!done) {
+                    if (L.t1 >= L.tend) finish(L, L.best < BIG ? L.best : -1.f, ranges, min_range, base_car);
+                    else {
+                        if (L.exit_axis == 0) L.ix += L.stepx; else L.iy += L.stepy;
+                        if (L.ix < 0 || L.ix >= L.th->hc || L.iy < 0 || L.iy >= L.th->vc)
+                            finish(L, L.best < BIG ? L.best : -1.f, ranges, min_range, base_car);
+                        else { L.t0 = L.t1; L.entry_axis = L.exit_axis; L.state = ST_CHUNK; }
+                    }
+                }
+            }
+            // ---------------- ... and on over the chunk grid to the next non-empty chunk (empty chunks: one shared-memory load each)
             if (pick == ST_CHUNK && L.state == ST_CHUNK) {
                 const TrackHeader* th = L.th;
                 const int hc = th->hc, vc = th->vc;
@@ -518,26 +538,6 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                 if (found < BIG) finish(L, fminf(L.best, fmaxf(L.ta + found, 0.f)), ranges, min_range, base_car);
                 else if (L.c == L.cend) L.state = ST_ADV;
                 else L.c += L.sg;
-            }
-            // ---------------- leave the current chunk
-            if (pick == ST_ADV && L.state == ST_ADV) {
-                bool done = false;
-                if (L.t1 <= L.tend) {                                // exit side face
-                    const bool far_side = L.exit_axis == 0 ? L.stepx > 0 : L.stepy > 0;
-                    const float along = L.exit_axis == 0 ? L.fyo + L.t1 * L.dfy : L.fxo + L.t1 * L.dfx;
-                    if (face_hit(L.m, L.ncol, L.nrow, L.exit_axis, far_side, along, (L.lz + L.t1 * L.dz) * (1.f / HF_RANGE))) {
-                        finish(L, fminf(L.best, L.t1), ranges, min_range, base_car); done = true;
-                    }
-                }
-                if (!done) {
-                    if (L.t1 >= L.tend) finish(L, L.best < BIG ? L.best : -1.f, ranges, min_range, base_car);
-                    else {
-                        if (L.exit_axis == 0) L.ix += L.stepx; else L.iy += L.stepy;
-                        if (L.ix < 0 || L.ix >= L.th->hc || L.iy < 0 || L.iy >= L.th->vc)
-                            finish(L, L.best < BIG ? L.best : -1.f, ranges, min_range, base_car);
-                        else { L.t0 = L.t1; L.entry_axis = L.exit_axis; L.state = ST_CHUNK; }
-                    }
-                }
             }
         }
     }
