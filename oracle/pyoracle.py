@@ -185,5 +185,16 @@ class Model:
         b = np.zeros(29); lib().fto_bias(self.ptr, _p(np.ascontiguousarray(qpos)), _p(np.ascontiguousarray(qvel)), _p(b)); return b
     def inverse(self, qpos, qvel, qacc):
         t = np.zeros(29); lib().fto_inverse(self.ptr, _p(np.ascontiguousarray(qpos)), _p(np.ascontiguousarray(qvel)), _p(np.ascontiguousarray(qacc)), _p(t)); return t
+    def constraint_problem(self, track, qpos, qvel, ctrl, maxrows=128):
+        """TEST SUPPORT: (M, qfrc_smooth, J, D, R, aref, floss, type) of the convex problem mj_fwdConstraint solves."""
+        M = np.zeros((29, 29)); qfs = np.zeros(29); J = np.zeros((maxrows, 29))
+        D = np.zeros(maxrows); R = np.zeros(maxrows); aref = np.zeros(maxrows); fl = np.zeros(maxrows)
+        ty = np.zeros(maxrows, dtype=np.int32)
+        L = lib()
+        L.fto_constraint_problem.restype = C.c_int
+        n = L.fto_constraint_problem(self.ptr, track.ptr if track is not None else None, _p(np.ascontiguousarray(qpos)),
+                                     _p(np.ascontiguousarray(qvel)), _p(np.ascontiguousarray(ctrl, dtype=np.float64)), maxrows,
+                                     _p(M), _p(qfs), _p(J), _p(D), _p(R), _p(aref), _p(fl), _p(ty))
+        return M, qfs, J[:n], D[:n], R[:n], aref[:n], fl[:n], ty[:n]
     def energy(self, qpos, qvel):
         return lib().fto_energy(self.ptr, _p(np.ascontiguousarray(qpos)), _p(np.ascontiguousarray(qvel)))

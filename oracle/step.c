@@ -1031,3 +1031,45 @@ void fto_body_xpos(const fto_model* m, const double* qpos, double* out) {
     kin_t* k = (kin_t*)malloc(sizeof(kin_t));
     kinematics(m, qpos, k); memcpy(out, k->xpos, sizeof k->xpos); free(k);
 }
+
+/* TEST SUPPORT: the convex problem mj_fwdConstraint solves for one state, so that a test can minimise it with an
+ * independent solver (tests/test_step_cpu.py).  Returns the number of rows n (<= maxrows); M 29x29, qfrc_smooth 29,
+ * J n x 29, D / R / aref / floss n, type n (0 equality, 1 friction loss, 2 limit, 3 contact). */
+int fto_constraint_problem(const fto_model* m, const fto_track* t, const double* qpos, const double* qvel, const double* ctrl,
+                           int maxrows, double* M, double* qfrc_smooth_out, double* J, double* D, double* R, double* aref,
+                           double* floss, int* type) {
+    kin_t* k = (kin_t*)malloc(sizeof(kin_t));
+    efc_t* e = (efc_t*)malloc(sizeof(efc_t));
+    kinematics(m, qpos, k); com_pos(m, k); crb(m, k);
+    contact_t con[MAXCON];
+    int nwheel = wheel_plane(m, k, con);
+    int ncon = wall_contacts(m, t, k, con, nwheel);
+    make_constraint(m, k, qpos, con, ncon, e);
+    com_vel(m, qvel, k);
+    double passive[NV], bias[NV], act[NV] = {0};
+    for (int d = 0; d < NV; d++) passive[d] = -m->dof_damping[d] * qvel[d];
+    for (int j = 0; j < NJNT; j++) if (m->jnt[j].stiffness > 0)
+        passive[m->jnt[j].dadr] += -m->jnt[j].stiffness * (qpos[m->jnt[j].qadr] - m->jnt[j].springref);
+    rne(m, k, qvel, 0, bias);
+    make_impedance(e, qvel);
+    {
+        const int thr[4] = {9, 15, 20, 25};
+        double f_turn = 20.0 * ctrl[1] - 20.0 * (qpos[7] - 0.0);
+        double tv = 0;
+        for (int w = 0; w < 4; w++) tv += 0.25 * qvel[thr[w]];
+        double f_fwd = 100.0 * ctrl[0] - 100.0 * (0.04 * tv);
+        if (f_fwd > 500) f_fwd = 500;
+        if (f_fwd < -500) f_fwd = -500;
+        act[6] += f_turn;
+        for (int w = 0; w < 4; w++) act[thr[w]] += 0.04 * 0.25 * f_fwd;
+    }
+    for (int d = 0; d < NV; d++) qfrc_smooth_out[d] = passive[d] - bias[d] + act[d];
+    memcpy(M, k->M, sizeof(double) * NV * NV);
+    int n = e->n < maxrows ? e->n : maxrows;
+    for (int i = 0; i < n; i++) {
+        memcpy(J + (size_t)i * NV, e->J[i], sizeof(double) * NV);
+        D[i] = e->D[i]; R[i] = e->R[i]; aref[i] = e->aref[i]; floss[i] = e->floss[i]; type[i] = e->type[i];
+    }
+    free(k); free(e);
+    return n;
+}
