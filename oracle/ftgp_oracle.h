@@ -121,7 +121,7 @@ double fto_energy(const fto_model* m, const double* qpos, const double* qvel);
 /* TEST SUPPORT: the convex problem of mj_fwdConstraint for one state (see oracle/step.c) */
 int fto_constraint_problem(const fto_model* m, const fto_track* t, const double* qpos, const double* qvel, const double* ctrl,
                            int maxrows, double* M, double* qfrc_smooth, double* J, double* D, double* R, double* aref,
-                           double* floss, int* type);
+                           double* floss, int* type, double* pos);
 
 #ifdef __cplusplus
 }

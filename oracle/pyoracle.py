@@ -189,12 +189,13 @@ class Model:
         """TEST SUPPORT: (M, qfrc_smooth, J, D, R, aref, floss, type) of the convex problem mj_fwdConstraint solves."""
         M = np.zeros((29, 29)); qfs = np.zeros(29); J = np.zeros((maxrows, 29))
         D = np.zeros(maxrows); R = np.zeros(maxrows); aref = np.zeros(maxrows); fl = np.zeros(maxrows)
-        ty = np.zeros(maxrows, dtype=np.int32)
+        ty = np.zeros(maxrows, dtype=np.int32); pos = np.zeros(maxrows)
         L = lib()
         L.fto_constraint_problem.restype = C.c_int
         n = L.fto_constraint_problem(self.ptr, track.ptr if track is not None else None, _p(np.ascontiguousarray(qpos)),
                                      _p(np.ascontiguousarray(qvel)), _p(np.ascontiguousarray(ctrl, dtype=np.float64)), maxrows,
-                                     _p(M), _p(qfs), _p(J), _p(D), _p(R), _p(aref), _p(fl), _p(ty))
+                                     _p(M), _p(qfs), _p(J), _p(D), _p(R), _p(aref), _p(fl), _p(ty), _p(pos))
+        self.last_pos = pos[:n]
         return M, qfs, J[:n], D[:n], R[:n], aref[:n], fl[:n], ty[:n]
     def energy(self, qpos, qvel):
         return lib().fto_energy(self.ptr, _p(np.ascontiguousarray(qpos)), _p(np.ascontiguousarray(qvel)))

@@ -1034,10 +1034,11 @@ void fto_body_xpos(const fto_model* m, const double* qpos, double* out) {
 
 /* TEST SUPPORT: the convex problem mj_fwdConstraint solves for one state, so that a test can minimise it with an
  * independent solver (tests/test_step_cpu.py).  Returns the number of rows n (<= maxrows); M 29x29, qfrc_smooth 29,
- * J n x 29, D / R / aref / floss n, type n (0 equality, 1 friction loss, 2 limit, 3 contact). */
+ * J n x 29, D / R / aref / floss n, type n (0 equality, 1 friction loss, 2 limit, 3 contact), pos n (constraint
+ * violation: equality residual, distance to the limit, contact distance; may be NULL). */
 int fto_constraint_problem(const fto_model* m, const fto_track* t, const double* qpos, const double* qvel, const double* ctrl,
                            int maxrows, double* M, double* qfrc_smooth_out, double* J, double* D, double* R, double* aref,
-                           double* floss, int* type) {
+                           double* floss, int* type, double* pos) {
     kin_t* k = (kin_t*)malloc(sizeof(kin_t));
     efc_t* e = (efc_t*)malloc(sizeof(efc_t));
     kinematics(m, qpos, k); com_pos(m, k); crb(m, k);
@@ -1069,6 +1070,7 @@ int fto_constraint_problem(const fto_model* m, const fto_track* t, const double*
     for (int i = 0; i < n; i++) {
         memcpy(J + (size_t)i * NV, e->J[i], sizeof(double) * NV);
         D[i] = e->D[i]; R[i] = e->R[i]; aref[i] = e->aref[i]; floss[i] = e->floss[i]; type[i] = e->type[i];
+        if (pos) pos[i] = e->pos[i];
     }
     free(k); free(e);
     return n;

@@ -339,3 +339,59 @@ def test_newton_solution_is_the_minimiser_found_by_an_independent_solver(model, 
         if walls_checked >= 12:
             break
     assert walls_checked >= 5
+
+
+def _integrate_pos(q, v, h):
+    """q (+) h v for the mushr joint layout (mj_integratePos): free joint, hinges / slides, four ball joints."""
+    def qmul(a, b):
+        return np.array([a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2],
+                         a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0]])
+
+    def qint(quat, w):
+        ang = np.linalg.norm(w) * h
+        if ang == 0:
+            return quat / np.linalg.norm(quat)
+        ax = w / np.linalg.norm(w)
+        return qmul(quat / np.linalg.norm(quat), np.concatenate([[np.cos(ang / 2)], ax * np.sin(ang / 2)]))
+    out = q.copy()
+    out[0:3] += h * v[0:3]
+    out[3:7] = qint(q[3:7], v[3:6])
+    scalar = [(7, 6), (8, 7), (9, 8), (10, 9), (15, 13), (16, 14), (17, 15), (22, 19), (23, 20), (28, 24), (29, 25)]
+    for qa, d in scalar:
+        out[qa] += h * v[d]
+    for qa, d in ((11, 10), (18, 16), (24, 21), (30, 26)):
+        out[qa:qa + 4] = qint(q[qa:qa + 4], v[d:d + 3])
+    return out
+
+
+def test_constraint_jacobians_are_the_derivatives_of_the_violations(model, otracks):
+    """Row Jacobians against central finite differences of the exported constraint violations: for a random velocity v,
+    (pos(q (+) eps v) - pos(q (-) eps v)) / (2 eps) = J v for equality, limit and (pyramid pairs averaged) contact-normal
+    rows.  Catches sign, frame and indexing errors in the row assembly independently of the solver."""
+    rng = np.random.default_rng(4)
+    t = otracks["track"]
+    checked = {0: 0, 2: 0, 3: 0}
+    for trial in range(12):
+        q, v, w = model.reset(rng.uniform(5, 35), -rng.uniform(5, 35), rng.uniform(-3, 3))
+        ctrl = np.array([rng.uniform(0, 4), rng.uniform(-0.9, 0.9)])
+        for k in range(int(rng.integers(40, 160))):
+            model.step(t, q, v, w, ctrl)
+        q[7] += 0.9 * np.sign(ctrl[1])                              # push the steering wheel past its +-1 limit half the time
+        vel = rng.normal(size=29) * 0.3
+        eps = 1e-6
+        M, qfs, J, D, R, aref, fl, ty = model.constraint_problem(t, q, np.zeros(29), ctrl); p0 = model.last_pos.copy()
+        _, _, Jp, *_rest, typ = model.constraint_problem(t, _integrate_pos(q, vel, eps), np.zeros(29), ctrl); pp = model.last_pos.copy()
+        _, _, Jm, *_rest, tym = model.constraint_problem(t, _integrate_pos(q, vel, -eps), np.zeros(29), ctrl); pm = model.last_pos.copy()
+        if len(pp) != len(p0) or len(pm) != len(p0) or not (np.array_equal(typ, ty) and np.array_equal(tym, ty)):
+            continue                                                # a row appeared / vanished inside the stencil
+        fd = (pp - pm) / (2 * eps)
+        for i in range(len(ty)):
+            if ty[i] in (0, 2):
+                assert abs(fd[i] - J[i] @ vel) < 1e-6 * (1 + abs(fd[i])), (trial, i, ty[i], fd[i], J[i] @ vel)
+                checked[int(ty[i])] += 1
+        con = np.nonzero(ty == 3)[0]
+        for c in range(0, len(con), 4):                             # rows Jn +- mu Jt1, Jn +- mu Jt2: the mean is Jn
+            jn = J[con[c:c + 4]].mean(0)
+            assert abs(fd[con[c]] - jn @ vel) < 1e-5 * (1 + abs(fd[con[c]])), (trial, c, fd[con[c]], jn @ vel)
+            checked[3] += 1
+    assert checked[0] >= 20 and checked[2] >= 20 and checked[3] >= 30, checked
