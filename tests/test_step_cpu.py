@@ -395,3 +395,103 @@ def test_constraint_jacobians_are_the_derivatives_of_the_violations(model, otrac
             assert abs(fd[con[c]] - jn @ vel) < 1e-5 * (1 + abs(fd[con[c]])), (trial, c, fd[con[c]], jn @ vel)
             checked[3] += 1
     assert checked[0] >= 20 and checked[2] >= 20 and checked[3] >= 30, checked
+
+
+def test_row_regularisers_and_references_follow_the_documented_formulas(model):
+    """D = 1/R and aref of every exported row recomputed in numpy from the formulas of SURVEY B.7 (impedance sigmoid
+    d(x), R = (1 - d)/d * diagApprox, K = 1/(dmax^2 tc^2), B = 2/(dmax tc), pyramidal R = 2 mu^2 R_normal) and the model
+    constants (dof_invweight0, body_invweight0) -- an independent statement of the softness of every constraint."""
+    c = model.constants()
+    dinv, binv = c["dof_invweight0"], c["body_invweight0"]
+    dmax, width, mid, tc = 0.95, 0.001, 0.5, 0.02
+
+    def imp(d0, pos):
+        x = abs(pos) / width
+        if x >= 1: return dmax
+        if x == 0: return d0
+        y = x * x / mid if x <= mid else 1 - (1 - x) ** 2 / (1 - mid)
+        return d0 + y * (dmax - d0)
+    K, B = 1 / (dmax * dmax * tc * tc), 2 / (dmax * tc)
+    rng = np.random.default_rng(6)
+    wheel_body = {7: 3, 13: 5, 19: 7, 24: 9}                       # suspension dof -> wheel body id (depth-first numbering)
+    rows = 0
+    for trial in range(10):
+        q, v, w = model.reset(rng.uniform(5, 35), -rng.uniform(5, 35), rng.uniform(-3, 3))
+        ctrl = np.array([rng.uniform(0, 4), rng.uniform(-0.9, 0.9)])
+        for k in range(int(rng.integers(30, 200))):
+            model.step(None, q, v, w, ctrl)
+        q[7] += 0.8 * np.sign(ctrl[1])
+        M, qfs, J, D, R, aref, fl, ty = model.constraint_problem(None, q, v, ctrl)
+        pos = model.last_pos
+        i = 0
+        while i < len(ty):
+            nz = np.nonzero(J[i])[0]
+            if ty[i] == 0:                                           # joint equality: two dofs
+                diag, d0 = dinv[nz].sum(), 0.9
+            elif ty[i] in (1, 2):                                    # friction loss / limit: one dof
+                assert len(nz) == 1
+                diag, d0 = dinv[nz[0]], 0.9
+            else:                                                    # wheel-ground contact: four pyramid rows, mixed solimp d0 = 0.45
+                susp = [d for d in wheel_body if J[i][d] != 0]
+                assert len(susp) == 1
+                diag, d0 = binv[wheel_body[susp[0]], 0], 0.45
+            d = imp(d0, pos[i])
+            Rn = max(1e-15, (1 - d) * diag / d)
+            vel = J[i] @ v
+            if ty[i] == 3:
+                mu = 0.5
+                for r in range(4):
+                    assert abs(R[i + r] / (2 * mu * mu * Rn) - 1) < 1e-12 and abs(D[i + r] * R[i + r] - 1) < 1e-12
+                    want = -B * (J[i + r] @ v) - K * d * pos[i + r]
+                    assert abs(aref[i + r] - want) <= 1e-9 * (1 + abs(want))
+                i += 4; rows += 4
+                continue
+            assert abs(R[i] / Rn - 1) < 1e-12 and abs(D[i] * R[i] - 1) < 1e-12, (ty[i], R[i], Rn)
+            want = -B * vel - (0 if ty[i] == 1 else K * d * pos[i])
+            assert abs(aref[i] - want) <= 1e-9 * (1 + abs(want)), (ty[i], aref[i], want)
+            i += 1; rows += 1
+    assert rows > 300
+
+
+def test_wheel_ground_distance_against_bruteforce_ellipsoid(model):
+    """The contact distance of every wheel-ground contact row against first principles: the wheel ellipsoid
+    (0.03, 0.01, 0.03; mushr.em.xml:69) is posed with numpy kinematics (car pose, wheel offset, suspension slide along
+    the car's z, steering about z, spin about y; mushr.em.xml:124-173), sampled at 1e6 surface points, and the lowest
+    one is compared with the row's `pos` (distance to the plane z = 0.01, mushr.em.xml:94)."""
+    rng = np.random.default_rng(8)
+    th, ph = np.meshgrid(np.linspace(0, np.pi, 1000), np.linspace(0, 2 * np.pi, 1000))
+    unit = np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), np.cos(th)], -1).reshape(-1, 3)
+    ell = unit * np.array([0.03, 0.01, 0.03])
+    wheels = [(0.06925, 0.0575, 8, 9, 10, 7), (0.06925, -0.0575, 15, 16, 17, 13), (-0.079, 0.0575, 22, None, 23, 19),
+              (-0.079, -0.0575, 28, None, 29, 24)]                                   # x, y, q susp, q steer, q spin, dof susp
+
+    def rot(q):
+        w, x, y, z = q / np.linalg.norm(q)
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                         [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    checked = 0
+    for trial in range(6):
+        q, v, w = model.reset(rng.uniform(5, 35), -rng.uniform(5, 35), rng.uniform(-3, 3))
+        ctrl = np.array([rng.uniform(0, 4), rng.uniform(-0.9, 0.9)])
+        for k in range(int(rng.integers(20, 150))):
+            model.step(None, q, v, w, ctrl)
+        M, qfs, J, D, R, aref, fl, ty = model.constraint_problem(None, q, v, ctrl)
+        pos = model.last_pos
+        R1 = rot(q[3:7])
+        con = np.nonzero(ty == 3)[0]
+        for c in range(0, len(con), 4):
+            i = con[c]
+            (wx, wy, qs, qst, qsp, dsusp), = [wh for wh in wheels if J[i][wh[5]] != 0]
+            a = q[qst] if qst is not None else 0.0
+            Rz = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+            b = q[qsp]
+            Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+            Rw = R1 @ Rz @ Ry
+            pw = q[0:3] + R1 @ np.array([wx, wy, 0.0244 + q[qs]])
+            lowest = (ell @ Rw.T + pw)[:, 2].min()
+            assert abs((lowest - 0.01) - pos[i]) < 2e-7, (trial, c, lowest - 0.01, pos[i])
+            # closed form of the same support function
+            assert abs(pw[2] - np.sqrt(((np.array([0.03, 0.01, 0.03]) * Rw[2]) ** 2).sum()) - 0.01 - pos[i]) < 1e-12
+            checked += 1
+    assert checked >= 12
