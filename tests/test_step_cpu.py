@@ -495,3 +495,40 @@ def test_wheel_ground_distance_against_bruteforce_ellipsoid(model):
             assert abs(pw[2] - np.sqrt(((np.array([0.03, 0.01, 0.03]) * Rw[2]) ** 2).sum()) - 0.01 - pos[i]) < 1e-12
             checked += 1
     assert checked >= 12
+
+
+def test_euler_update_against_numpy_restatement(model, otracks):
+    """mj_Euler with implicit joint damping and mj_integratePos restated in numpy from the exported
+    problem: qacc' = (M + h diag(damping))^-1 (qfrc_smooth + J' f(qacc)), qvel += h qacc', qpos (+)= h qvel (new velocity,
+    quaternions by the exponential map) -- compared with what the oracle's step returns."""
+    h = 0.004
+    damping = np.zeros(29)
+    damping[[7, 13, 19, 24]] = 12.5                                 # suspension slides   (mushr.em.xml:63)
+    damping[[6, 8, 14]] = 0.1                                       # steering hinges     (:78)
+    damping[[9, 15, 20, 25]] = 0.01                                 # throttle hinges     (:81)
+    rng = np.random.default_rng(10)
+    t = otracks["track"]
+    worst = 0
+    for trial in range(5):
+        q, v, w = model.reset(rng.uniform(5, 35), -rng.uniform(5, 35), rng.uniform(-3, 3))
+        ctrl = np.array([rng.uniform(0, 4), rng.uniform(-0.9, 0.9)])
+        for k in range(120):
+            if k % 10 == 0:
+                M, qfs, J, D, R, aref, fl, ty = model.constraint_problem(t, q, v, ctrl)
+            q0, v0 = q.copy(), v.copy()
+            model.step(t, q, v, w, ctrl)
+            if k % 10 == 0:
+                a = w                                               # qacc_warmstart <- the solver's qacc
+                r = J @ a - aref
+                f = np.where(ty == 0, -D * r, 0.0)
+                one = ((ty == 2) | (ty == 3)) & (r < 0)
+                f = np.where(one, -D * r, f)
+                fr = ty == 1
+                knee = R * fl
+                f = np.where(fr & (np.abs(r) < knee), -D * r, f)
+                f = np.where(fr & (np.abs(r) >= knee), -np.sign(r) * fl, f)
+                qa = np.linalg.solve(M + h * np.diag(damping), qfs + J.T @ f)
+                v1 = v0 + h * qa
+                q1 = _integrate_pos(q0, v1, h)
+                worst = max(worst, np.abs(v1 - v).max() / (1 + np.abs(v).max()), np.abs(q1 - q).max())
+    assert worst < 1e-8, worst                                      # measured 1.3e-10 (D up to 1e6 times rounding of the residuals)
