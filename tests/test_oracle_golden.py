@@ -163,3 +163,65 @@ def test_ray_wall_slope_geometry(oracle):
         assert abs(d - want) < 1e-9, (z, d, want)
     # above the wall top (0.2): miss
     assert t.ray([0.0, -0.3, 0.25], [1.0, 0.0, 0.0]) == -1
+
+
+def test_centreline_against_independent_python_restatement(otracks, walls):
+    """a10 / svg.path 6.3 semantics restated a second time, independently, in Python: parse `m x,y c ... z` (relative
+    cubics + closing line), segment lengths by dense numerical integration (the C code subdivides recursively),
+    Path.point(t) = bisect over the cumulative length fractions, then the segment's OWN Bezier parameter, 100 samples at
+    t = i/100, scaled by px / W * 40 and -px / H * 40 (custom.py:1185-1186).  svg.path itself is absent, so this pins
+    the C restatement against a second reading of the same published behaviour, not against the library."""
+    import bisect
+    import re
+    for name in ("track", "circle", "small-circle", "inkscape"):
+        wall, d = walls[name]
+        H, W = wall.shape
+        tok = re.findall(r"[a-zA-Z]|-?\d*\.?\d+(?:[eE][-+]?\d+)?", d)
+        segs, i, cmd = [], 0, None
+        cur = start = None
+        num = lambda k: complex(float(tok[k]), float(tok[k + 1]))
+        while i < len(tok):
+            if tok[i].isalpha():
+                cmd = tok[i]; i += 1
+                if cmd in "zZ":
+                    if abs(cur - start) > 0:
+                        segs.append(("L", cur, start))
+                    cur = start
+                continue
+            rel = cmd.islower()
+            if cmd in "mM":
+                pt = num(i); i += 2
+                cur = (cur + pt) if (rel and cur is not None) else pt
+                start = cur
+                cmd = "l" if rel else "L"                           # further pairs after a move are implicit line-tos
+            elif cmd in "cC":
+                base = cur if rel else 0
+                c1, c2, e = base + num(i), base + num(i + 2), base + num(i + 4); i += 6
+                segs.append(("C", cur, c1, c2, e)); cur = e
+            elif cmd in "lL":
+                e = (cur if rel else 0) + num(i); i += 2
+                segs.append(("L", cur, e)); cur = e
+            else:
+                raise AssertionError(f"unexpected path command {cmd}")
+
+        def point(seg, u):
+            if seg[0] == "L":
+                return seg[1] + (seg[2] - seg[1]) * u
+            _, p0, p1, p2, p3 = seg
+            return (1 - u) ** 3 * p0 + 3 * (1 - u) ** 2 * u * p1 + 3 * (1 - u) * u * u * p2 + u ** 3 * p3
+        us = np.linspace(0, 1, 200001)
+        lengths = [0.0] + [float(np.abs(np.diff(point(sg, us))).sum()) for sg in segs]      # the Move has length 0
+        frac = np.cumsum(lengths) / sum(lengths)
+        all_segs = [("L", start, start)] + segs
+        pts = []
+        for k in range(100):
+            t = k / 100
+            if t == 0:
+                z = start
+            else:
+                j = bisect.bisect(list(frac), t)
+                u = t / frac[0] if j == 0 else (t - frac[j - 1]) / (frac[j] - frac[j - 1])
+                z = point(all_segs[j], u)
+            pts.append([z.real / W * 40, -z.imag / H * 40])
+        got = otracks[name].centreline(d)
+        assert np.abs(got - np.array(pts)).max() < 2e-6, (name, np.abs(got - np.array(pts)).max())
