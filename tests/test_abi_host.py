@@ -92,3 +92,36 @@ def test_batched_torch_drivers_match_reference_classes():
         sp, st = cls().process_lidar(S)
         np.testing.assert_array_equal(sp.numpy(), z[key][:, 0])
         np.testing.assert_array_equal(st.numpy(), z[key][:, 1])
+
+
+def test_headless_runner_host_logic():
+    """ft_grandprix_b200.run without a GPU: ordinals (custom.py:47-55), driver loading rules (custom.py:1097-1109) and
+    the dashboard lines (custom.py:335-361) from a stand-in fleet."""
+    import torch
+    from ft_grandprix_b200 import run as runner
+    from ft_grandprix_b200.fleet import DRIVER_KINDS, LAP
+    from ft_grandprix_b200._lib import LAP_FIELDS, MAX_LAPTIMES
+    assert [runner.ordinal(n) for n in (1, 2, 3, 4, 11, 12, 13, 21, 22, 23, 101, 111)] == \
+        ["1st", "2nd", "3rd", "4th", "11th", "12th", "13th", "21st", "22nd", "23rd", "101st", "111th"]
+    kind, obj, path = runner.load_driver("ft_grandprix.nidc")
+    assert kind == DRIVER_KINDS["nidc"] and obj is None
+    kind, obj, path = runner.load_driver("file://" + os.path.join(ROOT, "tests", "drivers", "slowpoke.py"))
+    assert kind is None and obj.process_lidar(np.full(90, 2.0))[0] == 0.8
+    kind, obj, path = runner.load_driver("no.such.module")
+    assert kind == DRIVER_KINDS["lobotomy"] and obj is None           # import failure -> inert driver
+    kind, obj, path = runner.load_driver("http://example.org/x.py")
+    assert kind == DRIVER_KINDS["lobotomy"]
+
+    class Stand:
+        cars_per_world = 3
+        lap = torch.zeros(3, len(LAP_FIELDS), dtype=torch.int32)
+        times = torch.zeros(3, MAX_LAPTIMES, dtype=torch.int32)
+    f = Stand()
+    f.lap[:, LAP["good_start"]] = torch.tensor([1, 1, 0], dtype=torch.int32)
+    f.lap[:, LAP["completion"]] = torch.tensor([40, 10, 97], dtype=torch.int32)
+    f.lap[:, LAP["laps"]] = torch.tensor([0, 1, 0], dtype=torch.int32)
+    f.lap[1, LAP["finished"]] = 1; f.lap[1, LAP["ntimes"]] = 1; f.times[1, 0] = 12500
+    lines = runner.dashboard(f, ["red car", "orange car", "green car"])
+    assert lines[0].strip().startswith("1st  Car #1 - orange car: Car finished 1 laps in 50.00 seconds!") and "[50.00]" in lines[0]
+    assert lines[1].strip().startswith("2nd  Car #0 - red car: Laps: 0  Completion: 40%")
+    assert lines[2].strip().startswith("3rd  Car #2 - green car: Laps: 0  Completion: -3%")      # going backwards (custom.py:132-140)
