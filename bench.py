@@ -473,10 +473,8 @@ def run_episode(args, kind="episode"):
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        with torch.cuda.stream(stream):
-            fleet.tick(1)
-            ranges_h.copy_(fleet.ranges, non_blocking=True); lap_h.copy_(fleet.lap, non_blocking=True)
-        stream.synchronize()
+        fleet.tick_readback(ranges_h, lap_h)         # per-tick host delivery, copies overlapped with the kernels
+        fleet.sync_readback()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     tt = torch.tensor([dev_ms, e2e_ms, float(launches), gather_ms], dtype=torch.float64, device=fleet.device)
@@ -504,7 +502,7 @@ def run_episode(args, kind="episode"):
                          "note": "latency/issue-bound path: algorithmic HBM traffic is far below peak by construction (SURVEY 8d)"},
             "e2e": {"value": ncars_total * e2e_steps / (e2e_ms * 1e-3), "unit": "car-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": n * 90 * 4 + fleet.lap.numel() * 4, "steps": e2e_steps,
-                    "how": "fleet.tick + ranges and lap state to pinned host memory every step, wall clock"},
+                    "how": "Fleet.tick_readback: ranges and lap state to pinned host memory every tick (host waits for them), wall clock"},
             "gpu_launches": launches, "clocks": clocks, "rays_per_s": value * 90,
             "episode": {"gather_ms": gather_ms, "stats_rows": int(stats.shape[0]), "stats_bytes": int(stats.numel() * 4),
                         "laps_max": int(laps.max()),

@@ -102,12 +102,13 @@ class Fleet:
 
     def reset_grid(self):
         """The reference start grid: car i of each world at path[(i+5)*2] (custom.py:1232-1245)."""
+        slot = np.arange(self.ncars) % self.cars_per_world
+        tid = np.zeros(self.ncars, dtype=np.int64) if self.track_id is None else self.track_id.cpu().numpy().astype(np.int64)
         xy = np.zeros((self.ncars, 2)); yaw = np.zeros(self.ncars)
-        tid = None if self.track_id is None else self.track_id.cpu().numpy()
-        for c in range(self.ncars):
-            t = self.geom.tracks[0 if tid is None else int(tid[c])]
-            x, y, a = t.start_pose(c % self.cars_per_world)
-            xy[c] = (x, y); yaw[c] = a
+        for k, t in enumerate(self.geom.tracks):
+            poses = np.array([t.start_pose(i) for i in range(self.cars_per_world)])      # (x, y, yaw) per grid slot
+            sel = tid == k
+            xy[sel] = poses[slot[sel], :2]; yaw[sel] = poses[slot[sel], 2]
         self.reset(xy, yaw)
 
     # ------------------------------------------------------------------ the per-tick pieces
