@@ -123,6 +123,15 @@ int fto_constraint_problem(const fto_model* m, const fto_track* t, const double*
                            int maxrows, double* M, double* qfrc_smooth, double* J, double* D, double* R, double* aref,
                            double* floss, int* type, double* pos);
 
+
+/* N-car world (BASELINE config 5): one Newton problem over all cars, car-car contacts by this framework's definition
+ * (oracle/step.c).  Ground work for the coupled solve; not used by the product yet. */
+int fto_world_step(const fto_model* m, const fto_track* t, int ncars, double* qpos, double* qvel, double* warm,
+                   const double* ctrl, const uint8_t* shadowed, int* info);
+int fto_world_problem(const fto_model* m, const fto_track* t, int ncars, const double* qpos, const double* qvel, const double* ctrl,
+                      int maxrows, double* M, double* qfs, double* J, double* D, double* R, double* aref, double* floss, int* type,
+                      int* ncc_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -197,5 +197,25 @@ class Model:
                                      _p(M), _p(qfs), _p(J), _p(D), _p(R), _p(aref), _p(fl), _p(ty), _p(pos))
         self.last_pos = pos[:n]
         return M, qfs, J[:n], D[:n], R[:n], aref[:n], fl[:n], ty[:n]
+    def world_step(self, track, qpos, qvel, warm, ctrl, shadowed=None):
+        """One mj_step of an N-car world (one Newton problem over all cars), in place; returns (rc, info[3])."""
+        n = qpos.shape[0]
+        info = np.zeros(4, dtype=np.int32)
+        sh = None if shadowed is None else np.ascontiguousarray(shadowed, dtype=np.uint8)
+        L = lib(); L.fto_world_step.restype = C.c_int
+        rc = L.fto_world_step(self.ptr, track.ptr if track is not None else None, n, _p(qpos), _p(qvel), _p(warm),
+                              _p(np.ascontiguousarray(ctrl, dtype=np.float64)), _p(sh) if sh is not None else None, _p(info))
+        return rc, info
+    def world_problem(self, track, qpos, qvel, ctrl, maxrows=1024):
+        n = qpos.shape[0]; nv = 29 * n
+        M = np.zeros((nv, nv)); qfs = np.zeros(nv); J = np.zeros((maxrows, nv))
+        D = np.zeros(maxrows); R = np.zeros(maxrows); aref = np.zeros(maxrows); fl = np.zeros(maxrows)
+        ty = np.zeros(maxrows, dtype=np.int32); ncc = C.c_int(0)
+        L = lib(); L.fto_world_problem.restype = C.c_int
+        k = L.fto_world_problem(self.ptr, track.ptr if track is not None else None, n, _p(np.ascontiguousarray(qpos)),
+                                _p(np.ascontiguousarray(qvel)), _p(np.ascontiguousarray(ctrl, dtype=np.float64)), maxrows,
+                                _p(M), _p(qfs), _p(J), _p(D), _p(R), _p(aref), _p(fl), _p(ty), C.byref(ncc))
+        assert k >= 0
+        return M, qfs, J[:k], D[:k], R[:k], aref[:k], fl[:k], ty[:k], ncc.value
     def energy(self, qpos, qvel):
         return lib().fto_energy(self.ptr, _p(np.ascontiguousarray(qpos)), _p(np.ascontiguousarray(qvel)))

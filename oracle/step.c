@@ -1075,3 +1075,379 @@ int fto_constraint_problem(const fto_model* m, const fto_track* t, const double*
     free(k); free(e);
     return n;
 }
+
+
+/* ==================================================================================================================
+ * N-car world (BASELINE config 5, bracket.py-style races): the reference compiles all cars into ONE MjModel, so mj_step
+ * solves ONE Newton problem over nv = 29 N dofs -- a single line-search step and a single stopping rule for all cars --
+ * and cars that touch are coupled through contact rows that span two cars.
+ *
+ * Car-car contacts are THIS FRAMEWORK'S definition (like the wall contacts; MuJoCo's convex-convex CCD between chassis
+ * meshes cannot be restated without the library): a chassis hull vertex of car A that lies inside the bounding box of
+ * car B's chassis hull (in B's frame) gives one condim-3 contact, normal = B's box face of least penetration pointing
+ * out of B, dist = -penetration, point = midway, mu = 1, default solref / solimp, pyramidal rows J = J_A(p) - J_B(p).
+ * Not used by the product yet: ground work for the coupled solve, tested on the CPU.
+ * ================================================================================================================== */
+#define WMAXCARS 8
+#define WMAXCC 32                       /* car-car contacts per world */
+
+typedef struct {
+    int nv, n;
+    double* M;                           /* nv x nv, block diagonal */
+    double* J;                           /* n x nv */
+    double *D, *R, *aref, *floss, *qfs, *qas;
+    int* type;
+} wprob_t;
+
+static void wprob_free(wprob_t* p) {
+    free(p->M); free(p->J); free(p->D); free(p->R); free(p->aref); free(p->floss); free(p->qfs); free(p->qas); free(p->type);
+}
+
+static double wcost(const wprob_t* p, const double* jar, double* force, int* state) {
+    double cost = 0;
+    for (int i = 0; i < p->n; i++) {
+        double x = jar[i], D = p->D[i], f = 0; int st = 1;
+        if (p->type[i] == C_EQUALITY) { f = -D * x; cost += 0.5 * D * x * x; }
+        else if (p->type[i] == C_FRICTION) {
+            double fl = p->floss[i], Rf = p->R[i] * fl;
+            if (x <= -Rf) { f = fl; cost += -0.5 * Rf * fl - fl * x; st = 2; }
+            else if (x >= Rf) { f = -fl; cost += -0.5 * Rf * fl + fl * x; st = 3; }
+            else { f = -D * x; cost += 0.5 * D * x * x; }
+        } else {
+            if (x >= 0) { f = 0; st = 0; } else { f = -D * x; cost += 0.5 * D * x * x; }
+        }
+        if (force) force[i] = f;
+        if (state) state[i] = st;
+    }
+    return cost;
+}
+
+typedef struct {
+    const wprob_t* p;
+    double *qacc, *Ma, *jar, *force, *grad, *Mgrad, *search, *Mv, *jv, *quad, *H;
+    int* state;
+    double cost, gauss, quadGauss[3];
+} wsolver_t;
+
+static void matvec_blockdiag(const double* M, int nv, const double* x, double* y) {   /* M is block diagonal, 29 x 29 blocks */
+    for (int a = 0; a < nv; a++) {
+        int b0 = (a / NV) * NV; double t = 0;
+        for (int b = b0; b < b0 + NV; b++) t += M[(size_t)a * nv + b] * x[b];
+        y[a] = t;
+    }
+}
+
+static void ws_update_constraint(wsolver_t* s) {
+    const wprob_t* p = s->p;
+    s->cost = wcost(p, s->jar, s->force, s->state);
+    double g = 0;
+    for (int d = 0; d < p->nv; d++) g += (s->Ma[d] - p->qfs[d]) * (s->qacc[d] - p->qas[d]);
+    s->gauss = 0.5 * g;
+    s->cost += s->gauss;
+}
+
+static void ws_update_gradient(wsolver_t* s) {
+    const wprob_t* p = s->p; const int nv = p->nv;
+    for (int d = 0; d < nv; d++) {
+        double fc = 0;
+        for (int i = 0; i < p->n; i++) fc += p->J[(size_t)i * nv + d] * s->force[i];
+        s->grad[d] = s->Ma[d] - p->qfs[d] - fc;
+    }
+    memcpy(s->H, p->M, sizeof(double) * nv * nv);
+    for (int i = 0; i < p->n; i++) if (s->state[i] == 1) {
+        const double* J = p->J + (size_t)i * nv; double D = p->D[i];
+        for (int a = 0; a < nv; a++) if (J[a] != 0) for (int b = 0; b <= a; b++) s->H[(size_t)a * nv + b] += D * J[a] * J[b];
+    }
+    chol(s->H, nv, nv);
+    memcpy(s->Mgrad, s->grad, sizeof(double) * nv);
+    chol_solve(s->H, nv, nv, s->Mgrad);
+}
+
+static void wls_eval(const wsolver_t* s, lspoint_t* pt, double alpha) {
+    const wprob_t* p = s->p;
+    double q[3] = {s->quadGauss[0], s->quadGauss[1], s->quadGauss[2]};
+    for (int i = 0; i < p->n; i++) {
+        const double* qd = s->quad + 3 * (size_t)i;
+        double x = s->jar[i] + alpha * s->jv[i];
+        if (p->type[i] == C_EQUALITY) { q[0] += qd[0]; q[1] += qd[1]; q[2] += qd[2]; }
+        else if (p->type[i] == C_FRICTION) {
+            double fl = p->floss[i], Rf = p->R[i] * fl;
+            if (x <= -Rf) { q[0] += fl * (-0.5 * Rf - s->jar[i]); q[1] += -fl * s->jv[i]; }
+            else if (x >= Rf) { q[0] += fl * (-0.5 * Rf + s->jar[i]); q[1] += fl * s->jv[i]; }
+            else { q[0] += qd[0]; q[1] += qd[1]; q[2] += qd[2]; }
+        } else if (x < 0) { q[0] += qd[0]; q[1] += qd[1]; q[2] += qd[2]; }
+    }
+    pt->alpha = alpha;
+    pt->cost = alpha * alpha * q[2] + alpha * q[1] + q[0];
+    pt->deriv[0] = 2 * alpha * q[2] + q[1];
+    pt->deriv[1] = 2 * q[2];
+    if (pt->deriv[1] <= 0) pt->deriv[1] = FTO_MINVAL;
+}
+
+static double wline_search(wsolver_t* s, double scale) {                /* PrimalSearch, as line_search() above */
+    const wprob_t* p = s->p; const int nv = p->nv;
+    double snorm = 0;
+    for (int d = 0; d < nv; d++) snorm += s->search[d] * s->search[d];
+    snorm = sqrt(snorm);
+    if (snorm < FTO_MINVAL) return 0;
+    matvec_blockdiag(p->M, nv, s->search, s->Mv);
+    for (int i = 0; i < p->n; i++) { double t = 0; const double* J = p->J + (size_t)i * nv; for (int d = 0; d < nv; d++) t += J[d] * s->search[d]; s->jv[i] = t; }
+    s->quadGauss[0] = s->gauss; s->quadGauss[1] = 0; s->quadGauss[2] = 0;
+    for (int d = 0; d < nv; d++) { s->quadGauss[1] += s->search[d] * (s->Ma[d] - p->qfs[d]); s->quadGauss[2] += 0.5 * s->search[d] * s->Mv[d]; }
+    for (int i = 0; i < p->n; i++) {
+        double* qd = s->quad + 3 * (size_t)i;
+        qd[0] = 0.5 * p->D[i] * s->jar[i] * s->jar[i]; qd[1] = p->D[i] * s->jar[i] * s->jv[i]; qd[2] = 0.5 * p->D[i] * s->jv[i] * s->jv[i];
+    }
+    double gtol = SOLVER_TOL * LS_TOL * snorm / scale;
+    lspoint_t p0, p1, p2, pmid, p1n, p2n;
+    int it = 0;
+    wls_eval(s, &p0, 0);
+    wls_eval(s, &p1, p0.alpha - p0.deriv[0] / p0.deriv[1]);
+    if (p0.cost < p1.cost) p1 = p0;
+    if (fabs(p1.deriv[0]) < gtol) return p1.alpha;
+    int dir = p1.deriv[0] < 0 ? 1 : -1;
+    int p2update = 0;
+    p2 = p1;
+    while (p1.deriv[0] * dir <= -gtol && it < LS_ITER) {
+        p2 = p1; p2update = 1;
+        wls_eval(s, &p1, p1.alpha - p1.deriv[0] / p1.deriv[1]); it++;
+        if (fabs(p1.deriv[0]) < gtol) return p1.alpha;
+    }
+    if (it >= LS_ITER || !p2update) return p1.alpha;
+    while (it < LS_ITER) {
+        wls_eval(s, &pmid, 0.5 * (p1.alpha + p2.alpha)); it++;
+        wls_eval(s, &p1n, p1.alpha - p1.deriv[0] / p1.deriv[1]);
+        wls_eval(s, &p2n, p2.alpha - p2.deriv[0] / p2.deriv[1]);
+        lspoint_t* cand[3] = {&p1n, &p2n, &pmid};
+        for (int c = 0; c < 3; c++) if (fabs(cand[c]->deriv[0]) < gtol) return cand[c]->alpha;
+        int b1 = 0, b2 = 0;
+        double lo = fmin(p1.alpha, p2.alpha), hi = fmax(p1.alpha, p2.alpha);
+        for (int c = 0; c < 3; c++) {
+            if (cand[c]->alpha <= lo || cand[c]->alpha >= hi) continue;
+            if ((cand[c]->deriv[0] < 0) == (p1.deriv[0] < 0)) { p1 = *cand[c]; b1 = 1; }
+            else { p2 = *cand[c]; b2 = 1; }
+            lo = fmin(p1.alpha, p2.alpha); hi = fmax(p1.alpha, p2.alpha);
+        }
+        if (!b1 && !b2) break;
+    }
+    return p1.cost <= p2.cost ? p1.alpha : p2.alpha;
+}
+
+/* world-level Newton: one search direction, one alpha and one stopping rule for all cars (mj_solPrimal over the model) */
+static int wnewton(const wprob_t* p, double meaninertia, const double* warm, double* qacc, double* qfrc_constraint) {
+    const int nv = p->nv, n = p->n;
+    wsolver_t s; s.p = p;
+    s.qacc = calloc(nv, 8); s.Ma = calloc(nv, 8); s.grad = calloc(nv, 8); s.Mgrad = calloc(nv, 8); s.search = calloc(nv, 8); s.Mv = calloc(nv, 8);
+    s.jar = calloc(n + 1, 8); s.force = calloc(n + 1, 8); s.jv = calloc(n + 1, 8); s.quad = calloc(3 * (size_t)(n + 1), 8);
+    s.state = calloc(n + 1, sizeof(int)); s.H = malloc(sizeof(double) * nv * nv);
+    double* jar = calloc(n + 1, 8); double* Ma = calloc(nv, 8);
+    for (int i = 0; i < n; i++) { double t = -p->aref[i]; const double* J = p->J + (size_t)i * nv; for (int d = 0; d < nv; d++) t += J[d] * warm[d]; jar[i] = t; }
+    matvec_blockdiag(p->M, nv, warm, Ma);
+    double cw = wcost(p, jar, 0, 0);
+    for (int d = 0; d < nv; d++) cw += 0.5 * (Ma[d] - p->qfs[d]) * (warm[d] - p->qas[d]);
+    for (int i = 0; i < n; i++) { double t = -p->aref[i]; const double* J = p->J + (size_t)i * nv; for (int d = 0; d < nv; d++) t += J[d] * p->qas[d]; jar[i] = t; }
+    double cs = wcost(p, jar, 0, 0);
+    memcpy(s.qacc, cw > cs ? p->qas : warm, sizeof(double) * nv);
+    matvec_blockdiag(p->M, nv, s.qacc, s.Ma);
+    for (int i = 0; i < n; i++) { double t = -p->aref[i]; const double* J = p->J + (size_t)i * nv; for (int d = 0; d < nv; d++) t += J[d] * s.qacc[d]; s.jar[i] = t; }
+    double scale = 1 / (meaninertia * (nv > 1 ? nv : 1));
+    ws_update_constraint(&s);
+    ws_update_gradient(&s);
+    for (int d = 0; d < nv; d++) s.search[d] = -s.Mgrad[d];
+    int iter = 0;
+    while (iter < SOLVER_ITER) {
+        double alpha = wline_search(&s, scale);
+        if (alpha == 0) break;
+        for (int d = 0; d < nv; d++) { s.qacc[d] += alpha * s.search[d]; s.Ma[d] += alpha * s.Mv[d]; }
+        for (int i = 0; i < n; i++) s.jar[i] += alpha * s.jv[i];
+        double oldcost = s.cost;
+        ws_update_constraint(&s);
+        ws_update_gradient(&s);
+        for (int d = 0; d < nv; d++) s.search[d] = -s.Mgrad[d];
+        double gn = 0;
+        for (int d = 0; d < nv; d++) gn += s.grad[d] * s.grad[d];
+        double improvement = scale * (oldcost - s.cost), gradient = scale * sqrt(gn);
+        iter++;
+        if (improvement < SOLVER_TOL || gradient < SOLVER_TOL) break;
+    }
+    memcpy(qacc, s.qacc, sizeof(double) * nv);
+    for (int d = 0; d < nv; d++) { double fc = 0; for (int i = 0; i < n; i++) fc += p->J[(size_t)i * nv + d] * s.force[i]; qfrc_constraint[d] = fc; }
+    free(s.qacc); free(s.Ma); free(s.grad); free(s.Mgrad); free(s.search); free(s.Mv); free(s.jar); free(s.force); free(s.jv);
+    free(s.quad); free(s.state); free(s.H); free(jar); free(Ma);
+    return iter;
+}
+
+/* one row's regulariser and reference (make_impedance() for a single row with the default solref / solimp) */
+static void row_softness(double pos, double diag, double vel, double* R, double* aref) {
+    const double dmin = 0.9, dmax = 0.95, width = 0.001, mid = 0.5;
+    double x = fabs(pos / width), imp;
+    if (x >= 1) imp = dmax; else if (x == 0) imp = dmin;
+    else { double y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid); imp = dmin + y * (dmax - dmin); }
+    *R = fmax(FTO_MINVAL, (1 - imp) * diag / imp);
+    double tc = fmax(0.02, 2 * TIMESTEP);
+    double K = 1 / (dmax * dmax * tc * tc), B = 2 / (dmax * tc);
+    *aref = -B * vel - K * imp * pos;
+}
+
+/* Assembles the world problem.  Returns the number of car-car contacts.  kin / efc: per-car scratch (ncars entries). */
+static int world_assemble(const fto_model* m, const fto_track* t, int ncars, const double* qpos, const double* qvel,
+                          const double* ctrl, const uint8_t* shadowed, kin_t* kin, efc_t* efc, wprob_t* p, int* nwheel_out) {
+    const int nv = NV * ncars;
+    p->nv = nv;
+    p->M = calloc((size_t)nv * nv, 8); p->qfs = calloc(nv, 8); p->qas = calloc(nv, 8);
+    int nrows = 0;
+    for (int c = 0; c < ncars; c++) {
+        kin_t* k = &kin[c]; efc_t* e = &efc[c];
+        const double* q = qpos + (size_t)c * NQ; const double* v = qvel + (size_t)c * NV; const double* u = ctrl + 2 * (size_t)c;
+        kinematics(m, q, k); com_pos(m, k); crb(m, k);
+        contact_t con[MAXCON];
+        int nwheel = wheel_plane(m, k, con);
+        int ncon = (shadowed && shadowed[c]) ? nwheel : wall_contacts(m, t, k, con, nwheel);   /* custom.py:1455-1464 */
+        if (nwheel_out) nwheel_out[c] = nwheel;
+        make_constraint(m, k, q, con, ncon, e);
+        com_vel(m, v, k);
+        double passive[NV], bias[NV], act[NV] = {0};
+        for (int d = 0; d < NV; d++) passive[d] = -m->dof_damping[d] * v[d];
+        for (int j = 0; j < NJNT; j++) if (m->jnt[j].stiffness > 0)
+            passive[m->jnt[j].dadr] += -m->jnt[j].stiffness * (q[m->jnt[j].qadr] - m->jnt[j].springref);
+        rne(m, k, v, 0, bias);
+        make_impedance(e, v);
+        const int thr[4] = {9, 15, 20, 25};
+        double f_turn = 20.0 * u[1] - 20.0 * (q[7] - 0.0), tv = 0;
+        for (int w = 0; w < 4; w++) tv += 0.25 * v[thr[w]];
+        double f_fwd = 100.0 * u[0] - 100.0 * (0.04 * tv);
+        if (f_fwd > 500) f_fwd = 500;
+        if (f_fwd < -500) f_fwd = -500;
+        act[6] += f_turn;
+        for (int w = 0; w < 4; w++) act[thr[w]] += 0.04 * 0.25 * f_fwd;
+        double* qfs = p->qfs + (size_t)c * NV; double* qas = p->qas + (size_t)c * NV;
+        for (int d = 0; d < NV; d++) qfs[d] = passive[d] - bias[d] + act[d];
+        double L[NV * NV];
+        memcpy(L, k->M, sizeof L); chol(L, NV, NV);
+        memcpy(qas, qfs, sizeof(double) * NV); chol_solve(L, NV, NV, qas);
+        for (int a = 0; a < NV; a++) for (int b = 0; b < NV; b++) p->M[(size_t)(c * NV + a) * nv + c * NV + b] = k->M[a * NV + b];
+        nrows += e->n;
+    }
+    /* car-car contacts: hull vertex of A inside the hull bounding box of B */
+    typedef struct { int a, b; double dist, pos[3], frame[9]; } cc_t;
+    cc_t cc[WMAXCC]; int ncc = 0;
+    double lo[3] = {1e9, 1e9, 1e9}, hi[3] = {-1e9, -1e9, -1e9};
+    for (int v = 0; v < MUSHR_CHASSIS_NHULL; v++) for (int a = 0; a < 3; a++) { lo[a] = fmin(lo[a], m->hull[v][a]); hi[a] = fmax(hi[a], m->hull[v][a]); }
+    for (int A = 0; A < ncars; A++) for (int B = 0; B < ncars; B++) {
+        if (A == B || (shadowed && (shadowed[A] || shadowed[B]))) continue;
+        for (int v = 0; v < MUSHR_CHASSIS_NHULL && ncc < WMAXCC; v++) {
+            double pw[3], rel[3], ql[3];
+            mat_vec(pw, kin[A].xmat[1], m->hull[v]);
+            for (int a = 0; a < 3; a++) { pw[a] += kin[A].xpos[1][a]; rel[a] = pw[a] - kin[B].xpos[1][a]; }
+            const double* RB = kin[B].xmat[1];
+            for (int a = 0; a < 3; a++) ql[a] = RB[a] * rel[0] + RB[3 + a] * rel[1] + RB[6 + a] * rel[2];      /* R_B^T rel */
+            if (ql[0] <= lo[0] || ql[0] >= hi[0] || ql[1] <= lo[1] || ql[1] >= hi[1] || ql[2] <= lo[2] || ql[2] >= hi[2]) continue;
+            int axis = 0; double depth = 1e9, sign = 1;
+            for (int a = 0; a < 3; a++) {
+                if (ql[a] - lo[a] < depth) { depth = ql[a] - lo[a]; axis = a; sign = -1; }
+                if (hi[a] - ql[a] < depth) { depth = hi[a] - ql[a]; axis = a; sign = 1; }
+            }
+            cc_t* c = &cc[ncc++];
+            c->a = A; c->b = B; c->dist = -depth;
+            for (int a = 0; a < 3; a++) c->frame[a] = sign * RB[3 * a + axis];                                  /* outward normal of B's face */
+            make_frame(c->frame);
+            for (int a = 0; a < 3; a++) c->pos[a] = pw[a] + 0.5 * depth * c->frame[a];
+        }
+    }
+    p->n = nrows + 4 * ncc;
+    p->J = calloc((size_t)(p->n + 1) * nv, 8);
+    p->D = calloc(p->n + 1, 8); p->R = calloc(p->n + 1, 8); p->aref = calloc(p->n + 1, 8); p->floss = calloc(p->n + 1, 8);
+    p->type = calloc(p->n + 1, sizeof(int));
+    int r = 0;
+    for (int c = 0; c < ncars; c++) {
+        const efc_t* e = &efc[c];
+        for (int i = 0; i < e->n; i++, r++) {
+            memcpy(p->J + (size_t)r * nv + c * NV, e->J[i], sizeof(double) * NV);
+            p->D[r] = e->D[i]; p->R[r] = e->R[i]; p->aref[r] = e->aref[i]; p->floss[r] = e->floss[i]; p->type[r] = e->type[i];
+        }
+    }
+    for (int k = 0; k < ncc; k++) {
+        const cc_t* c = &cc[k];
+        double ja[3 * NV], jb[3 * NV], Jf[3][2 * NV];
+        jac_point(m, &kin[c->a], 1, c->pos, ja, 0);
+        jac_point(m, &kin[c->b], 1, c->pos, jb, 0);
+        for (int row = 0; row < 3; row++) for (int d = 0; d < NV; d++) {
+            Jf[row][d] = c->frame[3 * row] * ja[d] + c->frame[3 * row + 1] * ja[NV + d] + c->frame[3 * row + 2] * ja[2 * NV + d];
+            Jf[row][NV + d] = -(c->frame[3 * row] * jb[d] + c->frame[3 * row + 1] * jb[NV + d] + c->frame[3 * row + 2] * jb[2 * NV + d]);
+        }
+        const double mu = 1.0, diag = m->body_invweight0[1][0] + m->body_invweight0[1][0];
+        const double* va = qvel + (size_t)c->a * NV; const double* vb = qvel + (size_t)c->b * NV;
+        double Rn = 0, dummy;
+        row_softness(c->dist, diag, 0, &Rn, &dummy);
+        double Rpy = fmax(FTO_MINVAL, 2 * mu * mu * Rn);
+        for (int rr = 0; rr < 4; rr++, r++) {
+            double sgn = (rr & 1) ? -1 : 1; const double* Jt = Jf[1 + (rr >> 1)];
+            double* Jr = p->J + (size_t)r * nv; double vel = 0;
+            for (int d = 0; d < NV; d++) {
+                Jr[c->a * NV + d] = Jf[0][d] + sgn * mu * Jt[d];
+                Jr[c->b * NV + d] = Jf[0][NV + d] + sgn * mu * Jt[NV + d];
+                vel += Jr[c->a * NV + d] * va[d] + Jr[c->b * NV + d] * vb[d];
+            }
+            double Rrow, aref;
+            row_softness(c->dist, diag, vel, &Rrow, &aref);
+            p->R[r] = Rpy; p->D[r] = 1 / Rpy; p->aref[r] = aref; p->floss[r] = 0; p->type[r] = C_CONTACT;
+        }
+    }
+    return ncc;
+}
+
+/* One mj_step of an N-car world (N <= 8).  qpos [N][34], qvel / warm [N][29], ctrl [N][2]; shadowed [N] or NULL.
+ * info[0] = Newton iterations, info[1] = rows, info[2] = car-car contacts.  Returns 1 if the data was reset. */
+int fto_world_step(const fto_model* m, const fto_track* t, int ncars, double* qpos, double* qvel, double* warm,
+                   const double* ctrl, const uint8_t* shadowed, int* info) {
+    if (ncars < 1 || ncars > WMAXCARS) return -1;
+    int rc = 0;
+    if (bad(qpos, NQ * ncars) || bad(qvel, NV * ncars)) {                /* mj_checkPos / mj_checkVel reset the whole data */
+        for (int c = 0; c < ncars; c++) reset_data(m, qpos + (size_t)c * NQ, qvel + (size_t)c * NV, warm + (size_t)c * NV);
+        rc = 1;
+    }
+    kin_t* kin = malloc(sizeof(kin_t) * ncars); efc_t* efc = malloc(sizeof(efc_t) * ncars);
+    wprob_t p; memset(&p, 0, sizeof p);
+    int ncc = world_assemble(m, t, ncars, qpos, qvel, ctrl, shadowed, kin, efc, &p, 0);
+    const int nv = p.nv;
+    double* qacc = calloc(nv, 8); double* qfc = calloc(nv, 8);
+    int iters = wnewton(&p, m->meaninertia, warm, qacc, qfc);
+    if (bad(qacc, nv)) {
+        for (int c = 0; c < ncars; c++) reset_data(m, qpos + (size_t)c * NQ, qvel + (size_t)c * NV, warm + (size_t)c * NV);
+        rc = 1;
+    } else {
+        memcpy(warm, qacc, sizeof(double) * nv);
+        for (int c = 0; c < ncars; c++) {
+            double L[NV * NV], qa[NV];
+            memcpy(L, kin[c].M, sizeof L);
+            for (int d = 0; d < NV; d++) L[d * NV + d] += TIMESTEP * m->dof_damping[d];
+            chol(L, NV, NV);
+            for (int d = 0; d < NV; d++) qa[d] = p.qfs[c * NV + d] + qfc[c * NV + d];
+            chol_solve(L, NV, NV, qa);
+            for (int d = 0; d < NV; d++) qvel[(size_t)c * NV + d] += TIMESTEP * qa[d];
+            integrate_pos(m, qpos + (size_t)c * NQ, qvel + (size_t)c * NV, TIMESTEP);
+        }
+    }
+    if (info) { info[0] = iters; info[1] = p.n; info[2] = ncc; }
+    free(qacc); free(qfc); wprob_free(&p); free(kin); free(efc);
+    return rc;
+}
+
+/* TEST SUPPORT: the world problem, dense (M nv x nv, J n x nv ...); returns n rows or -1 if maxrows is too small. */
+int fto_world_problem(const fto_model* m, const fto_track* t, int ncars, const double* qpos, const double* qvel, const double* ctrl,
+                      int maxrows, double* M, double* qfs, double* J, double* D, double* R, double* aref, double* floss, int* type,
+                      int* ncc_out) {
+    if (ncars < 1 || ncars > WMAXCARS) return -1;
+    kin_t* kin = malloc(sizeof(kin_t) * ncars); efc_t* efc = malloc(sizeof(efc_t) * ncars);
+    wprob_t p; memset(&p, 0, sizeof p);
+    int ncc = world_assemble(m, t, ncars, qpos, qvel, ctrl, 0, kin, efc, &p, 0);
+    int n = p.n <= maxrows ? p.n : -1;
+    if (n >= 0) {
+        memcpy(M, p.M, sizeof(double) * p.nv * p.nv); memcpy(qfs, p.qfs, sizeof(double) * p.nv);
+        memcpy(J, p.J, sizeof(double) * (size_t)n * p.nv);
+        memcpy(D, p.D, 8 * n); memcpy(R, p.R, 8 * n); memcpy(aref, p.aref, 8 * n); memcpy(floss, p.floss, 8 * n); memcpy(type, p.type, sizeof(int) * n);
+    }
+    if (ncc_out) *ncc_out = ncc;
+    wprob_free(&p); free(kin); free(efc);
+    return n;
+}

@@ -532,3 +532,68 @@ def test_euler_update_against_numpy_restatement(model, otracks):
                 q1 = _integrate_pos(q0, v1, h)
                 worst = max(worst, np.abs(v1 - v).max() / (1 + np.abs(v).max()), np.abs(q1 - q).max())
     assert worst < 1e-8, worst                                      # measured 1.3e-10 (D up to 1e6 times rounding of the residuals)
+
+
+# ---------------------------------------------------------------------------------------------- N-car worlds (oracle only)
+def test_world_step_of_one_car_is_the_single_car_step(model):
+    """The world-level solver (dynamic sizes, one Newton problem over all cars) restricted to one car reproduces fto_step
+    bit for bit: same rows, same order of operations."""
+    q, v, w = model.reset(3.0, -4.0, 0.5)
+    ctrl = np.array([2.0, 0.3])
+    for k in range(120):
+        q1, v1, w1 = q.copy(), v.copy(), w.copy()
+        _, i1 = model.step(None, q1, v1, w1, ctrl)
+        Q, V, W = q[None].copy(), v[None].copy(), w[None].copy()
+        _, iw = model.world_step(None, Q, V, W, ctrl[None])
+        assert np.array_equal(Q[0], q1) and np.array_equal(V[0], v1) and np.array_equal(W[0], w1) and iw[0] == i1[0]
+        q, v, w = q1, v1, w1
+
+
+def test_world_of_distant_cars_agrees_with_independent_cars(model):
+    """Cars that do not touch are coupled only through the shared line search and stopping rule of the world's single
+    Newton problem: both converge to the same minimisers (deviation far below the 1e-5 bar; measured 2e-13)."""
+    n = 3
+    Q = np.zeros((n, 34)); V = np.zeros((n, 29)); W = np.zeros((n, 29))
+    U = np.array([[2.0, 0.3], [3.0, -0.5], [1.0, 0.0]])
+    for c in range(n):
+        Q[c], V[c], W[c] = model.reset(5.0 * c, -3.0, 0.3 * c)
+    Qi, Vi, Wi = Q.copy(), V.copy(), W.copy()
+    for k in range(150):
+        _, info = model.world_step(None, Q, V, W, U)
+        assert info[2] == 0
+        for c in range(n):
+            model.step(None, Qi[c], Vi[c], Wi[c], U[c])
+        np.testing.assert_allclose(Q, Qi, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(V, Vi, rtol=1e-9, atol=1e-9)
+
+
+def test_world_with_touching_cars(model):
+    """Car-car contacts (this framework's definition: hull vertex of A inside the hull box of B): the rear car drives into
+    the stationary front car and pushes it; the coupled world problem's solution equals the independent numpy minimiser;
+    the contact rows act with opposite sign on the two cars' translation dofs; a shadowed car is passed through."""
+    def spawn():
+        Q = np.zeros((2, 34)); V = np.zeros((2, 29)); W = np.zeros((2, 29))
+        Q[0], V[0], W[0] = model.reset(10.0, -10.0, 0.0)
+        Q[1], V[1], W[1] = model.reset(10.17, -10.01, 0.1)
+        return Q, V, W
+    U = np.array([[2.0, 0.0], [0.0, 0.0]])
+    Q, V, W = spawn()
+    seen = 0
+    for k in range(80):
+        if k in (3, 30, 70):
+            M, qfs, J, D, R, aref, fl, ty, ncc = model.world_problem(None, Q, V, U)
+            assert ncc >= 1
+            cc = J[len(ty) - 4 * ncc:]                               # car-car rows are last
+            assert np.abs(cc[:, 0:3] + cc[:, 29:32]).max() < 1e-12   # action = -reaction on the translation dofs
+            Q2, V2, W2 = Q.copy(), V.copy(), W.copy()
+            model.world_step(None, Q2, V2, W2, U)
+            a = _independent_minimiser(M, qfs, J, D, R, aref, fl, ty)
+            assert np.abs(a - W2.ravel()).max() < 1e-7 * (1 + np.abs(a).max())
+        _, info = model.world_step(None, Q, V, W, U)
+        seen += info[2] > 0
+    assert seen > 40 and V[1, 0] > 0.1 and Q[1, 0] - Q[0, 0] > 0.15      # the front car is being pushed, not run through
+    Q, V, W = spawn()
+    for k in range(80):
+        _, info = model.world_step(None, Q, V, W, U, shadowed=[0, 1])
+        assert info[2] == 0
+    assert abs(V[1, 0]) < 1e-2 and Q[0, 0] > 10.05                        # the shadowed car is not pushed; the other drove on
