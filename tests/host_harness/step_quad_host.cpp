@@ -104,3 +104,94 @@ extern "C" int hq_step_staged(double* qpos, double* qvel, double* warm, const do
     if (nsuspended) *nsuspended = nsus[0];
     return 0;
 }
+
+// ---- a whole "warp" (and CTA) of NQ quads on the host: EVERY collective is a barrier over all 4 NQ threads, exactly as
+// the device's full-mask shuffles / ballots / __syncthreads_or need every lane to arrive.  Control flow that is not
+// uniform across the quads of a warp (a quad that returns before a trailing collective, a loop one quad leaves early)
+// therefore hangs here, on the CPU build box, instead of hanging a GPU.
+struct WarpBarrier {
+    int nthreads; std::atomic<int> count{0}, gen{0};
+    void wait() {
+        const int g = gen.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) == nthreads - 1) { count.store(0, std::memory_order_relaxed); gen.store(g + 1, std::memory_order_release); }
+        else { int spins = 0; while (gen.load(std::memory_order_acquire) == g) if (++spins > 200) std::this_thread::yield(); }
+    }
+};
+struct WarpHostShared {
+    WarpBarrier bar; int nq;
+    std::vector<double> slot; std::vector<unsigned> bits;
+    std::vector<double> priv, shr; double ktab[QK_N];
+};
+template <int NQ_>
+struct WarpQuadHost {
+    static constexpr int PS = 4 * NQ_, CS = NQ_;
+    WarpHostShared* s; int w, quad, tid;
+    double& P(int i) const { return s->priv[(size_t)i * PS + tid]; }
+    double& C(int i) const { return s->shr[(size_t)i * CS + quad]; }
+    double K(int i) const { return s->ktab[i]; }
+    int lane() const { return w; }
+    double sum(double v) const {
+        s->slot[tid] = v; s->bar.wait();
+        const int b = 4 * quad;
+        const double a = v + s->slot[b + (w ^ 1)], c = s->slot[b + (w ^ 2)] + s->slot[b + (w ^ 3)];
+        s->bar.wait();
+        return a + c;
+    }
+    unsigned ballot(bool p) const {
+        s->bits[tid] = p ? 1u : 0u; s->bar.wait();
+        const int b = 4 * quad;
+        const unsigned m = s->bits[b] | s->bits[b + 1] << 1 | s->bits[b + 2] << 2 | s->bits[b + 3] << 3;
+        s->bar.wait();
+        return m;
+    }
+    bool any(bool p) const { return ballot(p) != 0; }
+    bool wany(bool p) const {
+        s->bits[tid] = p ? 1u : 0u; s->bar.wait();
+        unsigned m = 0; for (int i = 0; i < 4 * NQ_; i++) m |= s->bits[i];
+        s->bar.wait();
+        return m != 0;
+    }
+    bool cany(bool p) const { return wany(p); }
+    void sync() const { s->bar.wait(); }
+};
+
+// NQ cars stepped together as one warp / CTA with a staged solve: k1 Newton rounds, then the suspended cars (alone or
+// with finished neighbours idling as dead quads) to convergence.  Returns the number of suspensions.
+template <int NQ_>
+static int warp_step(double* qpos, double* qvel, double* warm, const double* ctrl, int* info4, int k1) {
+    WarpHostShared sh; sh.bar.nthreads = 4 * NQ_; sh.nq = NQ_;
+    sh.slot.assign(4 * NQ_, 0); sh.bits.assign(4 * NQ_, 0); sh.priv.assign((size_t)QP_N * 4 * NQ_, 0); sh.shr.assign((size_t)QC_N * NQ_, 0);
+    for (int g = 0; g < 25; g++) quad_const_entry(g_mc, g, sh.ktab);
+    std::vector<double> recs((size_t)QREC_DOUBLES * NQ_);
+    std::vector<int> suspended(NQ_, 0);
+    std::vector<std::thread> th;
+    for (int tid = 0; tid < 4 * NQ_; tid++)
+        th.emplace_back([&, tid]() {
+            WarpQuadHost<NQ_> q; q.s = &sh; q.tid = tid; q.w = tid & 3; q.quad = tid >> 2;
+            const int i = q.quad;
+            StepInfo si;
+            bool sus = step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), true, si,
+                                     QStage{k1, false, recs.data() + (size_t)i * QREC_DOUBLES});
+            q.sync();
+            if (q.w == 0) suspended[i] = sus;
+            q.sync();
+            // second launch: every quad takes part (the finished ones as dead quads, like the padding of a resume batch)
+            bool anysus = false; for (int c = 0; c < NQ_; c++) anysus |= suspended[c] != 0;
+            if (anysus) {
+                StepInfo s2;
+                const bool live = suspended[i] != 0;
+                step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), live, s2,
+                              QStage{0, true, recs.data() + (size_t)i * QREC_DOUBLES});
+                if (live) si = s2;
+                q.sync();
+            }
+            if (info4 && q.w == 0) { info4[4 * i] = si.iters; info4[4 * i + 1] = si.ncon_wheel; info4[4 * i + 2] = si.ncon_wall; info4[4 * i + 3] = si.reset; }
+        });
+    for (auto& t2 : th) t2.join();
+    int ns = 0; for (int c = 0; c < NQ_; c++) ns += suspended[c];
+    return ns;
+}
+extern "C" int hq_step_warp4(double* qpos, double* qvel, double* warm, const double* ctrl, int* info4, int k1) {
+    if (!g_ready) { g_mc = model_constants(); g_ready = true; }
+    return warp_step<4>(qpos, qvel, warm, ctrl, info4, k1);
+}

@@ -597,3 +597,16 @@ def test_world_with_touching_cars(model):
         _, info = model.world_step(None, Q, V, W, U, shadowed=[0, 1])
         assert info[2] == 0
     assert abs(V[1, 0]) < 1e-2 and Q[0, 0] > 10.05                        # the shadowed car is not pushed; the other drove on
+
+
+def test_quad_kernel_source_as_a_warp_of_quads_is_deadlock_free_and_bit_identical(host_quad_kernel):
+    """Four quads as ONE warp on the host, every collective a barrier over all 16 threads (what full-mask shuffles and
+    __syncthreads_or demand on the device), staged solve with cars that need different numbers of Newton rounds: must
+    finish (a quad leaving before a trailing collective hangs it -- the bug that once cost a 20-minute GPU hang is caught
+    here) and reproduce the single-quad results bit for bit."""
+    import sys
+    script = os.path.join(ROOT, "tests", "host_harness", "warp_lockstep_check.py")
+    lib = os.path.join(ROOT, "tests", "host_harness", "libstep_quad_host.so")
+    out = subprocess.run([sys.executable, script, ROOT, lib, "60"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.startswith("ok") and int(out.stdout.split()[1]) > 100          # suspensions really happened
