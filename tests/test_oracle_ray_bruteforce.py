@@ -95,3 +95,60 @@ def test_oracle_scan_matches_bruteforce_triangle_mesh(name, nposes, otracks, wal
             else:
                 worst = max(worst, abs(want - got[k, j]))
     assert edge <= 2 and worst < 1e-9, (edge, worst)
+
+
+def cylinder_mesh(pose, nfacets=1440):
+    """Triangles of another car's lidar cylinder (mushr.em.xml:108): r = 0.03, half height 0.015, centred at
+    (-0.0525, 0, 0.0575) in the car frame; side facets + two caps.  Chord error r (1 - cos(pi / n)) = 7e-8 m."""
+    w, x, y, z = pose[3:7] / np.linalg.norm(pose[3:7])
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    c = np.array([-0.0525, 0.0, 0.0575])
+    a = np.linspace(0, 2 * np.pi, nfacets + 1)
+    ring = np.stack([0.03 * np.cos(a), 0.03 * np.sin(a), np.zeros_like(a)], 1)
+    top, bot = ring + [0, 0, 0.015], ring - [0, 0, 0.015]
+    ctop, cbot = np.array([0, 0, 0.015]), np.array([0, 0, -0.015])
+    tris = []
+    for i in range(nfacets):
+        tris += [[bot[i], bot[i + 1], top[i + 1]], [bot[i], top[i + 1], top[i]], [ctop, top[i], top[i + 1]], [cbot, bot[i + 1], bot[i]]]
+    t = np.array(tris) + c
+    return t @ R.T + pose[:3]
+
+
+def test_oracle_world_scan_matches_bruteforce_with_other_cars(otracks, walls):
+    """Multi-car worlds (BASELINE config 5): each car's 90 rays against the walls AND the other cars' lidar cylinders
+    (its own is excluded: mj_ray's bodyexclude; a shadowed car is invisible), oracle scan_world vs the brute-force
+    caster over the wall mesh plus explicitly triangulated cylinders, for a tight cluster of four cars."""
+    wall, svg = walls["track"]
+    t = otracks["track"]
+    path = t.centreline(svg)
+    tris = chunk_mesh(wall)
+    n = 4
+    rng = np.random.default_rng(5)
+    poses = np.zeros((n, 7))
+    off = [(0.0, 0.0), (0.35, 0.05), (-0.30, 0.20), (0.10, -0.38)]          # a tight cluster: several beams end on a cylinder
+    for i in range(n):
+        yaw = rng.uniform(-3, 3)
+        poses[i] = [path[10, 0] + off[i][0], path[10, 1] + off[i][1], 0.0156, np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)]
+    vis = np.array([1, 1, 0, 1], dtype=np.uint8)                 # car 2 is shadowed: nobody sees it
+    got = t.scan_world(poses, vis)
+    alone = t.scan(poses)
+    cyl = [cylinder_mesh(poses[i]) for i in range(n)]
+    rx, rz, lr = -0.0525, 0.065, 0.03
+    seen_cars = 0
+    for i in range(n):
+        others = [cyl[j] for j in range(n) if j != i and vis[j]]
+        mesh = np.concatenate([tris] + others, 0)
+        w, x, y, z = poses[i, 3:7]
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                      [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                      [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        for j in range(90):
+            b = np.radians(4 * j - 90)
+            d = R @ np.array([np.sin(b), -np.cos(b), 0.0])
+            o = poses[i, :3] + R @ np.array([rx - lr * np.sin(b), lr * np.cos(b), rz])
+            want = brute_ray(mesh, o, d)
+            assert (want < 0) == (got[i, j] < 0) and abs(want - got[i, j]) < 2e-6, (i, j, want, got[i, j])
+            seen_cars += abs(got[i, j] - alone[i, j]) > 1e-3
+    assert seen_cars >= 8                                         # several rays really end on another car's cylinder
