@@ -45,7 +45,8 @@ SIGNATURES = {
     "ftgp_lidar": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "ftgp_lidar_host": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "ftgp_reset": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "ftgp_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "ftgp_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "ftgp_release_scratch": (_i, [_vp]),
     "ftgp_drivers": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp]),
     "ftgp_lap_update": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i, C.c_int32, C.c_int32, _vp]),
     "ftgp_tick": (_i, [C.POINTER(TickArgs), _i, _vp]),
@@ -59,7 +60,7 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise FtgpError(f"{LIB_PATH} is missing: build it with `python -m ft_grandprix_b200.build` "
+        raise FtgpError(f"{LIB_PATH} is missing: build it with `python ft_grandprix_b200/build.py` "
                         "(nvcc, sm_100a). There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():

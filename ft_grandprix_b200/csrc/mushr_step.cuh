@@ -12,8 +12,8 @@
 //   * constraint rows are implicit: friction / limit / equality rows are (dof, sign, D, aref) tuples,
 //     contact rows keep a 3x9 Jacobian (6 chassis dofs + 3 chain dofs);
 //   * fp64 throughout (MuJoCo's mjtNum), state rows of 34/29/29/2 doubles.  In THIS file one thread advances one car:
-//     it is the reference statement of the arithmetic (A/B kernel FTGP_STEP_IMPL=thread, and the source the CPU tests
-//     compile for the host); the production mapping, four lanes per car, is mushr_step_quad.cuh and shares these helpers.
+//     it is the plain statement of the arithmetic (the source the CPU tests compile for the host, and what evaluates the
+//     model's compile-time constants); the production mapping, four lanes per car, is mushr_step_quad.cuh and shares these helpers.
 // Everything is __host__ __device__ so the same source is unit-tested on the CPU build box (tests/
 // compile it with g++) before it ever runs on a B200.
 #pragma once

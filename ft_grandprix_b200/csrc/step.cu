@@ -77,56 +77,6 @@ __device__ bool wall_probe(const uint32_t* blob, const TrackHeader* th, const do
     return true;
 }
 
-struct Walls {                                  // thread-per-car flavour
-    const uint32_t* blob; const TrackHeader* th;
-    __device__ void operator()(const ModelConsts& mc, const Kin& k, Rows& r) const {
-        if (!blob) return;
-        for (int v = 0; v < MUSHR_CHASSIS_NHULL && r.ncon < MAXCON; v++) {
-            WallHit h;
-            if (!wall_probe(blob, th, k.R1, k.p1, v, h)) continue;
-            Contact& c = r.con[r.ncon++];
-            c.dist = h.dist; c.mu = 1.0; c.dmin = 0.9; c.wheel = -1; c.tran = mc.chassis_invweight0;
-            double off[3];
-            for (int a = 0; a < 3; a++) off[a] = h.pnt[a] - k.com[a];
-            for (int col = 0; col < 9; col++) {
-                double jp[3] = {0, 0, 0};
-                if (col < 6) { cross3(jp, k.cdof[col], off); for (int a = 0; a < 3; a++) jp[a] += k.cdof[col][3 + a]; }
-                c.J[0][col] = dot3(h.nrm, jp); c.J[1][col] = dot3(h.t1, jp); c.J[2][col] = dot3(h.t2, jp);
-            }
-        }
-    }
-};
-
-__global__ void __launch_bounds__(64)
-step_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
-            double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
-            const int32_t* __restrict__ lap, int64_t ncars, int nsteps, int32_t* __restrict__ status) {
-    const int64_t car = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (car >= ncars) return;
-    double q[NQ], v[NV], w[NV], u[2];
-    for (int i = 0; i < NQ; i++) q[i] = qpos[car * NQ + i];
-    for (int i = 0; i < NV; i++) { v[i] = qvel[car * NV + i]; w[i] = warm[car * NV + i]; }
-    u[0] = ctrl[2 * car]; u[1] = ctrl[2 * car + 1];
-    Walls walls{nullptr, nullptr};
-    // a finished ("shadowed") car no longer collides with walls: conaffinity 0 / contype 2 (custom.py:1455-1464)
-    const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
-    if (blob && !shadowed) {
-        const GeomHeader* gh = reinterpret_cast<const GeomHeader*>(blob);
-        int tid = track_id ? track_id[car] : 0;
-        if (tid < 0 || tid >= gh->ntracks) tid = 0;
-        walls.blob = blob; walls.th = reinterpret_cast<const TrackHeader*>(blob + gh->track_off[tid]);
-    }
-    int st = 0;
-    for (int s = 0; s < nsteps; s++) {
-        StepInfo info;
-        step_car(c_model, q, v, w, u, walls, info);
-        st = (info.iters & 0xFF) | (info.reset ? 0x100 : (st & 0x100)) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24);
-    }
-    for (int i = 0; i < NQ; i++) qpos[car * NQ + i] = q[i];
-    for (int i = 0; i < NV; i++) { qvel[car * NV + i] = v[i]; warm[car * NV + i] = w[i]; }
-    if (status) status[car] = st;
-}
-
 struct WallsQuad {                              // quad-per-car flavour: probe of one hull vertex
     const uint32_t* blob; const TrackHeader* th;
     __device__ __forceinline__ bool enabled() const { return blob != nullptr; }
@@ -242,150 +192,123 @@ __global__ void order_scatter_kernel(const int32_t* __restrict__ status, int64_t
     __syncthreads();
     if (i < ncars) perm[base[bin] + rank] = (int32_t)i;
 }
-// one scratch per (device, stream): fleets stepped concurrently on different streams must not share it
-struct OrderScratch {
-    int dev = -1; cudaStream_t stream = nullptr; int32_t* perm = nullptr; int32_t* counters = nullptr; int64_t cap = 0; uint64_t used = 0;
+// one scratch per (device, stream): fleets stepped concurrently on different streams must not share it.  Every access
+// (lookup, growth, the launches that use it) happens under g_step_mutex, so host threads never race on it; the launches
+// themselves are asynchronous, so the lock is held for microseconds.  ftgp_release_scratch() frees a stream's scratch.
+struct StepScratch {
+    int dev = -1; cudaStream_t stream = nullptr; uint64_t used = 0;
+    int32_t* perm = nullptr; int32_t* counters = nullptr; int64_t cap = 0;                                          // regrouping
     double* recs = nullptr; int32_t* lists = nullptr; int32_t* stage_counts = nullptr; int64_t stage_cap = 0;      // staged solve
+    void release() {
+        if (dev < 0) return;
+        int cur = 0;
+        cudaGetDevice(&cur); cudaSetDevice(dev);
+        if (perm) cudaFree(perm);
+        if (counters) cudaFree(counters);
+        if (recs) cudaFree(recs);
+        if (lists) cudaFree(lists);
+        if (stage_counts) cudaFree(stage_counts);
+        cudaSetDevice(cur);
+        *this = StepScratch();
+    }
 };
-static OrderScratch g_order[64];
-static std::mutex g_order_mutex;
-static uint64_t g_order_clock = 0;
-static OrderScratch* order_scratch(int dev, cudaStream_t stream) {
-    std::lock_guard<std::mutex> lock(g_order_mutex);
-    OrderScratch* lru = &g_order[0];
-    for (auto& o : g_order) {
-        if (o.dev == dev && o.stream == stream) { o.used = ++g_order_clock; return &o; }
+static StepScratch g_scratch[64];
+static std::mutex g_step_mutex;
+static uint64_t g_scratch_clock = 0;
+static int g_sm_count[16] = {0};
+static bool g_attr_ready[16] = {false};
+
+static StepScratch* step_scratch(int dev, cudaStream_t stream) {       // caller holds g_step_mutex
+    StepScratch* lru = &g_scratch[0];
+    for (auto& o : g_scratch) {
+        if (o.dev == dev && o.stream == stream) { o.used = ++g_scratch_clock; return &o; }
         if (o.used < lru->used) lru = &o;
     }
-    // not found: take a free slot, else recycle the least recently used one (cudaFree waits for work that uses it)
-    if (lru->dev >= 0) {
-        int cur = 0;
-        cudaGetDevice(&cur); cudaSetDevice(lru->dev);
-        if (lru->perm) cudaFree(lru->perm);
-        if (lru->counters) cudaFree(lru->counters);
-        if (lru->recs) cudaFree(lru->recs);
-        if (lru->lists) cudaFree(lru->lists);
-        if (lru->stage_counts) cudaFree(lru->stage_counts);
-        cudaSetDevice(cur);
-    }
-    *lru = OrderScratch();
-    lru->dev = dev; lru->stream = stream; lru->used = ++g_order_clock;
+    lru->release();              // not found: a free slot, else the least recently used one (cudaFree waits for its work)
+    lru->dev = dev; lru->stream = stream; lru->used = ++g_scratch_clock;
     return lru;
 }
 
-// cars grouped by (last Newton iteration count, wall contact) for the kernels that run several cars in lock-step
-static int order_cars(const int32_t* status, int64_t ncars, int dev, cudaStream_t stream, const int32_t** perm) {
-    *perm = nullptr;
-    static int use_order = -1;
-    if (use_order < 0) { const char* e = getenv("FTGP_STEP_ORDER"); use_order = (e && e[0] == '0') ? 0 : 1; }
-    if (!use_order || !status || ncars < 1024 || ncars >= (int64_t)1 << 31 || dev >= 16) return FTGP_OK;
-    OrderScratch* op = order_scratch(dev, stream);
-    if (!op) return FTGP_OK;
-    OrderScratch& o = *op;
-    if (o.cap < ncars) {
-        if (o.perm) cudaFree(o.perm);
-        if (!o.counters) FTGP_CUDA(cudaMalloc(&o.counters, 2 * NBIN * sizeof(int32_t)));
-        o.perm = nullptr; o.cap = 0;
-        FTGP_CUDA(cudaMalloc(&o.perm, ncars * sizeof(int32_t)));
-        o.cap = ncars;
-    }
-    FTGP_CUDA(cudaMemsetAsync(o.counters, 0, 2 * NBIN * sizeof(int32_t), stream));
-    const unsigned nb = (unsigned)((ncars + 255) / 256);
-    order_hist_kernel<<<nb, 256, 0, stream>>>(status, ncars, o.counters);
-    order_scatter_kernel<<<nb, 256, 0, stream>>>(status, ncars, o.counters, o.counters + NBIN, o.perm);
-    count_launch(2);
-    *perm = o.perm;
-    return FTGP_OK;
-}
+// The production mapping is frozen: 216-thread CTAs (54 cars, 6 warps + 24 lanes), CTA-level lock-step of the Newton
+// loop, cars regrouped by (last Newton iteration count, wall contact), staged solve with two Newton rounds in the first
+// launch (DESIGN.md 8 lists the measured alternatives; the A/B variants live in tests/host_harness, not in this library).
+// NOTE on the 24-lane tail warp: QuadDev's collectives use the full mask; lanes 24-31 of that warp do not exist (they
+// count as exited threads, which *_sync primitives ignore), and every quad is 4 lanes inside one warp.
+constexpr int STEP_NT = 216;
+constexpr int STAGE_ROUNDS = 2;
+constexpr int64_t ORDER_MIN_CARS = 1024, STAGE_MIN_CARS = 4096;
 
 int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
                 const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
                 cudaStream_t stream) {
     int dev = 0;
     FTGP_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) { set_error("ftgp_step: device index %d not supported", dev); return FTGP_ERR_UNSUPPORTED; }
+    std::lock_guard<std::mutex> lock(g_step_mutex);
     int rc = ensure_model(dev); if (rc) return rc;
-    // Two implementations of the same arithmetic (both parity-tested), FTGP_STEP_IMPL = quad (default) | thread:
-    //   quad   four lanes per car, one per wheel chain (mushr_step_quad.cuh): 1.47 ms per 65,536 cars
-    //   thread one thread per car (mushr_step.cuh): 16.7 KB local frame per thread, DRAM-latency bound, 5.3 ms; kept as the
-    //          A/B reference (it is also the source the CPU tests compile for the host)
-    // (a third mapping, one warp per car with the state in shared memory, measured 5.2 ms and was removed: DESIGN.md 3.2)
-    static int impl = -1;
-    if (impl < 0) { const char* e = getenv("FTGP_STEP_IMPL"); impl = (e && e[0] == 't') ? 1 : 2; }
-    const uint32_t* blob = g ? g->d_blob : nullptr;
-    if (impl == 2) {
-        static int qt = 0, lock = 1;
-        if (!qt) {
-            const char* e = getenv("FTGP_STEP_QT"); qt = e ? atoi(e) : 216; if (qt != 128 && qt != 192 && qt != 216) qt = 216;
-            const char* l = getenv("FTGP_STEP_LOCK"); lock = (l && l[0] == '0') ? 0 : 1;
-        }
-        const int32_t* perm = nullptr;
-        if ((rc = order_cars(status, ncars, dev, stream, &perm))) return rc;
-        // Staged solve (default for one step of a big fleet): K1 Newton rounds in the first launch, then the cars that are
-        // not done yet are packed into fresh CTAs: (optionally K2 more rounds, then) to convergence.  FTGP_STEP_K1=0
-        // switches it off.  Measured at 65,536 cars: 1.39 ms unstaged, 1.32 ms with K1 = 2 (the records cost 5.9 KB per car;
-        // if they cannot be allocated the step runs unstaged).
-        static int k1 = -1, k2 = 1;
-        if (k1 < 0) {
-            const char* e = getenv("FTGP_STEP_K1"); k1 = e ? atoi(e) : 2;
-            const char* f = getenv("FTGP_STEP_K2"); k2 = f ? atoi(f) : 0;
-        }
-        double* recs = nullptr; int32_t* lists = nullptr; int32_t* counts = nullptr;
-        if (k1 > 0 && nsteps == 1 && ncars >= 4096 && ncars < (int64_t)1 << 31 && qt == 216) {
-            OrderScratch* o = order_scratch(dev, stream);
-            if (o->stage_cap < ncars) {
-                if (o->recs) cudaFree(o->recs);
-                if (o->lists) cudaFree(o->lists);
-                o->recs = nullptr; o->lists = nullptr; o->stage_cap = 0;
-                if (!o->stage_counts) FTGP_CUDA(cudaMalloc(&o->stage_counts, 4 * sizeof(int32_t)));
-                if (cudaMalloc(&o->recs, (size_t)ncars * QREC_DOUBLES * sizeof(double)) == cudaSuccess &&
-                    cudaMalloc(&o->lists, (size_t)ncars * 2 * sizeof(int32_t)) == cudaSuccess) o->stage_cap = ncars;
-                else {                                    // no room for the records: run unstaged
-                    cudaGetLastError();
-                    if (o->recs) cudaFree(o->recs);
-                    o->recs = nullptr; o->lists = nullptr;
-                }
-            }
-            if (o->stage_cap >= ncars) {
-                recs = o->recs; lists = o->lists; counts = o->stage_counts;
-                FTGP_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), stream));
-            }
-        }
-        auto launch = [&](auto kern, size_t smem) -> int {
-            FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            FTGP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            kern<<<(unsigned)((ncars + qt / 4 - 1) / (qt / 4)), qt, smem, stream>>>(
-                blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status, recs, lists, counts, k1);
-            return FTGP_OK;
-        };
-        int rc2;
-        if (qt == 128) rc2 = launch(step_quad_kernel<128, true>, quad_smem_bytes<128>());
-        else if (qt == 216) rc2 = launch(step_quad_kernel<216, true>, quad_smem_bytes<216>());   // 54 cars: 6 warps + 24 lanes
-        else rc2 = lock ? launch(step_quad_kernel<192, true>, quad_smem_bytes<192>()) : launch(step_quad_kernel<192, false>, quad_smem_bytes<192>());
-        if (rc2) return rc2;
-        if (recs) {
-            static int nsm[16] = {0};
-            if (dev < 16 && !nsm[dev]) FTGP_CUDA(cudaDeviceGetAttribute(&nsm[dev], cudaDevAttrMultiProcessorCount, dev));
-            const int grid = dev < 16 ? nsm[dev] : 148;
-            const size_t smem = quad_smem_bytes<216>();
-            FTGP_CUDA(cudaFuncSetAttribute(step_quad_resume_kernel<216>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            FTGP_CUDA(cudaFuncSetAttribute(step_quad_resume_kernel<216>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            int32_t* la = lists; int32_t* lb = lists + ncars;
-            int ci = 0;
-            if (k2 > 0) {
-                step_quad_resume_kernel<216><<<grid, 216, smem, stream>>>(qpos, qvel, warm, ctrl, status, recs, la, counts + ci, lb, counts + ci + 1, k2);
-                count_launch();
-                std::swap(la, lb); ci++;
-            }
-            step_quad_resume_kernel<216><<<grid, 216, smem, stream>>>(qpos, qvel, warm, ctrl, status, recs, la, counts + ci, lb, counts + ci + 1, 0);
-            count_launch();
-        }
-    } else if (impl == 1) {
-        static int threads = 0;
-        if (!threads) { const char* e = getenv("FTGP_STEP_BLOCK"); threads = e ? atoi(e) : 64; if (threads < 32 || threads > 64) threads = 64; }
-        step_kernel<<<(unsigned)((ncars + threads - 1) / threads), threads, 0, stream>>>(
-            blob, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status);
+    constexpr size_t smem = quad_smem_bytes<STEP_NT>();
+    if (!g_attr_ready[dev]) {                       // once per device, not per launch
+        FTGP_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+        FTGP_CUDA(cudaFuncSetAttribute(step_quad_kernel<STEP_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FTGP_CUDA(cudaFuncSetAttribute(step_quad_kernel<STEP_NT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        FTGP_CUDA(cudaFuncSetAttribute(step_quad_resume_kernel<STEP_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FTGP_CUDA(cudaFuncSetAttribute(step_quad_resume_kernel<STEP_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        g_attr_ready[dev] = true;
     }
+    const uint32_t* blob = g ? g->d_blob : nullptr;
+    const bool big = ncars < (int64_t)1 << 31;
+    const bool reorder = status && big && ncars >= ORDER_MIN_CARS;
+    const bool staged = nsteps == 1 && big && ncars >= STAGE_MIN_CARS;
+    StepScratch* o = (reorder || staged) ? step_scratch(dev, stream) : nullptr;
+    // cars grouped by (last Newton iteration count, wall contact) for the kernel that runs 54 cars in lock-step
+    const int32_t* perm = nullptr;
+    if (reorder) {
+        if (o->cap < ncars) {
+            if (o->perm) cudaFree(o->perm);
+            o->perm = nullptr; o->cap = 0;
+            if (!o->counters) FTGP_CUDA(cudaMalloc(&o->counters, 2 * NBIN * sizeof(int32_t)));
+            FTGP_CUDA(cudaMalloc(&o->perm, ncars * sizeof(int32_t)));
+            o->cap = ncars;
+        }
+        FTGP_CUDA(cudaMemsetAsync(o->counters, 0, 2 * NBIN * sizeof(int32_t), stream));
+        const unsigned nb = (unsigned)((ncars + 255) / 256);
+        order_hist_kernel<<<nb, 256, 0, stream>>>(status, ncars, o->counters);
+        order_scatter_kernel<<<nb, 256, 0, stream>>>(status, ncars, o->counters, o->counters + NBIN, o->perm);
+        count_launch(2);
+        perm = o->perm;
+    }
+    // Staged solve (one step of a big fleet): STAGE_ROUNDS Newton rounds in the first launch, then the cars that are not
+    // done are packed into fresh CTAs by the persistent continuation kernel.  Measured at 65,536 cars: 1.39 ms unstaged,
+    // 1.31 ms staged.  If the records cannot be allocated the step runs unstaged.
+    double* recs = nullptr; int32_t* lists = nullptr; int32_t* counts = nullptr;
+    if (staged) {
+        if (o->stage_cap < ncars) {
+            if (o->recs) cudaFree(o->recs);
+            if (o->lists) cudaFree(o->lists);
+            o->recs = nullptr; o->lists = nullptr; o->stage_cap = 0;
+            if (!o->stage_counts) FTGP_CUDA(cudaMalloc(&o->stage_counts, 4 * sizeof(int32_t)));
+            if (cudaMalloc(&o->recs, (size_t)ncars * QREC_DOUBLES * sizeof(double)) == cudaSuccess &&
+                cudaMalloc(&o->lists, (size_t)ncars * 2 * sizeof(int32_t)) == cudaSuccess) o->stage_cap = ncars;
+            else {
+                cudaGetLastError();
+                if (o->recs) cudaFree(o->recs);
+                o->recs = nullptr; o->lists = nullptr;
+            }
+        }
+        if (o->stage_cap >= ncars) {
+            recs = o->recs; lists = o->lists; counts = o->stage_counts;
+            FTGP_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), stream));
+        }
+    }
+    constexpr int CARS = STEP_NT / 4;
+    step_quad_kernel<STEP_NT, true><<<(unsigned)((ncars + CARS - 1) / CARS), STEP_NT, smem, stream>>>(
+        blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status, recs, lists, counts, STAGE_ROUNDS);
     count_launch();
+    if (recs) {
+        step_quad_resume_kernel<STEP_NT><<<g_sm_count[dev], STEP_NT, smem, stream>>>(
+            qpos, qvel, warm, ctrl, status, recs, lists, counts, lists + ncars, counts + 1, 0);
+        count_launch();
+    }
     FTGP_CUDA(cudaGetLastError());
     return FTGP_OK;
 }
@@ -403,11 +326,20 @@ int launch_lap(const ftgp_geom* g, const double* qpos, int64_t stride, const int
 using namespace ftgp;
 
 extern "C" int ftgp_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
-                         const int32_t* track_id, int64_t ncars, int nsteps, int32_t* status, void* stream) {
+                         const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
+                         void* stream) {
     if (!qpos || !qvel || !warm || !ctrl || ncars < 0 || nsteps < 0) { set_error("ftgp_step: bad argument"); return FTGP_ERR_ARG; }
     if (ncars == 0 || nsteps == 0) return FTGP_OK;
     if (g) FTGP_CUDA(cudaSetDevice(g->device));
-    return launch_step(g, qpos, qvel, warm, ctrl, track_id, nullptr, ncars, nsteps, status, (cudaStream_t)stream);
+    return launch_step(g, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status, (cudaStream_t)stream);
+}
+
+extern "C" int ftgp_release_scratch(void* stream) {
+    int dev = 0;
+    FTGP_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_step_mutex);
+    for (auto& o : g_scratch) if (o.dev == dev && o.stream == (cudaStream_t)stream) o.release();
+    return FTGP_OK;
 }
 
 extern "C" int ftgp_tick(const ftgp_tick_args* a, int nticks, void* stream) {

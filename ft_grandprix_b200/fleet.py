@@ -68,6 +68,19 @@ class Fleet:
         self.steps = 0
         torch.cuda.synchronize(dev)
 
+    def close(self):
+        """Free the step kernel's per-stream scratch (about 6 KB per car)."""
+        if getattr(self, "stream", None) is not None and getattr(self, "lib", None) is not None:
+            with torch.cuda.device(self.device):
+                self.stream.synchronize()
+                self.lib.ftgp_release_scratch(self._s)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     # ------------------------------------------------------------------ helpers
     @property
     def _s(self):
@@ -135,8 +148,12 @@ class Fleet:
         self.sync()
         ranges = self.ranges.cpu().numpy().astype(np.float64)
         ctrl = self.ctrl.cpu().numpy()
+        finished = self.lap[:, LAP["finished"]].cpu().numpy()
         snaps = None
         for i, d in enumerate(drivers):
+            if finished[i]:                          # shadow() swapped in LobotomyDriver (custom.py:1437)
+                ctrl[i] = (0.0, 0.0)
+                continue
             try:
                 if len(inspect.signature(d.process_lidar).parameters) >= 2:   # v2 driver (custom.py:103)
                     if snaps is None:
@@ -150,10 +167,12 @@ class Fleet:
         self.ctrl.copy_(torch.from_numpy(ctrl))
         return self.ctrl
 
-    def step(self, nsteps=1):
-        """mujoco.mj_step(model, data) (custom.py:1425)."""
+    def step(self, nsteps=1, shadow_finished=True):
+        """mujoco.mj_step(model, data) (custom.py:1425).  Finished cars are shadow()ed as in the reference
+        (custom.py:1455-1464: they pass through walls) unless shadow_finished is False."""
         _lib.check(self.lib.ftgp_step(self.geom._ptr, _ptr(self.qpos), _ptr(self.qvel), _ptr(self.warm),
-                                      _ptr(self.ctrl), _ptr(self.track_id), self.ncars, int(nsteps),
+                                      _ptr(self.ctrl), _ptr(self.track_id),
+                                      _ptr(self.lap) if shadow_finished else None, self.ncars, int(nsteps),
                                       _ptr(self.status), self._s), "ftgp_step")
         self.steps += int(nsteps)
 

@@ -25,14 +25,11 @@ from .fleet import DRIVER_KINDS, LAP, TIMESTEP, Fleet
 from .track import Track
 
 
-def ordinal(n):                                      # custom.py:47-55
-    n = str(n)
-    if n == '0' or len(n) > 1 and n[-2] == '1': e = 'th'
-    elif n[-1] == '1': e = 'st'
-    elif n[-1] == '2': e = 'nd'
-    elif n[-1] == '3': e = 'rd'
-    else: e = 'th'
-    return n + e
+def ordinal(n):
+    """'1st', '2nd', '3rd', '4th', '11th', ... as the dashboard prints positions (behaviour of custom.py:47-55)."""
+    n = int(n)
+    suffix = "th" if 10 <= n % 100 <= 20 else {1: "st", 2: "nd", 3: "rd"}.get(n % 10, "th")
+    return f"{n}{suffix}"
 
 
 class LobotomyDriver:                                # ft_grandprix/lobotomy.py:1-3

@@ -113,9 +113,15 @@ int ftgp_reset(double* qpos, double* qvel, double* warm, double* ctrl, const dou
  * template/mushr.em.xml (timestep 0.004, Newton, pyramidal cones).  status: device
  * int32[ncars] or NULL, per car: bits 0-7 Newton iterations of the last step, bit 8 =
  * state was reset (MuJoCo's bad-state check), bits 16-23 wall contacts, bits 24-27
- * wheel-ground contacts.  g may be NULL (open ground plane, no walls). */
+ * wheel-ground contacts.  g may be NULL (open ground plane, no walls).  lap: device lap state
+ * (FTGP_LAP_* rows, see below) or NULL; a car whose FTGP_LAP_FINISHED field is set has been
+ * shadow()ed (custom.py:1455-1464: conaffinity 0 / contype 2): it no longer collides with walls. */
 int ftgp_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
-              const int32_t* track_id, int64_t ncars, int nsteps, int32_t* status, void* stream);
+              const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
+              void* stream);
+/* The step keeps per-(device, stream) scratch (regrouping lists, records of the staged solve: about
+ * 6 KB per car).  Frees the scratch of `stream` on the current device; call when a fleet is destroyed. */
+int ftgp_release_scratch(void* stream);
 
 /* ------------------------------------------------------------------ drivers */
 /* Device ports of the bundled drivers (nidc.py:116-131, fast.py:118-139, lobotomy.py:1-3)

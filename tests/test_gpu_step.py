@@ -44,7 +44,7 @@ def test_single_step_parity_1e5(ft, oracle):
     _load(fleet, Q, V, W, U)
     # open ground (no walls): pure MuJoCo-restated dynamics
     ft._lib.check(fleet.lib.ftgp_step(None, fleet.qpos.data_ptr(), fleet.qvel.data_ptr(), fleet.warm.data_ptr(),
-                                      fleet.ctrl.data_ptr(), None, n, 1, fleet.status.data_ptr(), fleet._s), "ftgp_step")
+                                      fleet.ctrl.data_ptr(), None, None, n, 1, fleet.status.data_ptr(), fleet._s), "ftgp_step")
     fleet.sync()
     info = model.step_n(None, Q, V, W, U)
     np.testing.assert_allclose(fleet.qpos.cpu().numpy(), Q, rtol=1e-5, atol=1e-10)
@@ -69,7 +69,7 @@ def test_trajectory_divergence_over_1000_ticks_is_reported(ft, oracle, capsys):
             U = np.stack([rng.uniform(0.5, 4, n), rng.uniform(-0.5, 0.5, n)], 1)
             fleet.ctrl.copy_(torch.from_numpy(U)); torch.cuda.synchronize()
         ft._lib.check(fleet.lib.ftgp_step(None, fleet.qpos.data_ptr(), fleet.qvel.data_ptr(), fleet.warm.data_ptr(),
-                                          fleet.ctrl.data_ptr(), None, n, 1, None, fleet._s), "ftgp_step")
+                                          fleet.ctrl.data_ptr(), None, None, n, 1, None, fleet._s), "ftgp_step")
         model.step_n(None, Q, V, W, U)
         if k % 100 == 99:
             fleet.sync()
