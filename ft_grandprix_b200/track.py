@@ -36,6 +36,8 @@ class Track:
             raise ValueError("pixels must be uint8/bool [H,W] (wall mask) or uint8 [H,W,3|4] (RGB)")
         px = np.ascontiguousarray(px)
         ch = 1 if px.ndim == 2 else px.shape[2]
+        # the wall mask itself (pixel is wall iff R+G+B == 765, chunk.py:39-43), kept for the rendered/ emitter (mjcf.py)
+        self.wall = px != 0 if px.ndim == 2 else px[:, :, :3].astype(np.int32).sum(2) == 765
         self.height, self.width = px.shape[:2]
         self.scale, self.chunk_px, self.name = float(scale), int(chunk_px), name
         lib = _lib.load()

@@ -11,6 +11,10 @@ frozen here as data:
   ft_grandprix_b200/assets/paths.json   per track: the `d` attribute of the first
                                         <g><path> of template/<track>-path.svg
                                         (ft_grandprix/curve.py:11-14)
+  ft_grandprix_b200/assets/meshes.npz   triangles + facet normals (float32) of
+                                        template/meshes/{simple_base_nano,mushr_wheel}.stl
+                                        (mushr.em.xml:38-39), re-serialised as binary STL by
+                                        the rendered/ emitter (ft_grandprix_b200/mjcf.py)
 
 No reference source code is copied, only the image/SVG *data* the reference
 ships as race inputs.
@@ -42,6 +46,15 @@ def main():
     np.savez_compressed(os.path.join(OUT, "tracks.npz"), **arrays)
     with open(os.path.join(OUT, "paths.json"), "w") as f:
         json.dump(paths, f, indent=1)
+    meshes = {}
+    for name in ("simple_base_nano", "mushr_wheel"):
+        b = open(os.path.join(REF, "template", "meshes", name + ".stl"), "rb").read()
+        n = int.from_bytes(b[80:84], "little")
+        assert 84 + 50 * n == len(b), "binary STL expected"
+        rec = np.frombuffer(b[84:], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+        meshes[name + "__tri"] = rec["v"].copy(); meshes[name + "__nrm"] = rec["n"].copy()
+        print(name, n, "triangles", file=sys.stderr)
+    np.savez_compressed(os.path.join(OUT, "meshes.npz"), **meshes)
 
 if __name__ == "__main__":
     main()

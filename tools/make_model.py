@@ -2,6 +2,10 @@
 """Derive the mesh-dependent compile-time constants of template/mushr.em.xml from the reference's STL
 assets (build container only; the GPU box has no reference tree).
 
+    python tools/make_model.py [--from-golden tests/golden/mujoco_golden.npz]
+
+With --from-golden the chassis CoM / inertia and the softener sphere are taken from constants captured from a real
+MuJoCo compile (tests/golden/make_mujoco_golden.py) instead of the restated rule.
 MuJoCo computes these when it compiles the MJCF; `mujoco` is absent here, so the
 "legacy" mesh-inertia rule (the default of the mesh `inertia` attribute in the pinned 3.2.x / 3.3.x
 releases) is restated: pyramids from the area-weighted face centroid to every triangle, |volume| each.
@@ -58,7 +62,38 @@ def hull_vertices(pts):
     return u[ConvexHull(u).vertices]
 
 
+def quat2mat(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def from_golden(path):
+    """Chassis CoM / inertia and the softener sphere from constants captured from a real MuJoCo compile
+    (tests/golden/make_mujoco_golden.py: const_body_*, const_geom_*).  Body 1 = `car #0` = chassis mesh + lidar
+    cylinder; the cylinder is analytic (density 1000, r 0.03, half height 0.015 at (-0.0525, 0, 0.0575),
+    mushr.em.xml:108), so the mesh's share is what is left."""
+    g = np.load(path, allow_pickle=False)
+    mb, ipos = float(g["const_body_mass"][1]), g["const_body_ipos"][1]
+    R = quat2mat(g["const_body_iquat"][1])
+    Ib = R @ np.diag(g["const_body_inertia"][1]) @ R.T                    # about ipos, body axes
+    lr, lh = 0.030, 0.015
+    lm = 1000.0 * np.pi * lr * lr * 2 * lh
+    lc = np.array([-0.0525, 0.0, 0.065 - lh / 2])
+    Il = np.diag([lm * (3 * lr * lr + 4 * lh * lh) / 12] * 2 + [lm * lr * lr / 2])
+    mass = mb - lm
+    com = (mb * ipos - lm * lc) / mass
+    shift = lambda m, d: m * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
+    I = Ib - Il - shift(lm, lc - ipos) - shift(mass, com - ipos)          # chassis about its own CoM
+    sid = int(g["const_softener_geom_ids"][0])
+    return mass, com, I, float(g["const_geom_size"][sid][0]), g["const_geom_pos"][sid]
+
+
 def main():
+    golden = None
+    if "--from-golden" in sys.argv:
+        golden = from_golden(sys.argv[sys.argv.index("--from-golden") + 1])
     base = load_stl(os.path.join(REF, "template/meshes/simple_base_nano.stl")) * 0.5          # mushr.em.xml:38
     wheel = load_stl(os.path.join(REF, "template/meshes/mushr_wheel.stl")) * (0.5 * 1.3)       # mushr.em.xml:39
     # chassis geom: mass 3.542137 at geom pos (0, 0, 0.5 * 0.094655) (mushr.em.xml:119)
@@ -75,13 +110,21 @@ def main():
     ev = np.linalg.eigvalsh(wI)
     hs = [0.5 * np.sqrt(6 * (ev[(k + 1) % 3] + ev[(k + 2) % 3] - ev[k]) / wvol) for k in range(3)]
     radius = float(np.mean(hs)) * 2.0
-    soft = {"radius": radius, "center": wcom.tolist(), "mass": 1e-5, "box_half": [float(h) for h in hs]}
-    out = {"chassis": chassis, "softener": soft,
-           "rule": "MuJoCo legacy mesh inertia restated (parity unpinned: mujoco absent)"}
+    rule = "MuJoCo legacy mesh inertia restated (parity unpinned: mujoco absent)"
+    if golden is not None:                                   # constants of a real MuJoCo compile win over the restated rule
+        gm, gcom, gI, gr, gc = golden
+        print("restated vs MuJoCo: chassis com", chassis["com"], gcom.tolist(), "inertia diag", np.diag(I), np.diag(gI),
+              "softener radius", radius, gr, file=sys.stderr)
+        assert abs(gm - mass) < 1e-6, (gm, mass)
+        I, radius, wcom = gI, gr, np.asarray(gc)
+        chassis["com"], chassis["inertia"] = gcom.tolist(), gI.tolist()
+        rule = "captured from a MuJoCo compile (tests/golden/mujoco_golden.npz)"
+    soft = {"radius": radius, "center": np.asarray(wcom).tolist(), "mass": 1e-5, "box_half": [float(h) for h in hs]}
+    out = {"chassis": chassis, "softener": soft, "rule": rule}
     json.dump(out, open(os.path.join(ROOT, "tests/golden/mushr_mesh.json"), "w"), indent=1)
     H = chassis["hull"]
     body = ["/* GENERATED by tools/make_model.py from template/meshes/ STL files -- do not edit.",
-            " * Mesh-derived constants of template/mushr.em.xml (MuJoCo legacy mesh-inertia rule restated). */",
+            f" * Mesh-derived constants of template/mushr.em.xml: {rule}. */",
             f"#define MUSHR_CHASSIS_MASS {mass!r}",
             "#define MUSHR_CHASSIS_COM {%s}" % ", ".join(repr(float(x)) for x in chassis["com"]),
             "#define MUSHR_CHASSIS_INERTIA {%s}" % ", ".join(repr(float(x)) for x in I.reshape(-1)),
