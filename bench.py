@@ -16,6 +16,12 @@ One "step" = one pass of the hot path over the whole fleet:
                  see each other's lidar cylinders and are ranked per world; car-car contacts are NOT generated
 Cars are sharded over the N ranks with no collective on the step path (weak scaling: the per-GPU
 fleet is fixed); only the final timing / stats are gathered.
+
+CPU arms (`--impl reference`, and the `cpu_baseline` key of the GPU line): at run time the script PROBES for a real
+MuJoCo (`import mujoco`, also with baseline/_ref on sys.path).  If it imports, the arm is the reference's own loop
+(custom.py:1337-1426: driver on last step's sensordata, ctrl write, mj_step) on the world this repo's emitter writes
+(ft_grandprix_b200/mjcf.py), single thread per model as the reference steps, kind "reference".  Otherwise it is the C
+restatement under oracle/ (kind "port").  The CPU arms never import the product package.
 """
 import argparse
 import json
@@ -106,19 +112,82 @@ def workload_name(wl, cars):
             "step": f"vehicle step only, {cars} cars/GPU on track.png"}[wl]
 
 
-# ----------------------------------------------------------------------------- CPU arms (oracle port)
+# ----------------------------------------------------------------------------- CPU arms
+def bundled_track(name="track"):
+    """(wall mask, SVG path data) of a bundled track, read straight from the data files (no product import)."""
+    z = np.load(os.path.join(ROOT, "ft_grandprix_b200", "assets", "tracks.npz"))
+    key = name.replace("-", "_")
+    shape = tuple(int(v) for v in z[key + "__shape"])
+    wall = np.unpackbits(z[key + "__bits"])[: shape[0] * shape[1]].reshape(shape)
+    d = json.load(open(os.path.join(ROOT, "ft_grandprix_b200", "assets", "paths.json")))[name]
+    return wall, d
+
+
+def probe_mujoco():
+    """The real reference engine, if this box has it (it does not in the build image: no wheel, no network)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.append(ref)
+    try:
+        import mujoco
+        return mujoco
+    except Exception:
+        return None
+
+
+def mujoco_units_per_s(mj, wl, ncars_model, ticks, seed=1):
+    """The reference's own loop on real MuJoCo, headless (no DearPyGui, no renderer, no physics_fps sleep): ONE model
+    with ncars_model cars, single thread, exactly as custom.py:1337-1426 steps it.  The world comes from this repo's
+    emitter, loaded by file path so that the product library is not touched."""
+    import importlib.util
+    import tempfile
+    from oracle import pyoracle
+    spec = importlib.util.spec_from_file_location("ftgp_mjcf", os.path.join(ROOT, "ft_grandprix_b200", "mjcf.py"))
+    mjcf = importlib.util.module_from_spec(spec); spec.loader.exec_module(mjcf)
+    wall, d_attr = bundled_track("track")
+    ot = pyoracle.Track(wall)
+    path = ot.centreline(d_attr)
+    cars = [{"driver": "ft_grandprix.nidc", "name": f"car {i}", "primary": "red", "secondary": "pink", "icon": "white.png"}
+            for i in range(ncars_model)]
+    with tempfile.TemporaryDirectory() as tmp:
+        meta = mjcf.write_chunks(wall, os.path.join(tmp, "chunks"), name="track", scale=2.0)
+        mjcf.produce_mjcf(cars, meta, tmp, rangefinders=90)
+        m = mj.MjModel.from_xml_path(os.path.join(tmp, "car.xml"))
+    dat = mj.MjData(m)
+    mj.mj_resetData(m, dat)
+    sens = [np.array([mj.mj_name2id(m, mj.mjtObj.mjOBJ_SENSOR, f"rangefinder #{i}.#{j}") for j in range(90)]) for i in range(ncars_model)]
+    qadr = [int(m.jnt_qposadr[mj.mj_name2id(m, mj.mjtObj.mjOBJ_JOINT, f"car #{i}")]) for i in range(ncars_model)]
+    turn = [mj.mj_name2id(m, mj.mjtObj.mjOBJ_ACTUATOR, f"turn #{i}") for i in range(ncars_model)]
+    fwd = [mj.mj_name2id(m, mj.mjtObj.mjOBJ_ACTUATOR, f"forward #{i}") for i in range(ncars_model)]
+    for i in range(ncars_model):                                   # position_vehicles (custom.py:1232-1245)
+        k = (i % 40 + 5) * 2
+        dlt = path[k + 1] - path[k]
+        yaw = float(np.arctan2(dlt[1], dlt[0]))
+        dat.qpos[qadr[i]:qadr[i] + 2] = path[k]
+        dat.qpos[qadr[i] + 3:qadr[i] + 7] = (np.cos(yaw / 2), 0, 0, np.sin(yaw / 2))
+    laps = [pyoracle.Lap(offset=(i % 40 + 5) * 2) for i in range(ncars_model)]
+    t0 = time.perf_counter()
+    for k in range(ticks):
+        if wl == "tick":
+            for i in range(ncars_model):
+                laps[i].update(path, np.array(dat.qpos[qadr[i]:qadr[i] + 2]), k, 10, 0)
+                r = pyoracle.driver(0, np.array(dat.sensordata[sens[i]]))
+                if r is not None:
+                    dat.ctrl[fwd[i]] = r[0]; dat.ctrl[turn[i]] = r[1]
+        mj.mj_step(m, dat)                                          # (rangefinders are evaluated inside, like the reference)
+    dt = time.perf_counter() - t0
+    return ncars_model * ticks * (90 if wl == "lidar" else 1) / dt, dt
+
+
 def cpu_units_per_s(wl, sample_cars, ticks, threads, seed=1):
     """Times the oracle (oracle/*.c, a C restatement: kind 'port') on a bounded sample of the workload."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import pyoracle
-    import ft_grandprix_b200 as ft
     pyoracle.build()
-    t = ft.Track.bundled("track")
-    z = np.load(os.path.join(ROOT, "ft_grandprix_b200", "assets", "tracks.npz"))
-    shape = tuple(int(v) for v in z["track__shape"])
-    wall = np.unpackbits(z["track__bits"])[: shape[0] * shape[1]].reshape(shape)
+    wall, d_attr = bundled_track("track")
     ot = pyoracle.Track(wall)
-    xy, yaw, poses = make_poses(t.path, sample_cars, seed, level=(wl != "lidar"))
+    tpath = ot.centreline(d_attr)
+    xy, yaw, poses = make_poses(tpath, sample_cars, seed, level=(wl != "lidar"))
     chunks = np.array_split(np.arange(sample_cars), threads)
     if wl == "lidar":
         def work(ix):
@@ -133,23 +202,28 @@ def cpu_units_per_s(wl, sample_cars, ticks, threads, seed=1):
     qpos = np.stack([s[0] for s in state]); qvel = np.stack([s[1] for s in state]); warm = np.stack([s[2] for s in state])
     ctrl = np.zeros((sample_cars, 2)); ranges = np.zeros((sample_cars, 90))
     laps = [pyoracle.Lap(offset=10) for _ in range(sample_cars)]
-
-    def work(ix):
+    # the sample is driven into the running regime first (untimed), like the GPU arm's --settle
+    def work(ix, nt):
         lo, hi = int(ix[0]), int(ix[-1]) + 1
-        for k in range(ticks):
+        for k in range(nt):
             if wl == "tick":
                 for i in range(lo, hi):
-                    laps[i].update(t.path, qpos[i, :2], k, 10, 0)
+                    laps[i].update(tpath, qpos[i, :2], k, 10, 0)
                     r = pyoracle.driver(0, ranges[i])
                     if r is not None:
                         ctrl[i] = r
                 ranges[lo:hi] = ot.scan(qpos[lo:hi, :7], threads=1)
             model.step_n(ot, qpos[lo:hi], qvel[lo:hi], warm[lo:hi], ctrl[lo:hi], nthreads=1)
-    t0 = time.perf_counter()
+    live = [c for c in chunks if len(c)]
     with ThreadPoolExecutor(threads) as ex:
-        list(ex.map(work, [c for c in chunks if len(c)]))
-    dt = time.perf_counter() - t0
+        list(ex.map(lambda c: work(c, CPU_SETTLE_TICKS), live))
+        t0 = time.perf_counter()
+        list(ex.map(lambda c: work(c, ticks), live))
+        dt = time.perf_counter() - t0
     return sample_cars * ticks / dt, dt
+
+
+CPU_SETTLE_TICKS = 50
 
 
 def run_reference(args):
@@ -158,26 +232,44 @@ def run_reference(args):
         return
     wl = args.workload if args.workload in ("lidar", "step") else "tick"      # episode / race: the CPU arm is the full tick
     threads = os.cpu_count() or 1
-    sample_cars = {"lidar": 64 * threads, "tick": 16 * threads, "step": 16 * threads}[wl]
+    mj = probe_mujoco()
+    bound = {"lidar": 64 * threads, "tick": 16 * threads, "step": 16 * threads}[wl]
+    sample_cars = max(1, min(args.cars, bound))                    # a bounded sample of the arm's --cars
     ticks = 1 if wl == "lidar" else 10
-    for _ in range(args.warmup):
-        cpu_units_per_s(wl, max(threads, sample_cars // 8), 1 if wl == "lidar" else 2, threads)
     vals, dts = [], []
-    for _ in range(args.steps):
-        v, dt = cpu_units_per_s(wl, sample_cars, ticks, threads)
-        vals.append(v); dts.append(dt)
+    if mj is not None and wl != "lidar":
+        # the real thing: one MuJoCo model, single thread, 3 cars (template/cars/cars.json's size) per model
+        ncm, ticks = 3, 400
+        for _ in range(args.warmup):
+            mujoco_units_per_s(mj, wl, ncm, 50)
+        for _ in range(args.steps):
+            v, dt = mujoco_units_per_s(mj, wl, ncm, ticks)
+            vals.append(v); dts.append(dt)
+        kind, cores = "reference", 1
+        sample = f"MuJoCo {mj.__version__}, one model of {ncm} cars x {ticks} ticks on track.png, headless custom.py:1337-1426 loop, 1 thread"
+        note = "reference = the reference's own MuJoCo loop (single process, single thread, as the reference steps)"
+    else:
+        for _ in range(args.warmup):
+            cpu_units_per_s(wl, max(threads, sample_cars // 8), 1 if wl == "lidar" else 2, threads)
+        for _ in range(args.steps):
+            v, dt = cpu_units_per_s(wl, sample_cars, ticks, threads)
+            vals.append(v); dts.append(dt)
+        kind, cores = "port", threads
+        sample = (f"{sample_cars} of {args.cars} cars x {ticks} tick(s) per step on track.png after {CPU_SETTLE_TICKS} settle ticks, "
+                  f"C oracle (oracle/*.c), {threads} threads")
+        note = ("reference = MuJoCo-on-CPU loop; `import mujoco` failed on this box (probed, also baseline/_ref), so the arm "
+                "times the C restatement of that loop (oracle/), not MuJoCo itself")
     value = float(np.mean(vals))
     metric, unit = ("lidar rays/s", "rays/s") if wl == "lidar" else ("car-steps/s", "car-steps/s")
-    sample = f"{sample_cars} cars x {ticks} tick(s) per step on track.png, C oracle (oracle/*.c), {threads} threads"
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(dts) * 1e3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(wl, args.cars), "sample": sample},
-            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": sample,
+                             "host_cores_available": threads},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0,
-            "note": "reference = MuJoCo-on-CPU loop; mujoco is not installable here, so the arm times the C "
-                    "restatement of that loop (oracle/), not MuJoCo itself"}
+            "gpu_launches": 0, "mujoco_probe": ("found " + mj.__version__) if mj is not None else "import mujoco failed",
+            "note": note}
     if wl != "lidar":
         line["rays_per_s"] = value * 90 if wl == "tick" else 0.0
     print(json.dumps(line), flush=True)
@@ -343,10 +435,23 @@ def run_gpu(args):
     dom_ms = lidar_ms if dom_is_lidar else step_ms
     per_unit = (BYTES["lidar"] if dom_is_lidar else BYTES["step"])
     achieved = cars * per_unit / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, prof = None, {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(dom)
+        prof = json.load(open(tp))
+        if cars == int(prof.get("cars", 65536)):            # the ncu capture is of ONE fleet size; no figure for others
+            traffic = prof.get(dom)
+    # FP64 pipe: the step is bound by FP64 issue + latency, not by HBM (SURVEY 8d asks for flop/s beside the HBM line).
+    # flop per launch = 2 x DFMA + DADD + DMUL thread-instructions of one step at this fleet size, from the committed
+    # ncu capture; peak = 148 SMs x 64 FP64 FMA/clk x 2 x SM clock (the public 37 TFLOP/s HGX B200 figure at 1.965 GHz)
+    fp64 = None
+    if step_ms is not None and cars == int(prof.get("cars", 65536)) and prof.get("step_fp64_flop"):
+        clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        peak_tf = 148 * 64 * 2 * clk / 1e12
+        ach_tf = prof["step_fp64_flop"] / (step_ms * 1e-3) / 1e12
+        fp64 = {"flop_per_step_launch": prof["step_fp64_flop"], "flop_per_car_step": prof["step_fp64_flop"] / cars,
+                "achieved_tflops": ach_tf, "peak_tflops": peak_tf, "frac": ach_tf / peak_tf,
+                "pipe_busy_pct_ncu": prof.get("step_fp64_pipe_pct"), "source": "profiles/traffic.json (ncu sass op counts)"}
     kernels = {}
     if lidar_ms is not None:
         kernels["lidar_kernel"] = {"ms": float(lidar_ms), "rays_per_s": cars * 90 / (lidar_ms * 1e-3), "ns_per_ray": lidar_ms * 1e6 / (cars * 90),
@@ -371,18 +476,25 @@ def run_gpu(args):
                          "note": "latency/issue-bound path: algorithmic HBM traffic is far below peak by construction (SURVEY §8 d)"},
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "how": "public API with pinned host buffers, wall clock around H2D + kernels + D2H; the host waits for every tick's ranges and lap state"},
-            "gpu_launches": launches, "clocks": clocks, "kernels": kernels}
+            "gpu_launches": launches, "clocks": clocks, "kernels": kernels, "fp64": fp64}
+    line["config"]["settle_ticks"] = settle
     if wl != "lidar":
         line["rays_per_s"] = value * 90 if wl == "tick" else 0.0
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            threads = 1
-            sc = {"lidar": 4096, "tick": 128, "step": 128}[wl]          # ~10-20 s of single-thread CPU work
-            nt = 1 if wl == "lidar" else 60
-            v, dt = cpu_units_per_s(wl, sc, nt, threads)
-            line["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
-                                    "host_cores_available": os.cpu_count(),
-                                    "sample": f"{sc} cars x {nt} tick(s), C oracle single thread ({dt:.1f} s)"}
+            mj = probe_mujoco()
+            if mj is not None and wl != "lidar":
+                v, dt = mujoco_units_per_s(mj, wl, 3, 1500)
+                line["cpu_baseline"] = {"value": v, "unit": unit, "cores": 1, "kind": "reference", "host_cores_available": os.cpu_count(),
+                                        "sample": f"MuJoCo {mj.__version__}: one model of 3 cars x 1500 ticks, headless reference loop ({dt:.1f} s)"}
+            else:
+                threads = 1
+                sc = {"lidar": 4096, "tick": 128, "step": 128}[wl]          # ~10-20 s of single-thread CPU work
+                nt = 1 if wl == "lidar" else 60
+                v, dt = cpu_units_per_s(wl, sc, nt, threads)
+                line["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
+                                        "host_cores_available": os.cpu_count(), "mujoco_probe": "import mujoco failed",
+                                        "sample": f"{sc} cars x {nt} tick(s) after {CPU_SETTLE_TICKS} settle ticks, C oracle single thread ({dt:.1f} s)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -424,7 +536,8 @@ def run_episode(args, kind="episode"):
     else:
         cpw, tracks = 1, [ft.Track.bundled("circle"), ft.Track.bundled("small-circle")]
         nworlds = args.cars
-        race = ShardedRace(nworlds, 1, 2, lambda n, tid, first: ft.Fleet(Geometry(tracks, device=local), n, device=local, track_id=tid, driver="nidc"))
+        race = ShardedRace(nworlds, 1, 2, lambda n, tid, first: ft.Fleet(Geometry(tracks, device=local), n, device=local, track_id=tid, driver="nidc",
+                                                                         lap_target=args.lap_target))
         fleet = race.fleet
         n = fleet.ncars
         xy = np.zeros((n, 2)); yaw = np.zeros(n)
@@ -437,11 +550,17 @@ def run_episode(args, kind="episode"):
     ncars_total = nworlds * cpw
     stream = fleet.stream
     sampler = ClockSampler(local); sampler.start()
-    with torch.cuda.stream(stream):
-        for _ in range(args.settle):
-            fleet.tick(1)
-        for _ in range(args.warmup):
-            fleet.tick(1)
+    full = bool(args.full_episode) and kind == "episode"
+    if not full:
+        with torch.cuda.stream(stream):
+            for _ in range(args.settle):
+                fleet.tick(1)
+            for _ in range(args.warmup):
+                fleet.tick(1)
+    else:                                                    # an episode starts at the reset: warm the code paths on a scratch copy
+        sd = fleet.state_dict()
+        fleet.tick(args.warmup); fleet.sync()
+        fleet.load_state_dict(sd); torch.cuda.synchronize()
     stream.synchronize()
 
     def barrier():
@@ -453,15 +572,27 @@ def run_episode(args, kind="episode"):
     launches0 = lib.ftgp_launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ticks_done = 0
     with torch.cuda.stream(stream):
         e0.record(stream)
-        for _ in range(args.steps):
-            fleet.tick(1)
+        if not full:
+            for _ in range(args.steps):
+                fleet.tick(1)
+            ticks_done = args.steps
+        else:
+            # "until all finished lap_target laps or 25 000 ticks (100 s)".  Each rank runs its own shard
+            # to the end (no collective on the step path); the finished count is read back every 250 ticks.
+            FIN = ft.fleet.LAP["finished"]
+            while ticks_done < 25000:
+                fleet.tick(250); ticks_done += 250
+                if int((fleet.lap[:, FIN] == 0).sum().item()) == 0:
+                    break
         e1.record(stream)
     barrier()
     clocks = sampler.stop()
     launches = lib.ftgp_launch_count() - launches0
     dev_ms = e0.elapsed_time(e1)
+    car_steps = float(n) * ticks_done
     t0 = time.perf_counter()
     stats = race.episode_stats()                     # the only collective of the episode
     torch.cuda.synchronize()
@@ -477,16 +608,18 @@ def run_episode(args, kind="episode"):
         fleet.sync_readback()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    tt = torch.tensor([dev_ms, e2e_ms, float(launches), gather_ms], dtype=torch.float64, device=fleet.device)
+    tt = torch.tensor([dev_ms, e2e_ms, float(launches), gather_ms, float(ticks_done)], dtype=torch.float64, device=fleet.device)
+    cs = torch.tensor([car_steps], dtype=torch.float64, device=fleet.device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, launches, gather_ms = float(tt[0]), float(tt[1]), int(tt[2]), float(tt[3])
-    value = ncars_total * args.steps / (dev_ms * 1e-3)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, launches, gather_ms, ticks_max = float(tt[0]), float(tt[1]), int(tt[2]), float(tt[3]), int(tt[4])
+    value = float(cs[0]) / (dev_ms * 1e-3)
     peak, peak_src = peaks()
     achieved = value * BYTES["tick"] / 1e9
     laps = stats[:, STAT_FIELDS.index("laps")]
-    line = {"metric": "car-steps/s", "value": value, "unit": "car-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+    line = {"metric": "car-steps/s", "value": value, "unit": "car-steps/s", "n_gpus": world, "steps": ticks_max, "warmup": args.warmup,
+            "ms_per_step": dev_ms / ticks_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": (f"sharded episode, {nworlds} cars in total on circle/small-circle alternating by world index, "
                                     f"full tick, stats gathered once (BASELINE config 4)") if kind == "episode" else
@@ -505,7 +638,8 @@ def run_episode(args, kind="episode"):
                     "how": "Fleet.tick_readback: ranges and lap state to pinned host memory every tick (host waits for them), wall clock"},
             "gpu_launches": launches, "clocks": clocks, "rays_per_s": value * 90,
             "episode": {"gather_ms": gather_ms, "stats_rows": int(stats.shape[0]), "stats_bytes": int(stats.numel() * 4),
-                        "laps_max": int(laps.max()),
+                        "laps_max": int(laps.max()), "ticks": ticks_max, "to_completion": full, "lap_target": args.lap_target,
+                        "finished_cars": int(stats[:, STAT_FIELDS.index("finished")].sum()) if "finished" in STAT_FIELDS else None,
                         "cars_moved_5cm_this_rank": int(((fleet.qpos[:, :2] - xy0).norm(dim=1) > 0.05).sum())}}
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -521,7 +655,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("FTGP_WORKLOAD", "tick"), choices=["tick", "lidar", "step", "episode", "race"])
     ap.add_argument("--cars", type=int, default=None)
-    ap.add_argument("--settle", type=int, default=200, help="untimed ticks before timing (tick/step workloads)")
+    ap.add_argument("--settle", type=int, default=1000, help="untimed ticks before timing (SURVEY 8d config 3: 1 000 warm ticks)")
+    ap.add_argument("--full-episode", action="store_true",
+                    help="episode workload: run until every car of the rank has finished --lap-target laps or 25 000 ticks (SURVEY 8d config 4)")
+    ap.add_argument("--lap-target", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused-check", action="store_true", help="assert that ftgp_tick == the four separate calls, bit for bit")
     args = ap.parse_args()
