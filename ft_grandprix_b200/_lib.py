@@ -50,6 +50,8 @@ SIGNATURES = {
     "ftgp_drivers": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp]),
     "ftgp_lap_update": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i, C.c_int32, C.c_int32, _vp]),
     "ftgp_tick": (_i, [C.POINTER(TickArgs), _i, _vp]),
+    "ftgp_release_graphs": (_i, []),
+    "ftgp_tick_use_graphs": (_i, [_i]),
 }
 
 _lib = None

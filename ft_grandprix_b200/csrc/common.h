@@ -12,6 +12,7 @@ void set_error(const char* fmt, ...);
 bool cuda_ok(cudaError_t e, const char* what);
 void count_launch(int n = 1);
 
+
 #define FTGP_CUDA(call)                                        \
     do {                                                       \
         if (!ftgp::cuda_ok((call), #call)) return FTGP_ERR_CUDA; \
@@ -62,6 +63,8 @@ struct ftgp_track {
     std::vector<uint8_t> dims;        // 2*nchunks (ncol, nrow)
     std::vector<uint32_t> masks;      // nchunks * 13 words
 };
+
+namespace ftgp { void forget_geom(const struct ::ftgp_geom* geom); }   // drops captured tick graphs that reference the geometry
 
 struct ftgp_geom {
     int device = 0;

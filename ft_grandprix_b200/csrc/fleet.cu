@@ -49,9 +49,11 @@ __device__ __forceinline__ double pick(double e0, double e1, double e2, int idx)
 
 __global__ void __launch_bounds__(256)
 drivers_kernel(const float* __restrict__ ranges, const int32_t* __restrict__ kind, int default_kind,
-               const int32_t* __restrict__ lap, double* __restrict__ ctrl, int64_t ncars) {
+               const int32_t* __restrict__ lap, double* __restrict__ ctrl, int64_t ncars, int32_t* __restrict__ steps_dev) {
     const int lane = threadIdx.x & 31;
     const int64_t car = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // graph-replayed tick: the lap kernel (earlier on this stream) has read the tick counter; nothing else reads it this tick
+    if (steps_dev && blockIdx.x == 0 && threadIdx.x == 0) *steps_dev += 1;
     if (car >= ncars) return;
     int k = kind ? kind[car] : default_kind;
     if (lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED]) k = FTGP_DRIVER_LOBOTOMY;   // shadow(): custom.py:1437
@@ -141,7 +143,8 @@ __global__ void lap_kernel(const uint32_t* __restrict__ blob, const double* __re
                            const int32_t* __restrict__ track_id, int32_t* __restrict__ lap,
                            int32_t* __restrict__ times, int32_t* __restrict__ winners,
                            const int32_t* __restrict__ status, int64_t ncars, int cpw, int32_t steps,
-                           int32_t lap_target) {
+                           int32_t lap_target, const int32_t* __restrict__ steps_dev) {
+    if (steps_dev) steps = *steps_dev;              // graph-replayed tick: self.steps lives on the device
     const int64_t world = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t first = world * cpw;
     if (first >= ncars) return;
@@ -194,10 +197,10 @@ __global__ void lap_kernel(const uint32_t* __restrict__ blob, const double* __re
 }
 
 int launch_drivers(const float* ranges, const int32_t* kind, int default_kind, const int32_t* lap, double* ctrl,
-                   int64_t ncars, cudaStream_t stream) {
+                   int64_t ncars, cudaStream_t stream, int32_t* steps_dev) {
     const int threads = 256;
     int64_t blocks = (ncars * 32 + threads - 1) / threads;
-    drivers_kernel<<<(unsigned)blocks, threads, 0, stream>>>(ranges, kind, default_kind, lap, ctrl, ncars);
+    drivers_kernel<<<(unsigned)blocks, threads, 0, stream>>>(ranges, kind, default_kind, lap, ctrl, ncars, steps_dev);
     count_launch();
     FTGP_CUDA(cudaGetLastError());
     return FTGP_OK;
@@ -205,11 +208,11 @@ int launch_drivers(const float* ranges, const int32_t* kind, int default_kind, c
 
 int launch_lap(const ftgp_geom* g, const double* qpos, int64_t stride, const int32_t* track_id, int32_t* lap,
                int32_t* times, int32_t* winners, const int32_t* status, int64_t ncars, int cpw, int32_t steps,
-               int32_t lap_target, cudaStream_t stream) {
+               int32_t lap_target, cudaStream_t stream, const int32_t* steps_dev) {
     int64_t nworlds = (ncars + cpw - 1) / cpw;
     const int threads = 128;
     lap_kernel<<<(unsigned)((nworlds + threads - 1) / threads), threads, 0, stream>>>(
-        g->d_blob, qpos, stride, track_id, lap, times, winners, status, ncars, cpw, steps, lap_target);
+        g->d_blob, qpos, stride, track_id, lap, times, winners, status, ncars, cpw, steps, lap_target, steps_dev);
     count_launch();
     FTGP_CUDA(cudaGetLastError());
     return FTGP_OK;
@@ -232,7 +235,7 @@ extern "C" int ftgp_drivers(const float* ranges, const int32_t* kind, int defaul
                             double* ctrl, int64_t ncars, void* stream) {
     if (!ranges || !ctrl || ncars < 0 || default_kind < 0 || default_kind > 2) { set_error("ftgp_drivers: bad argument"); return FTGP_ERR_ARG; }
     if (ncars == 0) return FTGP_OK;
-    return launch_drivers(ranges, kind, default_kind, lap, ctrl, ncars, (cudaStream_t)stream);
+    return launch_drivers(ranges, kind, default_kind, lap, ctrl, ncars, (cudaStream_t)stream, nullptr);
 }
 
 extern "C" int ftgp_lap_update(const ftgp_geom* g, const double* qpos, int64_t qpos_stride,
@@ -245,5 +248,5 @@ extern "C" int ftgp_lap_update(const ftgp_geom* g, const double* qpos, int64_t q
     if (ncars == 0) return FTGP_OK;
     FTGP_CUDA(cudaSetDevice(g->device));
     return launch_lap(g, qpos, qpos_stride, track_id, lap, times, winners, status, ncars, cars_per_world, steps,
-                      lap_target, (cudaStream_t)stream);
+                      lap_target, (cudaStream_t)stream, nullptr);
 }

@@ -11,6 +11,7 @@
 #include "mushr_consts.h"
 #include "mushr_step_quad.cuh"
 #include <cstdlib>
+#include <atomic>
 #include <mutex>
 #include <utility>
 
@@ -199,6 +200,7 @@ struct StepScratch {
     int dev = -1; cudaStream_t stream = nullptr; uint64_t used = 0;
     int32_t* perm = nullptr; int32_t* counters = nullptr; int64_t cap = 0;                                          // regrouping
     double* recs = nullptr; int32_t* lists = nullptr; int32_t* stage_counts = nullptr; int64_t stage_cap = 0;      // staged solve
+    uint64_t generation = 0;     // bumped whenever a buffer is (re)allocated or freed: captured graphs hold these pointers
     void release() {
         if (dev < 0) return;
         int cur = 0;
@@ -209,7 +211,9 @@ struct StepScratch {
         if (lists) cudaFree(lists);
         if (stage_counts) cudaFree(stage_counts);
         cudaSetDevice(cur);
+        const uint64_t gen = generation + 1;
         *this = StepScratch();
+        generation = gen;
     }
 };
 static StepScratch g_scratch[64];
@@ -268,7 +272,7 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
             o->perm = nullptr; o->cap = 0;
             if (!o->counters) FTGP_CUDA(cudaMalloc(&o->counters, 2 * NBIN * sizeof(int32_t)));
             FTGP_CUDA(cudaMalloc(&o->perm, ncars * sizeof(int32_t)));
-            o->cap = ncars;
+            o->cap = ncars; o->generation++;
         }
         FTGP_CUDA(cudaMemsetAsync(o->counters, 0, 2 * NBIN * sizeof(int32_t), stream));
         const unsigned nb = (unsigned)((ncars + 255) / 256);
@@ -285,7 +289,7 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
         if (o->stage_cap < ncars) {
             if (o->recs) cudaFree(o->recs);
             if (o->lists) cudaFree(o->lists);
-            o->recs = nullptr; o->lists = nullptr; o->stage_cap = 0;
+            o->recs = nullptr; o->lists = nullptr; o->stage_cap = 0; o->generation++;
             if (!o->stage_counts) FTGP_CUDA(cudaMalloc(&o->stage_counts, 4 * sizeof(int32_t)));
             if (cudaMalloc(&o->recs, (size_t)ncars * QREC_DOUBLES * sizeof(double)) == cudaSuccess &&
                 cudaMalloc(&o->lists, (size_t)ncars * 2 * sizeof(int32_t)) == cudaSuccess) o->stage_cap = ncars;
@@ -317,10 +321,111 @@ int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const i
                  const uint8_t* visible, const int32_t* lap, int64_t ncars, int cpw, float* ranges, float* min_range,
                  cudaStream_t stream);
 int launch_drivers(const float* ranges, const int32_t* kind, int default_kind, const int32_t* lap, double* ctrl,
-                   int64_t ncars, cudaStream_t stream);
+                   int64_t ncars, cudaStream_t stream, int32_t* steps_dev);
 int launch_lap(const ftgp_geom* g, const double* qpos, int64_t stride, const int32_t* track_id, int32_t* lap,
                int32_t* times, int32_t* winners, const int32_t* status, int64_t ncars, int cpw, int32_t steps,
-               int32_t lap_target, cudaStream_t stream);
+               int32_t lap_target, cudaStream_t stream, const int32_t* steps_dev);
+
+// ---- one tick = custom.py:1337-1426 for the whole fleet, in the reference's order
+static int issue_tick(const ftgp_tick_args* a, int32_t steps, int32_t* steps_dev, cudaStream_t s) {
+    int rc;
+    // custom.py:1340-1372 progress + lap logic from the current pose
+    if ((rc = launch_lap(a->geom, a->qpos, FTGP_NQ, a->track_id, a->lap, a->times, a->winners, a->status, a->ncars,
+                         a->cars_per_world, steps, a->lap_target, s, steps_dev))) return rc;
+    // custom.py:1395-1423 driver on the ranges of the previous mj_step, control write
+    if ((rc = launch_drivers(a->ranges, a->driver_kind, a->default_driver, a->lap, a->ctrl, a->ncars, s, steps_dev))) return rc;
+    // custom.py:1425 mj_step: rangefinders are evaluated from the pre-step pose, then the state advances
+    if ((rc = launch_lidar(a->geom, a->qpos, FTGP_NQ, a->track_id, nullptr, a->lap, a->ncars, a->cars_per_world, a->ranges,
+                           nullptr, s))) return rc;
+    return launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, 1, a->status, s);
+}
+
+// ---- small fleets: the tick is launch-bound (4-9 launches of a few microseconds of work each), so it is captured once
+// into a CUDA graph per (arguments, stream) and replayed.  The only per-tick value, self.steps, lives in a device counter
+// that the lap kernel reads and the driver kernel bumps.  The first tick of a new argument set runs eagerly (it may
+// allocate scratch, which a capture must not); graphs are rebuilt when the step scratch they point into is re-allocated.
+constexpr int64_t GRAPH_MAX_CARS = 16384;
+static std::atomic<int> g_use_graphs{1};
+struct TickGraph {
+    ftgp_tick_args key{}; cudaStream_t stream = nullptr; int dev = -1;
+    cudaGraphExec_t exec = nullptr; int32_t* steps_dev = nullptr; int32_t shadow = INT32_MIN;
+    uint64_t scratch_gen = 0; int launches_per_tick = 0; bool seen = false; uint64_t used = 0;
+};
+static TickGraph g_graphs[32];
+static std::mutex g_graph_mutex;
+static uint64_t g_graph_clock = 0;
+__global__ void set_i32_kernel(int32_t* p, int32_t v) { *p = v; }
+
+static uint64_t scratch_generation(int dev, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_step_mutex);
+    for (auto& o : g_scratch) if (o.dev == dev && o.stream == stream) return o.generation;
+    return 0;
+}
+static bool same_key(const ftgp_tick_args& x, const ftgp_tick_args& y) {
+    return x.geom == y.geom && x.qpos == y.qpos && x.qvel == y.qvel && x.warm == y.warm && x.ctrl == y.ctrl && x.ranges == y.ranges &&
+           x.track_id == y.track_id && x.driver_kind == y.driver_kind && x.lap == y.lap && x.times == y.times &&
+           x.winners == y.winners && x.status == y.status && x.ncars == y.ncars && x.cars_per_world == y.cars_per_world &&
+           x.default_driver == y.default_driver && x.lap_target == y.lap_target;
+}
+static void drop_graph(TickGraph& g) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.steps_dev) cudaFree(g.steps_dev);
+    g = TickGraph();
+}
+
+// returns FTGP_OK and sets *done = number of ticks issued through the graph (0: caller runs them eagerly)
+static int graph_ticks(const ftgp_tick_args* a, int nticks, cudaStream_t s, int* done) {
+    *done = 0;
+    int dev = 0;
+    FTGP_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_graph_mutex);
+    TickGraph* e = nullptr; TickGraph* lru = &g_graphs[0];
+    for (auto& g : g_graphs) {
+        if (g.seen && g.dev == dev && g.stream == s && same_key(g.key, *a)) { e = &g; break; }
+        if (g.used < lru->used) lru = &g;
+    }
+    int32_t steps = a->steps;
+    if (!e) {                                   // first tick with these arguments: register, run ONE tick eagerly
+        drop_graph(*lru);
+        lru->key = *a; lru->stream = s; lru->dev = dev; lru->seen = true;
+        e = lru;
+        const int rc = issue_tick(a, steps, nullptr, s);
+        if (rc) return rc;
+        steps++; nticks--; *done = 1;
+        if (nticks == 0) { e->used = ++g_graph_clock; return FTGP_OK; }
+    }
+    e->used = ++g_graph_clock;
+    const uint64_t gen = scratch_generation(dev, s);
+    if (e->exec && e->scratch_gen != gen) { cudaGraphExecDestroy(e->exec); e->exec = nullptr; }
+    if (!e->exec) {
+        if (!e->steps_dev) FTGP_CUDA(cudaMalloc(&e->steps_dev, sizeof(int32_t)));
+        const int64_t l0 = ftgp_launch_count();
+        cudaGraph_t graph = nullptr;
+        FTGP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        const int rc = issue_tick(a, 0, e->steps_dev, s);
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (rc || ce != cudaSuccess || !graph) {                 // capture refused (e.g. scratch had to grow): stay eager
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            count_launch((int)(l0 - ftgp_launch_count()));
+            return FTGP_OK;
+        }
+        e->launches_per_tick = (int)(ftgp_launch_count() - l0);
+        count_launch(-e->launches_per_tick);                     // nothing ran during the capture
+        const cudaError_t ie = cudaGraphInstantiate(&e->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { e->exec = nullptr; cudaGetLastError(); return FTGP_OK; }
+        e->scratch_gen = scratch_generation(dev, s);
+        if (e->scratch_gen != gen) { cudaGraphExecDestroy(e->exec); e->exec = nullptr; return FTGP_OK; }
+        e->shadow = INT32_MIN;
+    }
+    if (e->shadow != steps) { set_i32_kernel<<<1, 1, 0, s>>>(e->steps_dev, steps); count_launch(); }
+    for (int t = 0; t < nticks; t++) FTGP_CUDA(cudaGraphLaunch(e->exec, s));
+    count_launch(nticks * e->launches_per_tick);
+    e->shadow = steps + nticks;
+    *done += nticks;
+    return FTGP_OK;
+}
 
 }  // namespace ftgp
 using namespace ftgp;
@@ -345,20 +450,29 @@ extern "C" int ftgp_release_scratch(void* stream) {
 extern "C" int ftgp_tick(const ftgp_tick_args* a, int nticks, void* stream) {
     if (!a || !a->geom || !a->qpos || !a->qvel || !a->warm || !a->ctrl || !a->ranges || !a->lap || !a->times ||
         a->ncars < 0 || a->cars_per_world < 1 || nticks < 0) { set_error("ftgp_tick: bad argument"); return FTGP_ERR_ARG; }
-    if (a->ncars == 0) return FTGP_OK;
+    if (a->ncars == 0 || nticks == 0) return FTGP_OK;
     FTGP_CUDA(cudaSetDevice(a->geom->device));
     cudaStream_t s = (cudaStream_t)stream;
-    for (int t = 0; t < nticks; t++) {
-        int rc;
-        // custom.py:1340-1372 progress + lap logic from the current pose
-        if ((rc = launch_lap(a->geom, a->qpos, FTGP_NQ, a->track_id, a->lap, a->times, a->winners, a->status, a->ncars,
-                             a->cars_per_world, a->steps + t, a->lap_target, s))) return rc;
-        // custom.py:1395-1423 driver on the ranges of the previous mj_step, control write
-        if ((rc = launch_drivers(a->ranges, a->driver_kind, a->default_driver, a->lap, a->ctrl, a->ncars, s))) return rc;
-        // custom.py:1425 mj_step: rangefinders are evaluated from the pre-step pose, then the state advances
-        if ((rc = launch_lidar(a->geom, a->qpos, FTGP_NQ, a->track_id, nullptr, a->lap, a->ncars, a->cars_per_world, a->ranges,
-                               nullptr, s))) return rc;
-        if ((rc = launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, 1, a->status, s))) return rc;
+    int t0 = 0, rc;
+    if (a->ncars <= GRAPH_MAX_CARS && s != nullptr && g_use_graphs.load()) {           // (the legacy default stream cannot be captured)
+        if ((rc = graph_ticks(a, nticks, s, &t0))) return rc;
     }
+    for (int t = t0; t < nticks; t++)
+        if ((rc = issue_tick(a, a->steps + t, nullptr, s))) return rc;
     return FTGP_OK;
+}
+
+extern "C" int ftgp_tick_use_graphs(int enable) { return g_use_graphs.exchange(enable ? 1 : 0); }
+
+extern "C" int ftgp_release_graphs(void) {
+    std::lock_guard<std::mutex> lock(g_graph_mutex);
+    for (auto& g : g_graphs) drop_graph(g);
+    return FTGP_OK;
+}
+
+namespace ftgp {
+void forget_geom(const ftgp_geom* geom) {       // ftgp_geom_destroy: captured ticks point into the geometry blob
+    std::lock_guard<std::mutex> lock(g_graph_mutex);
+    for (auto& g : g_graphs) if (g.seen && g.key.geom == geom) drop_graph(g);
+}
 }

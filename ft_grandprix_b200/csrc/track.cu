@@ -291,6 +291,7 @@ extern "C" ftgp_geom* ftgp_geom_create(const ftgp_track* const* tracks, const do
 extern "C" void ftgp_geom_destroy(ftgp_geom* g) {
     if (!g) return;
     cudaSetDevice(g->device);
+    ftgp::forget_geom(g);
     if (g->d_scratch) cudaFree(g->d_scratch);
     if (g->d_blob) cudaFree(g->d_blob);
     if (g->host_stream) cudaStreamDestroy(g->host_stream);

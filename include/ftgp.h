@@ -163,8 +163,15 @@ typedef struct {
  * lap update -> built-in driver on last tick's ranges -> ctrl -> [rangefinders from the
  * pre-step pose, mj_step] ; the same one-tick sensor lag as the reference.
  * cars_per_world > 1: the cars of a world see each other's lidar cylinder and are ranked
- * together, but car-car CONTACTS are not generated yet (they pass through each other). */
+ * together, but car-car CONTACTS are not generated yet (they pass through each other).
+ * Fleets of up to 16 384 cars are launch-bound: from the second call with the same arguments and a non-NULL stream the
+ * tick is replayed from a CUDA graph captured once (same kernels, same order, bit-identical results; self.steps
+ * lives in a device counter).  ftgp_release_graphs() drops the cached graphs. */
 int ftgp_tick(const ftgp_tick_args* a, int nticks, void* stream);
+int ftgp_release_graphs(void);
+/* enable != 0 (default): small fleets replay the captured tick; 0: every tick is issued launch by launch.
+ * Returns the previous setting (for A/B timing in the bench). */
+int ftgp_tick_use_graphs(int enable);
 
 #ifdef __cplusplus
 }

@@ -485,3 +485,32 @@ def test_closed_loop_free_running_divergence_is_reported(ft, oracle, otracks, ca
             print(f"\n[report] closed loop, free running, {n} car(s) on {name}.png, {ticks} ticks, |xyz(GPU) - xyz(oracle)| "
                   "(median, max, fraction > 1 mm): " + "; ".join(f"t={k}: {a:.1e}, {b:.1e}, {c:.2f}" for k, (a, b, c) in marks.items())
                   + f"; lap integers equal for {same:.2%} of cars; within 1 cm at the end: {tog:.2%}")
+
+
+@pytest.mark.parametrize("n", [1, 40, 4096])
+def test_graph_replayed_tick_is_bit_identical_to_the_eager_tick(ft, n):
+    """Small fleets replay the tick from a CUDA graph (ftgp_tick): same kernels, same order -> same bits as the four
+    separate calls, across several ftgp_tick calls, a reset in between and a second fleet on the same stream size."""
+    t = ft.Track.bundled("track")
+    from conftest import random_poses
+    poses = random_poses(t.path, max(n, 2), seed=21, level=True)[:n]
+    xy = poses[:, :2]; yaw = 2 * np.arctan2(poses[:, 6], poses[:, 3])
+    a = ft.Fleet(t, n, lap_target=1); b = ft.Fleet(t, n, lap_target=1)
+    for rnd in range(2):
+        a.reset(xy, yaw); b.reset(xy, yaw)
+        for chunk in (1, 3, 25, 1, 60):
+            a.tick(chunk)                                         # eager first tick, then captured + replayed
+            for _ in range(chunk):
+                b.lap_update(); b.drive(); b.lidar(); b.step(1)
+        a.sync(); b.sync()
+        assert a.steps == b.steps == 90
+        for k in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "times", "status", "winners"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (k, rnd)
+    prev = a.lib.ftgp_tick_use_graphs(0)                           # and with graphs switched off
+    a.reset(xy, yaw); b.reset(xy, yaw)
+    a.tick(30)
+    for _ in range(30):
+        b.lap_update(); b.drive(); b.lidar(); b.step(1)
+    a.sync(); b.sync()
+    a.lib.ftgp_tick_use_graphs(prev)
+    assert torch.equal(a.qpos, b.qpos) and torch.equal(a.lap, b.lap)
