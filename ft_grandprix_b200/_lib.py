@@ -40,6 +40,8 @@ SIGNATURES = {
     "ftgp_centreline": (_i, [C.c_char_p, _i, _i, _i, _i, _i, _d, _vp]),
     "ftgp_geom_create": (_vp, [_vp, _vp, _i, _i]),
     "ftgp_geom_destroy": (None, [_vp]),
+    "ftgp_geom_blob": (_i64, [_vp, _vp, _i, _vp, _i64]),
+    "ftgp_blob_track_view": (_i, [_vp, _i, _vp, _vp]),
     "ftgp_geom_device": (_i, [_vp]),
     "ftgp_geom_bytes": (_i64, [_vp]),
     "ftgp_lidar": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),

@@ -31,6 +31,7 @@
 // oracle on the CPU build box before it runs on a B200.
 #pragma once
 #include "mushr_step.cuh"
+#include "hfield_contact.cuh"
 
 // The solver's pieces are inlined into the kernel on the device: as separate functions (the ABI saves and restores
 // ~100 live registers around every call) the step took 1.93 ms for 65,536 cars, inlined 1.48 ms.
@@ -114,11 +115,18 @@ FT_HDN void quad_const_entry(const ModelConsts& mc, int g, double* t) {      // 
     t[3 * g] = f > 0 ? 1 / R : 0.0; t[3 * g + 1] = f > 0 ? R * f : 0.0; t[3 * g + 2] = f;
 }
 
-// chassis (wall) contacts owned by the lane: rare, kept in the lane's frame and only touched when nch > 0
-constexpr int QMAXCH = 2;            // MAXCON = 8 contacts over four lanes
-struct QChassis { double D[QMAXCH], aref[QMAXCH][4], J[QMAXCH][3][6], dx[QMAXCH][3], ds[QMAXCH][3]; };
-struct QState { double cost, gauss, c0; unsigned mask; int nch; };     // c0 = qacc_smooth' qfrc_smooth / 2
-constexpr int QB_FR = 0, QB_FR6 = 6, QB_LIM = 7, QB_LIM6 = 9, QB_WC = 10, QB_CH = 14;
+// Rare contacts owned by the lane, kept in the lane's frame (local memory) and only touched when present:
+//   * up to QMAXCH contacts of the car body's geoms (chassis hull vertices / lidar cylinder against walls and ground):
+//     MAXBODYCON = 8 over four lanes, Jacobian over the six chassis dofs only;
+//   * the lane's wheel against a wall (ww = 1): Jacobian over the six chassis dofs and chain slots 0-2.
+// All of them: condim 3, mu = 1 (hfield / chassis / cylinder friction 1 > wheel 0.3, plane 0.5).
+constexpr int QMAXCH = 2, MAXBODYCON = 4 * QMAXCH;
+struct QChassis {
+    double D[QMAXCH], aref[QMAXCH][4], J[QMAXCH][3][6], dx[QMAXCH][3], ds[QMAXCH][3];
+    double wD, waref[4], wJ[3][9], wdx[3], wds[3];                      // wheel-wall contact
+};
+struct QState { double cost, gauss, c0; unsigned mask; int nch, ww; };  // c0 = qacc_smooth' qfrc_smooth / 2
+constexpr int QB_FR = 0, QB_FR6 = 6, QB_LIM = 7, QB_LIM6 = 9, QB_WC = 10, QB_CH = 14, QB_WW = 22;
 constexpr double WC_MU = 0.5, CH_MU = 1.0;
 constexpr double REF_B = 2 / (0.95 * 0.02);          // kbi(): B of the default solref with dmax 0.95
 
@@ -155,7 +163,7 @@ FT_HD void wc_dots(const Q& qd, const double* xr, const double* xc, double* d3) 
 
 // ---- cost of this lane's rows at the vector X: forces J^T f into fr (root, lane's share) / fc (chain), zone mask --
 template <class Q>
-FT_QN double rows_eval(const Q& qd, const QChassis& ch, int nch, QVec X, double* fr, double* fc, unsigned& mask_out) {
+FT_QN double rows_eval(const Q& qd, const QChassis& ch, int nch, int ww, QVec X, double* fr, double* fc, unsigned& mask_out) {
     const int w = qd.lane();
     double xr[NR], xc[NC];
     vec_load(qd, X, xr, xc);
@@ -223,6 +231,20 @@ FT_QN double rows_eval(const Q& qd, const QChassis& ch, int nch, QVec X, double*
             for (int col = 0; col < 6; col++) fr[col] += (ch.J[s][0][col] + sg * ch.J[s][ta][col]) * f;
         }
     }
+    if (ww) {                                                            // the lane's wheel against a wall
+        double d3[3];
+        for (int a = 0; a < 3; a++) d3[a] = dot6q(ch.wJ[a], xr) + ch.wJ[a][6] * xc[0] + ch.wJ[a][7] * xc[1] + ch.wJ[a][8] * xc[2];
+        for (int rr = 0; rr < 4; rr++) {
+            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+            const double jar = d3[0] + sg * d3[ta] - ch.waref[rr];
+            if (jar >= 0) continue;
+            cost += 0.5 * ch.wD * jar * jar;
+            mask |= 1u << (QB_WW + rr);
+            const double f = -ch.wD * jar;
+            for (int col = 0; col < 6; col++) fr[col] += (ch.wJ[0][col] + sg * ch.wJ[ta][col]) * f;
+            for (int k = 0; k < 3; k++) fc[k] += (ch.wJ[0][6 + k] + sg * ch.wJ[ta][6 + k]) * f;
+        }
+    }
     mask_out = mask;
     return cost;
 }
@@ -258,7 +280,7 @@ template <class Q>
 FT_QN void quad_evaluate(const Q& qd, const QChassis& ch, QState& st, bool on) {
     double fr[NR], fc[NC], g_r[NR], g_c[NC];
     unsigned mask;
-    double cc = rows_eval(qd, ch, st.nch, VX, fr, fc, mask);
+    double cc = rows_eval(qd, ch, st.nch, st.ww, VX, fr, fc, mask);
     double g = 0;
 #pragma unroll
     for (int l = 0; l < NC; l++) {
@@ -357,6 +379,23 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
                     const double di = D * Jr[i];
 #pragma unroll
                     for (int j = 0; j <= i; j++) Pp[tri(i, j)] += di * Jr[j];
+                }
+            }
+        }
+        if (st.ww) {                                                     // wheel-wall rows: root block, chain block and border
+            for (int rr = 0; rr < 4; rr++) {
+                if (!(mask >> (QB_WW + rr) & 1u)) continue;
+                const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+                double Jr[9];
+                for (int col = 0; col < 9; col++) Jr[col] = ch.wJ[0][col] + sg * ch.wJ[ta][col];
+                for (int i = 0; i < 6; i++) {
+                    const double di = ch.wD * Jr[i];
+                    for (int j = 0; j <= i; j++) Pp[tri(i, j)] += di * Jr[j];
+                }
+                for (int l = 0; l < 3; l++) {
+                    const double dl = ch.wD * Jr[6 + l];
+                    for (int k = 0; k <= l; k++) W[tri(l, k)] += dl * Jr[6 + k];
+                    for (int j = 0; j < 6; j++) B[l][j] += dl * Jr[j];
                 }
             }
         }
@@ -463,6 +502,16 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
 #pragma unroll
             for (int l = 0; l < 3; l++) t[l] -= qd.P(QP_CJ + 3 + l) * u[0] + qd.P(QP_CJ + 9 + l) * u[1] + qd.P(QP_CJ + 15 + l) * u[2];
         }
+        if (mode == 1 && st.ww) {                                        // (the wheel-wall rows' share of the border, as above)
+            for (int rr = 0; rr < 4; rr++) {
+                if (!(st.mask >> (QB_WW + rr) & 1u)) continue;
+                const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+                double sacc = 0;
+                for (int col = 0; col < 6; col++) sacc += (ch.wJ[0][col] + sg * ch.wJ[ta][col]) * xr[col];
+                sacc *= ch.wD;
+                for (int l = 0; l < 3; l++) t[l] -= (ch.wJ[0][6 + l] + sg * ch.wJ[ta][6 + l]) * sacc;
+            }
+        }
 #pragma unroll
         for (int l = 0; l < NC; l++) {
             double sacc = t[l];
@@ -499,7 +548,7 @@ struct QLs {
 };
 
 template <class Q>
-FT_HD void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, const QLs& L, LsPoint& pt, double alpha) {
+FT_HD void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, int ww, const QLs& L, LsPoint& pt, double alpha) {
     double q0 = L.c0, q1 = L.c1, q2 = L.c2;
 #pragma unroll
     for (int l = 0; l < NC; l++) {
@@ -537,6 +586,14 @@ FT_HD void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, const QLs& L, 
         for (int rr = 0; rr < 4; rr++) {
             const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
             const double jar = ch.dx[s][0] + sg * ch.dx[s][ta] - ch.aref[s][rr], jv = ch.ds[s][0] + sg * ch.ds[s][ta];
+            if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
+        }
+    }
+    if (ww) {
+        const double D = ch.wD;
+        for (int rr = 0; rr < 4; rr++) {
+            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+            const double jar = ch.wdx[0] + sg * ch.wdx[ta] - ch.waref[rr], jv = ch.wds[0] + sg * ch.wds[ta];
             if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
         }
     }
@@ -606,8 +663,13 @@ FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, doubl
         }
         for (int s = 0; s < st.nch; s++)
             for (int a = 0; a < 3; a++) { ch.dx[s][a] = dot6q(ch.J[s][a], xr); ch.ds[s][a] = dot6q(ch.J[s][a], sr); }
+        if (st.ww)
+            for (int a = 0; a < 3; a++) {
+                ch.wdx[a] = dot6q(ch.wJ[a], xr) + ch.wJ[a][6] * xc[0] + ch.wJ[a][7] * xc[1] + ch.wJ[a][8] * xc[2];
+                ch.wds[a] = dot6q(ch.wJ[a], sr) + ch.wJ[a][6] * sc[0] + ch.wJ[a][7] * sc[1] + ch.wJ[a][8] * sc[2];
+            }
     }
-    const int nch = st.nch;
+    const int nch = st.nch, ww = st.ww;
     const double gtol = SOLVER_TOL * LS_TOL * snorm / scale;
     enum { S_P0, S_P1, S_NEWTON, S_MID, S_A1, S_A2, S_DONE };
     int state = (on && snorm >= MINVAL) ? S_P0 : S_DONE, it = 0;
@@ -616,7 +678,7 @@ FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, doubl
     LsPoint p0, p1, p2, pm, a1, pt;
     p0.alpha = p0.cost = p0.d0 = 0; p0.d1 = 1; p1 = p0; p2 = p0; pm = p0; a1 = p0;
     while (qd.wany(state != S_DONE)) {
-        quad_ls_eval(qd, ch, nch, L, pt, alpha);
+        quad_ls_eval(qd, ch, nch, ww, L, pt, alpha);
         bool loop1 = false, loop2 = false;
         switch (state) {
         case S_P0:
@@ -674,11 +736,21 @@ FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, doubl
 }
 
 // ---- position + velocity stage of the lane: kinematics, M -> shared memory, bias, smooth force, contacts, rows ----
-struct QWallHit { double dist, nrm[3], t1[3], t2[3], pnt[3]; };
+// WallFn: the height-field walls of the car's track (hfield_contact.cuh rules V and S), or none
 struct QNoWalls {                    // open ground
     FT_HD bool enabled() const { return false; }
-    FT_HD bool operator()(const double*, const double*, int, QWallHit&) const { return false; }
+    FT_HD bool vertex(const double*, QWallHit&) const { return false; }
+    FT_HD bool convex(int, const double*, double, const double*, const double*, QWallHit&) const { return false; }
 };
+struct QHfWalls {                    // walls of one compiled track
+    HfView hv; bool on;
+    FT_HD bool enabled() const { return on; }
+    FT_HD bool vertex(const double* p, QWallHit& h) const { return hf_vertex_probe(hv, p, h); }
+    FT_HD bool convex(int kind, const double* size, double bound, const double* pos, const double* R, QWallHit& h) const {
+        return hf_convex(hv, kind, size, bound, pos, R, h);
+    }
+};
+constexpr double LIDAR_CYL_BOUND = 0.0336;       // > sqrt(0.03^2 + 0.015^2): bounding radius of the lidar cylinder
 
 template <class Q, class WallFn>
 FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, const double* qc, const double* vr, const double* vc,
@@ -937,26 +1009,78 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
         qd.P(QP_WC) = Dw;
         info.ncon_wheel = popc4(qd.ballot(on));
     }
-    // ---- chassis hull vertices vs walls: hit i (in vertex order, capped like the thread-per-car version) goes to
-    // lane i & 3, slot i >> 2
-    st.nch = 0;
-    info.ncon_wall = 0;
-    if (qd.wany(walls.enabled())) {
-        unsigned hits = 0;
-        for (int k = 0; k < 3; k++) {
-            const int v = 4 * k + w;
+    // ---- the lane's wheel ellipsoid vs the walls (rule S): one contact, Jacobian over chassis dofs + chain slots 0-2
+    st.ww = 0; st.nch = 0;
+    info.ncon_wall = 0; info.ncon_ground = 0;
+    const bool wall_on = walls.enabled();
+    if (qd.wany(wall_on)) {
+        if (wall_on) {
             QWallHit h;
-            const bool hit = walls.enabled() && v < MUSHR_CHASSIS_NHULL && walls(R1, p1, v, h);
-            hits |= qd.ballot(hit) << (4 * k);
+            const double wsz[3] = {WS0, WS1, WS2};
+            if (walls.convex(HF_ELLIPSOID, wsz, 0.03, pw, Rw, h)) {
+                st.ww = 1;
+                const double o[3] = {h.pnt[0] - com[0], h.pnt[1] - com[1], h.pnt[2] - com[2]};
+                double vel[3] = {0, 0, 0};
+                for (int col = 0; col < 9; col++) {
+                    const double* ax = col < 6 ? cdr[col] : cd[col - 6];
+                    double jp[3];
+                    cross3(jp, ax, o);
+                    for (int a = 0; a < 3; a++) jp[a] += ax[3 + a];
+                    const double j0 = dot3(h.nrm, jp), j1 = dot3(h.t1, jp), j2 = dot3(h.t2, jp), vk = col < 6 ? vr[col] : vc[col - 6];
+                    ch.wJ[0][col] = j0; ch.wJ[1][col] = j1; ch.wJ[2][col] = j2;
+                    vel[0] += j0 * vk; vel[1] += j1 * vk; vel[2] += j2 * vk;
+                }
+                kbi(0.45, h.dist, mc.wheel_invweight0[w], K, B, imp, R);
+                double Rpy = 2 * CH_MU * CH_MU * R; if (Rpy < MINVAL) Rpy = MINVAL;
+                ch.wD = 1 / Rpy;
+                for (int rr = 0; rr < 4; rr++) {
+                    const double sg = (rr & 1) ? -1.0 : 1.0;
+                    ch.waref[rr] = -B * (vel[0] + sg * CH_MU * vel[1 + (rr >> 1)]) - K * imp * h.dist;
+                }
+            }
+        }
+        info.ncon_wall = popc4(qd.ballot(st.ww != 0));
+    }
+    // ---- contacts of the car body's geoms: candidate c = 2 v (hull vertex v against the walls, rule V), 2 v + 1 (vertex v
+    // below the ground plane), 20 (lidar cylinder against the walls, rule S), 21 (cylinder below the ground plane); in that
+    // order, the first MAXBODYCON hits count; hit number i goes to lane i & 3, slot i >> 2.
+    // Nothing of the body can reach the ground while the bounding box of hull + cylinder stays above the plane:
+    const double body_zmin = p1[2] - fabs(R1[6]) * 0.1034 - fabs(R1[7]) * 0.0473 + (R1[8] > 0 ? R1[8] * 0.0151 : R1[8] * 0.0726);
+    const bool ground_on = body_zmin < PLANE_Z;
+    if (qd.wany(wall_on || ground_on)) {
+        const double hull[MUSHR_CHASSIS_NHULL][3] = MUSHR_CHASSIS_HULL;
+        const double csz[2] = {0.03, 0.015}, cloc[3] = {-0.0525, 0.0, 0.065 - 0.015 / 2}, down[3] = {0, 0, -1};
+        constexpr int NCAND = 2 * MUSHR_CHASSIS_NHULL + 2;
+        auto candidate = [&](int c, QWallHit& h) -> bool {
+            if (c >= NCAND) return false;
+            const bool ground = c & 1;
+            if (ground ? !ground_on : !wall_on) return false;
+            double p[3];
+            if (c < 2 * MUSHR_CHASSIS_NHULL) {
+                mat_vec3(p, R1, hull[c >> 1]);
+                for (int a = 0; a < 3; a++) p[a] += p1[a];
+                return ground ? ground_probe(p, h) : walls.vertex(p, h);
+            }
+            mat_vec3(p, R1, cloc);
+            for (int a = 0; a < 3; a++) p[a] += p1[a];
+            if (!ground) return walls.convex(HF_CYLINDER, csz, LIDAR_CYL_BOUND, p, R1, h);
+            double sp[3];
+            hf_support(HF_CYLINDER, csz, p, R1, down, sp);
+            return ground_probe(sp, h);
+        };
+        unsigned hits = 0;
+        for (int k = 0; k < (NCAND + 3) / 4; k++) {
+            QWallHit h;
+            hits |= qd.ballot(candidate(4 * k + w, h)) << (4 * k);
         }
         if (hits) {
-            const int cap = MAXCON - info.ncon_wheel;
             int rank = 0;
-            for (int v = 0; v < MUSHR_CHASSIS_NHULL && rank < cap; v++) {
-                if (!(hits >> v & 1u)) continue;
+            for (int c = 0; c < NCAND && rank < MAXBODYCON; c++) {
+                if (!(hits >> c & 1u)) continue;
+                if (c & 1) info.ncon_ground++; else info.ncon_wall++;
                 if ((rank & 3) == w) {
                     QWallHit h;
-                    walls(R1, p1, v, h);
+                    candidate(c, h);
                     const int s = st.nch++;
                     double o[3], vel[3] = {0, 0, 0};
                     for (int a = 0; a < 3; a++) o[a] = h.pnt[a] - com[a];
@@ -978,7 +1102,6 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
                 }
                 rank++;
             }
-            info.ncon_wall = rank;
         }
     }
     qd.sync();                       // per-car slots visible to the quad
@@ -1007,8 +1130,9 @@ FT_HD void quad_store_chain(int w, double* dst, const double* c, int base) {   /
 // packs the suspended cars of the whole fleet into fresh CTAs and goes on.  A CTA runs its cars in lock-step, so
 // without this every car pays for the slowest of its 54 neighbours: measured mean 2.1 Newton iterations per car,
 // 4.5 per CTA (tools/iteration_stats.py).  The arithmetic a car sees does not change (results are bit-identical).
-constexpr int QREC_LANE = QP_N + 46 + 2;                   // per lane: private slots, chassis contacts, (cost, gauss)
-constexpr int QREC_DOUBLES = 4 * QREC_LANE + QC_N + 8;     // + per-car slots + (c0, mask[4], nch[4], info) packed below
+constexpr int QREC_CH = QMAXCH * (1 + 4 + 18), QREC_WW = 1 + 4 + 27;
+constexpr int QREC_LANE = QP_N + QREC_CH + QREC_WW + 2;    // per lane: private slots, body contacts, wheel-wall contact, (cost, gauss)
+constexpr int QREC_DOUBLES = 4 * QREC_LANE + QC_N + 10;    // + per-car slots + (c0, mask[4], nch[4], ww[4], info) packed below
 struct QStage {
     int max_rounds;              // Newton rounds this launch may spend (<= 0: unlimited)
     bool resume;                 // the car's state comes from rec instead of qpos / qvel
@@ -1022,45 +1146,58 @@ FT_HD void quad_suspend(const Q& qd, const QChassis& ch, const QState& st, const
     double* r2 = rec + 4 * QP_N;
     {
         int k = 0;
-        for (int s = 0; s < QMAXCH; s++) {
-            r2[4 * k++ + w] = ch.D[s];
-            for (int rr = 0; rr < 4; rr++) r2[4 * k++ + w] = ch.aref[s][rr];
-            for (int a = 0; a < 3; a++) for (int c = 0; c < 6; c++) r2[4 * k++ + w] = ch.J[s][a][c];
+        for (int s = 0; s < QMAXCH; s++) {                            // (only the contacts that exist travel)
+            if (s < st.nch) {
+                r2[4 * k++ + w] = ch.D[s];
+                for (int rr = 0; rr < 4; rr++) r2[4 * k++ + w] = ch.aref[s][rr];
+                for (int a = 0; a < 3; a++) for (int c = 0; c < 6; c++) r2[4 * k++ + w] = ch.J[s][a][c];
+            } else k += 1 + 4 + 18;
         }
+        if (st.ww) {
+            r2[4 * k++ + w] = ch.wD;
+            for (int rr = 0; rr < 4; rr++) r2[4 * k++ + w] = ch.waref[rr];
+            for (int a = 0; a < 3; a++) for (int c = 0; c < 9; c++) r2[4 * k++ + w] = ch.wJ[a][c];
+        } else k += QREC_WW;
         r2[4 * k++ + w] = st.cost; r2[4 * k++ + w] = st.gauss;
     }
     double* r3 = rec + 4 * QREC_LANE;
     for (int i = w; i < QC_N; i += 4) r3[i] = qd.C(i);
     double* r4 = r3 + QC_N;
+    int* ii = reinterpret_cast<int*>(r4 + 1);
     if (w == 0) {
         r4[0] = st.c0;
-        int* ii = reinterpret_cast<int*>(r4 + 1);
-        ii[8] = info.iters; ii[9] = info.ncon_wheel; ii[10] = info.ncon_wall; ii[11] = info.reset;
+        ii[12] = info.iters; ii[13] = info.ncon_wheel; ii[14] = info.ncon_wall; ii[15] = info.reset; ii[16] = info.ncon_ground;
     }
-    int* ii = reinterpret_cast<int*>(r4 + 1);
-    ii[w] = (int)st.mask; ii[4 + w] = st.nch;
+    ii[w] = (int)st.mask; ii[4 + w] = st.nch; ii[8 + w] = st.ww;
 }
 template <class Q>
 FT_HD void quad_resume(const Q& qd, QChassis& ch, QState& st, StepInfo& info, const double* rec) {
     const int w = qd.lane();
     for (int i = 0; i < QP_N; i++) qd.P(i) = rec[4 * i + w];
-    const double* r2 = rec + 4 * QP_N;
-    {
-        int k = 0;
-        for (int s = 0; s < QMAXCH; s++) {
-            ch.D[s] = r2[4 * k++ + w];
-            for (int rr = 0; rr < 4; rr++) ch.aref[s][rr] = r2[4 * k++ + w];
-            for (int a = 0; a < 3; a++) for (int c = 0; c < 6; c++) ch.J[s][a][c] = r2[4 * k++ + w];
-        }
-        st.cost = r2[4 * k++ + w]; st.gauss = r2[4 * k++ + w];
-    }
     const double* r3 = rec + 4 * QREC_LANE;
     for (int i = 0; i < QC_N; i++) qd.C(i) = r3[i];          // every lane writes the same values
     const double* r4 = r3 + QC_N;
     st.c0 = r4[0];
     const int* ii = reinterpret_cast<const int*>(r4 + 1);
-    st.mask = (unsigned)ii[w]; st.nch = ii[4 + w];
-    info.iters = ii[8]; info.ncon_wheel = ii[9]; info.ncon_wall = ii[10]; info.reset = ii[11];
+    st.mask = (unsigned)ii[w]; st.nch = ii[4 + w]; st.ww = ii[8 + w];
+    info.iters = ii[12]; info.ncon_wheel = ii[13]; info.ncon_wall = ii[14]; info.reset = ii[15]; info.ncon_ground = ii[16];
+    const double* r2 = rec + 4 * QP_N;
+    {
+        int k = 0;
+        for (int s = 0; s < QMAXCH; s++) {
+            if (s < st.nch) {
+                ch.D[s] = r2[4 * k++ + w];
+                for (int rr = 0; rr < 4; rr++) ch.aref[s][rr] = r2[4 * k++ + w];
+                for (int a = 0; a < 3; a++) for (int c = 0; c < 6; c++) ch.J[s][a][c] = r2[4 * k++ + w];
+            } else k += 1 + 4 + 18;
+        }
+        if (st.ww) {
+            ch.wD = r2[4 * k++ + w];
+            for (int rr = 0; rr < 4; rr++) ch.waref[rr] = r2[4 * k++ + w];
+            for (int a = 0; a < 3; a++) for (int c = 0; c < 9; c++) ch.wJ[a][c] = r2[4 * k++ + w];
+        } else k += QREC_WW;
+        st.cost = r2[4 * k++ + w]; st.gauss = r2[4 * k++ + w];
+    }
 }
 
 // ---- the step -----------------------------------------------------------------------------------------------------
@@ -1074,8 +1211,8 @@ FT_HDN bool step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, doub
     const int qa = chain_q(w), da = chain_d(w);
     QChassis ch;
     QState st;
-    st.cost = 0; st.gauss = 0; st.mask = 0; st.c0 = 0; st.nch = 0;
-    info.reset = 0; info.iters = 0; info.ncon_wheel = 0; info.ncon_wall = 0;
+    st.cost = 0; st.gauss = 0; st.mask = 0; st.c0 = 0; st.nch = 0; st.ww = 0;
+    info.reset = 0; info.iters = 0; info.ncon_wheel = 0; info.ncon_wall = 0; info.ncon_ground = 0;
     qd.sync();                                                             // previous step's root state is in memory
     if (stage.resume) {
         if (live) quad_resume(qd, ch, st, info, stage.rec);
@@ -1143,8 +1280,8 @@ FT_HDN bool step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, doub
             c0 = qd.sum(c0); gw = qd.sum(gw);
             for (int i = 0; i < NR; i++) { c0 += qd.C(VS.c + i) * qd.C(VQFS.c + i); gw += qd.C(VX.c + i) * (0.5 * qd.C(VMA.c + i) - qd.C(VQFS.c + i)); }
             st.c0 = 0.5 * c0;
-            const double cw = qd.sum(rows_eval(qd, ch, st.nch, VX, fr_, fc_, m_)) + (gw + st.c0);
-            const double cs = qd.sum(rows_eval(qd, ch, st.nch, VS, fr_, fc_, m_));
+            const double cw = qd.sum(rows_eval(qd, ch, st.nch, st.ww, VX, fr_, fc_, m_)) + (gw + st.c0);
+            const double cs = qd.sum(rows_eval(qd, ch, st.nch, st.ww, VS, fr_, fc_, m_));
             double r[NR], c[NC], r2[NR], c2[NC];
             vec_load(qd, VS, r, c); vec_load(qd, VQFS, r2, c2);
             qd.sync();

@@ -31,58 +31,25 @@ static int ensure_model(int device) {
     return FTGP_OK;
 }
 
-// chassis-vs-wall contacts (this framework's definition, identical to oracle/step.c wall_contacts()):
-// each chassis hull vertex below the hfield surface gives one condim-3 contact against the surface
-// triangle's plane.  Reads the compiled track from global memory (L2-resident, ~50 KB).
-typedef QWallHit WallHit;     // { dist, nrm[3], t1[3], t2[3], pnt[3] }
-
-__device__ bool wall_probe(const uint32_t* blob, const TrackHeader* th, const double* R1, const double* p1, int v, WallHit& h) {
-    const double hull[MUSHR_CHASSIS_NHULL][3] = MUSHR_CHASSIS_HULL;
-    const uint16_t* index = reinterpret_cast<const uint16_t*>(blob + th->index_off);
-    const uint32_t* chunks = blob + th->chunks_off;
-    double p[3];
-    mat_vec3(p, R1, hull[v]);
-    for (int a = 0; a < 3; a++) p[a] += p1[a];
-    const int i = (int)floor(p[0] / th->dsize_x + 0.5), j = (int)floor(-p[1] / th->dsize_y + 0.5);
-    if (i < 0 || i >= th->hc || j < 0 || j >= th->vc) return false;
-    const uint32_t cid = index[(th->vc - 1 - j) * th->hc + i];
-    if (cid == EMPTY_CHUNK) return false;
-    const uint32_t* m = chunks + cid * CHUNK_WORDS;
-    const int ncol = m[13] & 0xFF, nrow = (m[13] >> 8) & 0xFF;
-    const double sx = 0.5 * th->dsize_x, sy = 0.5 * th->dsize_y;
-    const double dx = 2 * sx / (ncol - 1), dy = 2 * sy / (nrow - 1);
-    const double u = (p[0] - th->dsize_x * i + sx) / dx, vv = (p[1] + th->dsize_y * j + sy) / dy;
-    int cc = (int)floor(u), rr = (int)floor(vv);
-    cc = cc < 0 ? 0 : (cc > ncol - 2 ? ncol - 2 : cc); rr = rr < 0 ? 0 : (rr > nrow - 2 ? nrow - 2 : rr);
-    const double fu = u - cc, fv = vv - rr;
-    auto bit = [&](int r_, int c_) { int b = r_ * ncol + c_; return (double)((m[b >> 5] >> (b & 31)) & 1u) * 0.3; };
-    const double z00 = bit(rr, cc), z10 = bit(rr, cc + 1), z01 = bit(rr + 1, cc), z11 = bit(rr + 1, cc + 1);
-    double gx, gy, z;
-    if (fv <= fu) { gx = (z10 - z00) / dx; gy = (z11 - z10) / dy; z = z00 + (z10 - z00) * fu + (z11 - z10) * fv; }
-    else { gx = (z11 - z01) / dx; gy = (z01 - z00) / dy; z = z00 + (z11 - z01) * fu + (z01 - z00) * fv; }
-    const double nn = sqrt(gx * gx + gy * gy + 1);
-    h.nrm[0] = -gx / nn; h.nrm[1] = -gy / nn; h.nrm[2] = 1 / nn;
-    const double hh = -0.1 + z;
-    if (hh <= -0.1 + 1e-12 && h.nrm[2] > 0.999999) return false;
-    h.dist = (p[2] - hh) * h.nrm[2];
-    if (h.dist >= 0) return false;
-    // frame (mju_makeFrame)
-    h.t1[0] = h.t1[1] = h.t1[2] = 0;
-    if (h.nrm[1] < 0.5 && h.nrm[1] > -0.5) h.t1[1] = 1; else h.t1[2] = 1;
-    const double d = dot3(h.nrm, h.t1);
-    for (int a = 0; a < 3; a++) h.t1[a] -= d * h.nrm[a];
-    const double tn = sqrt(dot3(h.t1, h.t1));
-    for (int a = 0; a < 3; a++) h.t1[a] /= tn;
-    cross3(h.t2, h.nrm, h.t1);
-    for (int a = 0; a < 3; a++) h.pnt[a] = p[a] - h.nrm[a] * h.dist * 0.5;
-    return true;
+// the walls of the car's track as the contact rules see them (hfield_contact.cuh); read from global memory (L2-resident, ~50 KB)
+__device__ __forceinline__ QHfWalls track_walls(const uint32_t* blob, const int32_t* track_id, int64_t car, bool shadowed) {
+    QHfWalls w;
+    w.on = false; w.hv.index = nullptr; w.hv.chunks = nullptr; w.hv.hc = w.hv.vc = 0; w.hv.size_x = w.hv.size_y = 1;
+    if (!blob || shadowed) return w;        // a finished ("shadowed") car no longer collides with walls (custom.py:1455-1464)
+    const GeomHeader* gh = reinterpret_cast<const GeomHeader*>(blob);
+    int tid = track_id ? track_id[car] : 0;
+    if (tid < 0 || tid >= gh->ntracks) tid = 0;
+    const TrackHeader* th = reinterpret_cast<const TrackHeader*>(blob + gh->track_off[tid]);
+    w.on = true;
+    w.hv.index = reinterpret_cast<const uint16_t*>(blob + th->index_off);
+    w.hv.chunks = blob + th->chunks_off;
+    w.hv.hc = th->hc; w.hv.vc = th->vc; w.hv.size_x = th->dsize_x; w.hv.size_y = th->dsize_y;
+    return w;
 }
-
-struct WallsQuad {                              // quad-per-car flavour: probe of one hull vertex
-    const uint32_t* blob; const TrackHeader* th;
-    __device__ __forceinline__ bool enabled() const { return blob != nullptr; }
-    __device__ __forceinline__ bool operator()(const double* R1, const double* p1, int v, QWallHit& h) const { return wall_probe(blob, th, R1, p1, v, h); }
-};
+__device__ __forceinline__ int status_word(const StepInfo& info, int prev) {
+    return (info.iters & 0xFF) | (info.reset ? 0x100 : (prev & 0x100)) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24) |
+           ((info.ncon_ground > 7 ? 7 : info.ncon_ground) << 28);
+}
 
 // Quad-per-car: four lanes (one per wheel chain) advance one car, 8 cars per warp; see mushr_step_quad.cuh.
 // Shared memory: [slot][thread] for the lane-private slots, [slot][car] for the per-car slots, then the table of
@@ -106,14 +73,8 @@ step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
     if (perm) car = perm[car];                      // cars grouped by their last Newton iteration count
     QuadDev<NT, NT / 4, LOCK> qd;
     qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.qs = tid & 28;
-    WallsQuad walls{nullptr, nullptr};
     const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
-    if (blob && !shadowed) {
-        const GeomHeader* gh = reinterpret_cast<const GeomHeader*>(blob);
-        int tid_ = track_id ? track_id[car] : 0;
-        if (tid_ < 0 || tid_ >= gh->ntracks) tid_ = 0;
-        walls.blob = blob; walls.th = reinterpret_cast<const TrackHeader*>(blob + gh->track_off[tid_]);
-    }
+    const QHfWalls walls = track_walls(blob, track_id, car, shadowed);
     int st = 0;
     for (int s = 0; s < nsteps; s++) {
         StepInfo info;
@@ -125,7 +86,7 @@ step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
             if (live && qd.w == 0) list_out[atomicAdd(count_out, 1)] = (int32_t)car;
             return;
         }
-        st = (info.iters & 0xFF) | (info.reset ? 0x100 : (st & 0x100)) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24);
+        st = status_word(info, st);
     }
     if (status && qd.w == 0 && live) status[car] = st;
 }
@@ -146,7 +107,7 @@ step_quad_resume_kernel(double* __restrict__ qpos, double* __restrict__ qvel, do
     const int n = *count_in;
     QuadDev<NT, NT / 4, true> qd;
     qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.qs = tid & 28;
-    const WallsQuad walls{nullptr, nullptr};             // (the position stage, which probes the walls, is behind us)
+    const QHfWalls walls = track_walls(nullptr, nullptr, 0, true);   // (the position stage, which probes the walls, is behind us)
     for (int base = blockIdx.x * CARS; base < n; base += gridDim.x * CARS) {
         const int e = base + cib;
         const bool live = e < n;
@@ -156,7 +117,7 @@ step_quad_resume_kernel(double* __restrict__ qpos, double* __restrict__ qvel, do
         const bool suspended = step_car_quad(qd, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, live, info, stage);
         if (live && qd.w == 0) {
             if (suspended) list_out[atomicAdd(count_out, 1)] = (int32_t)car;
-            else if (status) status[car] = (info.iters & 0xFF) | (info.reset ? 0x100 : 0) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24);
+            else if (status) status[car] = status_word(info, 0);
         }
         __syncthreads();                                 // the next batch reuses the shared-memory slots
     }

@@ -206,16 +206,16 @@ bad:
 }
 
 // ---------------------------------------------------------------- device upload
-extern "C" ftgp_geom* ftgp_geom_create(const ftgp_track* const* tracks, const double* const* paths,
-                                       int ntracks, int device) {
-    if (!tracks || ntracks < 1 || ntracks > FTGP_MAX_TRACKS) { set_error("ftgp_geom_create: ntracks must be 1..%d", FTGP_MAX_TRACKS); return nullptr; }
+// the geometry blob (layout: common.h) of up to FTGP_MAX_TRACKS compiled tracks; empty on error
+static std::vector<uint32_t> build_blob(const ftgp_track* const* tracks, const double* const* paths, int ntracks) {
+    if (!tracks || ntracks < 1 || ntracks > FTGP_MAX_TRACKS) { set_error("geometry: ntracks must be 1..%d", FTGP_MAX_TRACKS); return {}; }
     std::vector<uint32_t> blob(sizeof(GeomHeader) / 4, 0);
     GeomHeader gh{};
     gh.ntracks = ntracks;
     std::vector<int> thdr_off(ntracks);
     for (int k = 0; k < ntracks; k++) {
         const ftgp_track* t = tracks[k];
-        if (!t) { set_error("ftgp_geom_create: track %d is null", k); return nullptr; }
+        if (!t) { set_error("geometry: track %d is null", k); return {}; }
         TrackHeader th{};
         th.hc = t->hc; th.vc = t->vc; th.nchunks = (int)t->counts.size(); th.chunk_px = t->chunk_px;
         th.size_x = (float)t->size_x; th.size_y = (float)t->size_y;
@@ -273,7 +273,31 @@ extern "C" ftgp_geom* ftgp_geom_create(const ftgp_track* const* tracks, const do
     while (blob.size() % 4) blob.push_back(0);
     gh.total_words = (int)blob.size();
     memcpy(blob.data(), &gh, sizeof gh);
+    return blob;
+}
 
+extern "C" int64_t ftgp_geom_blob(const ftgp_track* const* tracks, const double* const* paths, int ntracks,
+                                  uint32_t* out, int64_t cap_words) {
+    const std::vector<uint32_t> blob = build_blob(tracks, paths, ntracks);
+    if (blob.empty()) return -1;
+    if (out && cap_words >= (int64_t)blob.size()) memcpy(out, blob.data(), blob.size() * 4);
+    return (int64_t)blob.size();
+}
+
+extern "C" int ftgp_blob_track_view(const uint32_t* blob, int track, int32_t* out4, double* size_xy2) {
+    if (!blob || !out4 || !size_xy2) { set_error("ftgp_blob_track_view: bad argument"); return FTGP_ERR_ARG; }
+    GeomHeader gh; memcpy(&gh, blob, sizeof gh);
+    if (track < 0 || track >= gh.ntracks) { set_error("ftgp_blob_track_view: no such track"); return FTGP_ERR_ARG; }
+    TrackHeader th; memcpy(&th, blob + gh.track_off[track], sizeof th);
+    out4[0] = th.index_off; out4[1] = th.chunks_off; out4[2] = th.hc; out4[3] = th.vc;
+    size_xy2[0] = th.dsize_x; size_xy2[1] = th.dsize_y;
+    return FTGP_OK;
+}
+
+extern "C" ftgp_geom* ftgp_geom_create(const ftgp_track* const* tracks, const double* const* paths,
+                                       int ntracks, int device) {
+    std::vector<uint32_t> blob = build_blob(tracks, paths, ntracks);
+    if (blob.empty()) return nullptr;
     ftgp_geom* g = new ftgp_geom();
     g->device = device; g->ntracks = ntracks; g->bytes = (int64_t)blob.size() * 4;
     g->h_blob = blob;

@@ -79,6 +79,13 @@ typedef struct ftgp_geom ftgp_geom;
 ftgp_geom* ftgp_geom_create(const ftgp_track* const* tracks, const double* const* paths,
                             int ntracks, int device);
 void ftgp_geom_destroy(ftgp_geom* g);
+/* Host-only: the same geometry blob in host memory (no CUDA device needed; for tools and the CPU test harness).
+ * Returns the blob size in 32-bit words (out may be NULL to query it), -1 on error. */
+int64_t ftgp_geom_blob(const ftgp_track* const* tracks, const double* const* paths, int ntracks,
+                       uint32_t* out, int64_t cap_words);
+/* Where one track sits inside a blob: out4 = {index grid offset, chunk table offset (32-bit words), horizontal_chunks,
+ * vertical_chunks}, size_xy2 = chunk pitch in metres.  index grid: uint16[vc][hc] (row vc-1-j), chunk table: 28 words each. */
+int ftgp_blob_track_view(const uint32_t* blob, int track, int32_t* out4, double* size_xy2);
 int ftgp_geom_device(const ftgp_geom* g);
 int64_t ftgp_geom_bytes(const ftgp_geom* g);
 
@@ -112,8 +119,9 @@ int ftgp_reset(double* qpos, double* qvel, double* warm, double* ctrl, const dou
 /* Replaces mujoco.mj_step(model, data) (custom.py:1425) for ncars independent cars of
  * template/mushr.em.xml (timestep 0.004, Newton, pyramidal cones).  status: device
  * int32[ncars] or NULL, per car: bits 0-7 Newton iterations of the last step, bit 8 =
- * state was reset (MuJoCo's bad-state check), bits 16-23 wall contacts, bits 24-27
- * wheel-ground contacts.  g may be NULL (open ground plane, no walls).  lap: device lap state
+ * state was reset (MuJoCo's bad-state check), bits 16-23 contacts with walls (wheels, chassis hull
+ * vertices, lidar cylinder), bits 24-27 wheel-ground contacts, bits 28-30 chassis / lidar-cylinder
+ * contacts with the ground (a flipped car).  g may be NULL (open ground plane, no walls).  lap: device lap state
  * (FTGP_LAP_* rows, see below) or NULL; a car whose FTGP_LAP_FINISHED field is set has been
  * shadow()ed (custom.py:1455-1464: conaffinity 0 / contype 2): it no longer collides with walls. */
 int ftgp_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,

@@ -217,5 +217,11 @@ class Model:
                                 _p(M), _p(qfs), _p(J), _p(D), _p(R), _p(aref), _p(fl), _p(ty), C.byref(ncc))
         assert k >= 0
         return M, qfs, J[:k], D[:k], R[:k], aref[:k], fl[:k], ty[:k], ncc.value
+    def contacts(self, track, qpos, maxcon=16):
+        """TEST SUPPORT: [(body, dist, pos[3], normal[3], mu, d0)] of one car (oracle/step.c car_contacts)."""
+        out = np.zeros((maxcon, 10))
+        L = lib(); L.fto_contacts.restype = C.c_int
+        n = L.fto_contacts(self.ptr, track.ptr if track is not None else None, _p(np.ascontiguousarray(qpos, dtype=np.float64)), _p(out), maxcon)
+        return out[:n]
     def energy(self, qpos, qvel):
         return lib().fto_energy(self.ptr, _p(np.ascontiguousarray(qpos)), _p(np.ascontiguousarray(qvel)))

@@ -15,7 +15,7 @@
  * Scope: an independent car on the ground plane and (optionally) the hfield walls of a
  * compiled track.  Wheel-ground contacts are MuJoCo's analytic plane-vs-convex support
  * point.  Wall contacts and chassis/lidar-ground contacts are NOT MuJoCo's convex-vs-prism
- * CCD (SURVEY hard part 2): they are this framework's own definition, see wall_contacts().
+ * CCD (SURVEY hard part 2): they are this framework's own definition, see car_contacts().
  */
 #include "oracle_internal.h"
 #include "mushr_mesh.h"
@@ -29,7 +29,8 @@
 #define NV FTO_NV
 #define NQ FTO_NQ
 #define NEQ 2
-#define MAXCON 8            /* framework rule: at most 8 contacts per car (4 wheel-ground first, then chassis-wall in hull-vertex order) */
+#define MAXCON 16           /* framework rule: 4 wheel-ground + 4 wheel-wall + up to MAXBODYCON contacts of the car body's geoms */
+#define MAXBODYCON 8
 #define MAXEFC (NEQ + 23 + 7 + 4 * MAXCON)
 
 enum { J_FREE, J_BALL, J_SLIDE, J_HINGE };
@@ -570,34 +571,135 @@ static int wheel_plane(const fto_model* m, const kin_t* k, contact_t* con) {
     return n;
 }
 
-/* Wall contacts -- THIS FRAMEWORK'S DEFINITION, not MuJoCo's CCD (SURVEY B.6 [V], hard part 2).
- * MuJoCo collides the chassis hull / lidar cylinder / wheel ellipsoids with per-triangle prisms of
- * every overlapping hfield through MPR/GJK; bit-level agreement is unrealistic, so the framework
- * defines: each of a fixed set of probe points on the car (the 10 chassis hull vertices and the four
- * wheel centres' outermost horizontal points) that lies below the hfield surface height(x, y) gives
- * one condim-3 contact with the surface triangle's plane: normal = triangle normal (pointing out of
- * the wall), dist = signed distance to that plane, friction = max(geom) = 1 (hfield default) with
- * default solref/solimp.  The CUDA product implements the identical rule. */
+/* Contacts other than wheel-ground -- THIS FRAMEWORK'S DEFINITION, not MuJoCo's CCD (SURVEY B.6 [V], hard part 2).
+ * MuJoCo collides the chassis hull / lidar cylinder / wheel ellipsoids (contype 1, mushr.em.xml:69,108,119) with
+ * per-triangle prisms of every overlapping hfield (conaffinity 1, :92) through MPR / GJK, and with the ground plane
+ * (conaffinity 3, :94) through its plane-convex routines; bit-level agreement of those contact sets is unrealistic, so the
+ * framework defines (the CUDA product implements the identical rules from independent code):
+ *
+ *   rule V (vertex probe)   a chassis hull vertex p below the hfield surface at (p.x, p.y) -> one contact against that
+ *                           surface triangle's plane; a hull vertex below the ground plane z = 0.01 -> one contact, n = +z
+ *   rule S (support point)  a smooth convex geom G (wheel ellipsoid, lidar cylinder): for every surface triangle T of the
+ *                           hfield cells under G's bounding square with at least one raised vertex, let n be T's unit normal
+ *                           and s the support point of G in direction -n; if s projects vertically into T and lies below
+ *                           T's plane, (T, s) is a candidate; the DEEPEST candidate is G's one wall contact.  Against the
+ *                           ground plane: s = support point in -z, one contact if s.z < 0.01 (the wheel-ground rule).
+ *   every contact: condim 3, dist = signed distance to the plane, pos = point - n dist / 2, frame = mju_makeFrame(n);
+ *   friction = max of the two geoms (hfield / chassis / cylinder default 1, plane 0.5, wheel 0.3), solref default,
+ *   solimp[0] = mean (0.45 with a wheel, else 0.9).
+ *   order and caps: wheel-ground (<= 4), wheel-wall (<= 1 per wheel), then the car body's contacts, at most MAXBODYCON:
+ *   per hull vertex in mesh order its wall then its ground contact, then cylinder-wall, then cylinder-ground.
+ *   A shadowed (finished) car has contype 2: ground contacts only (custom.py:1455-1464). */
 static void hfield_plane_at(const fto_track* t, double x, double y, double* nrm, double* h);
-static int wall_contacts(const fto_model* m, const fto_track* t, const kin_t* k, contact_t* con, int n) {
-    if (!t) return n;
-    for (int v = 0; v < MUSHR_CHASSIS_NHULL && n < MAXCON; v++) {
+enum { G_ELLIPSOID, G_CYLINDER };
+static void support_local(int kind, const double* size, const double* d, double* s) {   /* support point in direction d, geom frame */
+    if (kind == G_ELLIPSOID) {
+        double n = 0;
+        for (int a = 0; a < 3; a++) { s[a] = size[a] * d[a]; n += s[a] * s[a]; }
+        n = sqrt(n);
+        for (int a = 0; a < 3; a++) s[a] = size[a] * s[a] / n;
+    } else {                                                                            /* cylinder: radius size[0], half height size[1] */
+        double h = sqrt(d[0] * d[0] + d[1] * d[1]);
+        s[0] = h > FTO_MINVAL ? size[0] * d[0] / h : 0; s[1] = h > FTO_MINVAL ? size[0] * d[1] / h : 0;
+        s[2] = d[2] >= 0 ? size[1] : -size[1];
+    }
+}
+static void support_world(int kind, const double* size, const double* pos, const double* R, const double* dir, double* out) {
+    double dl[3] = {R[0] * dir[0] + R[3] * dir[1] + R[6] * dir[2], R[1] * dir[0] + R[4] * dir[1] + R[7] * dir[2],
+                    R[2] * dir[0] + R[5] * dir[1] + R[8] * dir[2]};
+    double sl[3];
+    support_local(kind, size, dl, sl);
+    mat_vec(out, R, sl);
+    for (int a = 0; a < 3; a++) out[a] += pos[a];
+}
+/* rule S against the walls: 1 if G touches, with the contact's normal, support point and distance */
+static int convex_hfield(const fto_track* t, int kind, const double* size, double bound, const double* pos, const double* R,
+                         double* nrm_out, double* s_out, double* dist_out) {
+    int found = 0;
+    double best = 0;
+    const int i0 = (int)floor((pos[0] - bound) / t->size_x + 0.5), i1 = (int)floor((pos[0] + bound) / t->size_x + 0.5);
+    const int j0 = (int)floor(-(pos[1] + bound) / t->size_y + 0.5), j1 = (int)floor(-(pos[1] - bound) / t->size_y + 0.5);
+    for (int i = i0; i <= i1; i++) for (int j = j0; j <= j1; j++) {
+        if (i < 0 || i >= t->hc || j < 0 || j >= t->vc) continue;
+        const int id = t->index[i * t->vc + j];
+        if (id < 0) continue;
+        const fto_chunk* c = &t->chunks[id];
+        const double dx = 2 * c->size[0] / (c->ncol - 1), dy = 2 * c->size[1] / (c->nrow - 1);
+        const double x0 = c->pos[0] - c->size[0], y0 = c->pos[1] - c->size[1];
+        int c0 = (int)floor((pos[0] - bound - x0) / dx), c1 = (int)floor((pos[0] + bound - x0) / dx);
+        int r0 = (int)floor((pos[1] - bound - y0) / dy), r1 = (int)floor((pos[1] + bound - y0) / dy);
+        if (c0 < 0) c0 = 0;
+        if (r0 < 0) r0 = 0;
+        if (c1 > c->ncol - 2) c1 = c->ncol - 2;
+        if (r1 > c->nrow - 2) r1 = c->nrow - 2;
+        for (int rr = r0; rr <= r1; rr++) for (int cc = c0; cc <= c1; cc++) {
+            const double z00 = c->data[rr * c->ncol + cc] * c->size[2], z10 = c->data[rr * c->ncol + cc + 1] * c->size[2];
+            const double z01 = c->data[(rr + 1) * c->ncol + cc] * c->size[2], z11 = c->data[(rr + 1) * c->ncol + cc + 1] * c->size[2];
+            for (int tri = 0; tri < 2; tri++) {
+                double gx, gy, za;                                               /* plane: z = za + gx (fu dx) + gy (fv dy) */
+                if (tri == 0) { if (z00 == 0 && z10 == 0 && z11 == 0) continue; gx = (z10 - z00) / dx; gy = (z11 - z10) / dy; za = z00; }
+                else { if (z00 == 0 && z01 == 0 && z11 == 0) continue; gx = (z11 - z01) / dx; gy = (z01 - z00) / dy; za = z00; }
+                const double nn = sqrt(gx * gx + gy * gy + 1);
+                const double nrm[3] = {-gx / nn, -gy / nn, 1 / nn}, dir[3] = {gx / nn, gy / nn, -1 / nn};
+                double sp[3];
+                support_world(kind, size, pos, R, dir, sp);
+                const double fu = (sp[0] - x0) / dx - cc, fv = (sp[1] - y0) / dy - rr;
+                if (tri == 0 ? !(fv >= 0 && fv <= fu && fu <= 1) : !(fu >= 0 && fu <= fv && fv <= 1)) continue;
+                const double zs = c->pos[2] + za + gx * fu * dx + gy * fv * dy;
+                const double dist = (sp[2] - zs) * nrm[2];
+                if (dist >= 0 || (found && dist >= best)) continue;
+                found = 1; best = dist;
+                memcpy(nrm_out, nrm, 24); memcpy(s_out, sp, 24); *dist_out = dist;
+            }
+        }
+    }
+    return found;
+}
+static void contact_fill(contact_t* c, int body, const double* point, const double* nrm, double dist, double mu, double d0) {
+    c->dist = dist; c->body = body;
+    for (int a = 0; a < 3; a++) c->pos[a] = point[a] - nrm[a] * dist * 0.5;
+    memcpy(c->frame, nrm, 24); make_frame(c->frame);
+    c->mu[0] = c->mu[1] = mu;
+    c->solref[0] = 0.02; c->solref[1] = 1;
+    const double si[5] = {d0, 0.95, 0.001, 0.5, 2};
+    memcpy(c->solimp, si, sizeof si);
+}
+/* appends to con[n..]; counts[0] = wheel-wall, [1] = body-wall, [2] = body-ground contacts */
+static int car_contacts(const fto_model* m, const fto_track* t, const kin_t* k, contact_t* con, int n, int* counts) {
+    const double up[3] = {0, 0, 1}, down[3] = {0, 0, -1};
+    counts[0] = counts[1] = counts[2] = 0;
+    if (t) for (int w = 0; w < 4; w++) {                                              /* wheel ellipsoids vs walls (rule S) */
+        const int b = m->wheel_body[w];
+        double nrm[3], sp[3], dist;
+        if (!convex_hfield(t, G_ELLIPSOID, m->wheel_size, 0.03, k->xpos[b], k->xmat[b], nrm, sp, &dist)) continue;
+        contact_fill(&con[n++], b, sp, nrm, dist, 1.0, 0.45);
+        counts[0]++;
+    }
+    int nb = 0;
+    for (int v = 0; v < MUSHR_CHASSIS_NHULL; v++) {                                   /* chassis hull vertices (rule V) */
         double p[3];
         mat_vec(p, k->xmat[1], m->hull[v]);
         for (int a = 0; a < 3; a++) p[a] += k->xpos[1][a];
-        double nrm[3], h;
-        hfield_plane_at(t, p[0], p[1], nrm, &h);
-        if (h <= -0.1 + 1e-12 && nrm[2] > 0.999999) continue;                      /* flat floor cell: below the ground plane */
-        double dist = (p[2] - h) * nrm[2];
-        if (dist >= 0) continue;
-        contact_t* c = &con[n++];
-        c->dist = dist; c->body = 1;
-        for (int a = 0; a < 3; a++) c->pos[a] = p[a] - nrm[a] * dist * 0.5;
-        memcpy(c->frame, nrm, 24); make_frame(c->frame);
-        c->mu[0] = c->mu[1] = 1.0;
-        c->solref[0] = 0.02; c->solref[1] = 1;
-        const double si[5] = {0.9, 0.95, 0.001, 0.5, 2};
-        memcpy(c->solimp, si, sizeof si);
+        if (t && nb < MAXBODYCON) {
+            double nrm[3], h;
+            hfield_plane_at(t, p[0], p[1], nrm, &h);
+            const double dist = (p[2] - h) * nrm[2];
+            if (!(h <= -0.1 + 1e-12 && nrm[2] > 0.999999) && dist < 0) {             /* (flat floor cell: below the ground plane) */
+                contact_fill(&con[n++], 1, p, nrm, dist, 1.0, 0.9); nb++; counts[1]++;
+            }
+        }
+        if (p[2] - 0.01 < 0 && nb < MAXBODYCON) { contact_fill(&con[n++], 1, p, up, p[2] - 0.01, 1.0, 0.9); nb++; counts[2]++; }
+    }
+    {                                                                                 /* lidar cylinder (mushr.em.xml:108) */
+        const double size[2] = {0.03, 0.015}, local[3] = {-0.0525, 0.0, 0.065 - 0.015 / 2};
+        double pos[3], nrm[3], sp[3], dist;
+        mat_vec(pos, k->xmat[1], local);
+        for (int a = 0; a < 3; a++) pos[a] += k->xpos[1][a];
+        if (t && nb < MAXBODYCON && convex_hfield(t, G_CYLINDER, size, 0.0336, pos, k->xmat[1], nrm, sp, &dist)) {
+            contact_fill(&con[n++], 1, sp, nrm, dist, 1.0, 0.9); nb++; counts[1]++;
+        }
+        support_world(G_CYLINDER, size, pos, k->xmat[1], down, sp);
+        if (sp[2] - 0.01 < 0 && nb < MAXBODYCON) { contact_fill(&con[n++], 1, sp, up, sp[2] - 0.01, 1.0, 0.9); nb++; counts[2]++; }
     }
     return n;
 }
@@ -934,8 +1036,8 @@ int fto_step(const fto_model* m, const fto_track* t, double* qpos, double* qvel,
     /* ---- position stage */
     kinematics(m, qpos, k); com_pos(m, k); crb(m, k);
     contact_t con[MAXCON];
-    int nwheel = wheel_plane(m, k, con);
-    int ncon = wall_contacts(m, t, k, con, nwheel);
+    int nwheel = wheel_plane(m, k, con), cnt[3];
+    int ncon = car_contacts(m, t, k, con, nwheel, cnt);
     make_constraint(m, k, qpos, con, ncon, e);
     /* ---- velocity stage */
     com_vel(m, qvel, k);
@@ -976,9 +1078,29 @@ int fto_step(const fto_model* m, const fto_track* t, double* qpos, double* qvel,
     chol_solve(L, NV, NV, qa);
     for (int d = 0; d < NV; d++) qvel[d] += TIMESTEP * qa[d];
     integrate_pos(m, qpos, qvel, TIMESTEP);
-    if (info) { info[0] = iters; info[1] = e->n; info[2] = nwheel; info[3] = ncon - nwheel; info[4] = 0; }
+    /* info[3] = contacts with walls (wheels + chassis + lidar cylinder), info[5] = chassis / cylinder contacts with the ground */
+    if (info) { info[0] = iters; info[1] = e->n; info[2] = nwheel; info[3] = cnt[0] + cnt[1]; info[4] = 0; info[5] = cnt[2]; info[6] = cnt[0]; }
     free(k); free(e);
     return rc;
+}
+
+/* TEST SUPPORT: the contact set of one car at qpos, 10 doubles per contact: body, dist, pos[3], normal[3], mu, solimp d0.
+ * Order: wheel-ground, wheel-wall, car-body contacts (see car_contacts).  Returns the number of contacts. */
+int fto_contacts(const fto_model* m, const fto_track* t, const double* qpos, double* out, int maxcon) {
+    kin_t* k = (kin_t*)malloc(sizeof(kin_t));
+    kinematics(m, qpos, k); com_pos(m, k);
+    contact_t con[MAXCON];
+    int cnt[3];
+    int n = car_contacts(m, t, k, con, wheel_plane(m, k, con), cnt);
+    if (n > maxcon) n = maxcon;
+    for (int c = 0; c < n; c++) {
+        double* o = out + 10 * c;
+        o[0] = con[c].body; o[1] = con[c].dist;
+        memcpy(o + 2, con[c].pos, 24); memcpy(o + 5, con[c].frame, 24);
+        o[8] = con[c].mu[0]; o[9] = con[c].solimp[0];
+    }
+    free(k);
+    return n;
 }
 
 typedef struct { const fto_model* m; const fto_track* t; double *qpos, *qvel, *warm; const double* ctrl; int64_t lo, hi; int* info; } job_t;
@@ -1043,8 +1165,8 @@ int fto_constraint_problem(const fto_model* m, const fto_track* t, const double*
     efc_t* e = (efc_t*)malloc(sizeof(efc_t));
     kinematics(m, qpos, k); com_pos(m, k); crb(m, k);
     contact_t con[MAXCON];
-    int nwheel = wheel_plane(m, k, con);
-    int ncon = wall_contacts(m, t, k, con, nwheel);
+    int nwheel = wheel_plane(m, k, con), cnt[3];
+    int ncon = car_contacts(m, t, k, con, nwheel, cnt);
     make_constraint(m, k, qpos, con, ncon, e);
     com_vel(m, qvel, k);
     double passive[NV], bias[NV], act[NV] = {0};
@@ -1301,8 +1423,8 @@ static int world_assemble(const fto_model* m, const fto_track* t, int ncars, con
         const double* q = qpos + (size_t)c * NQ; const double* v = qvel + (size_t)c * NV; const double* u = ctrl + 2 * (size_t)c;
         kinematics(m, q, k); com_pos(m, k); crb(m, k);
         contact_t con[MAXCON];
-        int nwheel = wheel_plane(m, k, con);
-        int ncon = (shadowed && shadowed[c]) ? nwheel : wall_contacts(m, t, k, con, nwheel);   /* custom.py:1455-1464 */
+        int nwheel = wheel_plane(m, k, con), cnt[3];
+        int ncon = car_contacts(m, (shadowed && shadowed[c]) ? 0 : t, k, con, nwheel, cnt);    /* custom.py:1455-1464 */
         if (nwheel_out) nwheel_out[c] = nwheel;
         make_constraint(m, k, q, con, ncon, e);
         com_vel(m, v, k);

@@ -47,6 +47,12 @@ struct QuadHost : QuadMem<4, 1> {
 
 static ModelConsts g_mc;
 static bool g_ready = false;
+// walls: one compiled track of the product's geometry blob (ftgp_geom_blob / ftgp_blob_track_view), or none
+static QHfWalls g_walls = {{nullptr, nullptr, 0, 0, 1.0, 1.0}, false};
+extern "C" void hq_set_walls(const uint16_t* index, const uint32_t* chunks, int hc, int vc, double size_x, double size_y) {
+    g_walls.on = index != nullptr;
+    g_walls.hv.index = index; g_walls.hv.chunks = chunks; g_walls.hv.hc = hc; g_walls.hv.vc = vc; g_walls.hv.size_x = size_x; g_walls.hv.size_y = size_y;
+}
 extern "C" int hq_step_ghost(double* qpos, double* qvel, double* warm, const double* ctrl, long n, int nsteps, int* info4, int ghost_w, int ghost_c) {
     if (!g_ready) { g_mc = model_constants(); g_ready = true; }
     QuadHostShared sh;
@@ -59,7 +65,7 @@ extern "C" int hq_step_ghost(double* qpos, double* qvel, double* warm, const dou
                 for (int k = 0; k < nsteps; k++) {
                     StepInfo si;
                     q.ghost_w = ghost_w; q.ghost_c = ghost_c;
-                    step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), true, si, QStage{0, false, nullptr});
+                    step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, g_walls, true, si, QStage{0, false, nullptr});
                     q.sync();
                     if (info4 && w == 0) { info4[4 * i] = si.iters; info4[4 * i + 1] = si.ncon_wheel; info4[4 * i + 2] = si.ncon_wall; info4[4 * i + 3] = si.reset; }
                 }
@@ -87,7 +93,7 @@ extern "C" int hq_step_staged(double* qpos, double* qvel, double* warm, const do
                 const int budget[3] = {k1, k2, 0};
                 bool sus = false;
                 for (int stage = 0; stage < 3; stage++) {
-                    sus = step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), true, si,
+                    sus = step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, g_walls, true, si,
                                         QStage{budget[stage], stage > 0, rec.data()});
                     q.sync();
                     if (!sus) break;
@@ -170,7 +176,7 @@ static int warp_step(double* qpos, double* qvel, double* warm, const double* ctr
             WarpQuadHost<NQ_> q; q.s = &sh; q.tid = tid; q.w = tid & 3; q.quad = tid >> 2;
             const int i = q.quad;
             StepInfo si;
-            bool sus = step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), true, si,
+            bool sus = step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, g_walls, true, si,
                                      QStage{k1, false, recs.data() + (size_t)i * QREC_DOUBLES});
             q.sync();
             if (q.w == 0) suspended[i] = sus;
@@ -180,7 +186,7 @@ static int warp_step(double* qpos, double* qvel, double* warm, const double* ctr
             if (anysus) {
                 StepInfo s2;
                 const bool live = suspended[i] != 0;
-                step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, QNoWalls(), live, s2,
+                step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, g_walls, live, s2,
                               QStage{0, true, recs.data() + (size_t)i * QREC_DOUBLES});
                 if (live) si = s2;
                 q.sync();

@@ -154,54 +154,4 @@ def test_oracle_world_scan_matches_bruteforce_with_other_cars(otracks, walls):
     assert seen_cars >= 8                                         # several rays really end on another car's cylinder
 
 
-def test_wall_contact_distances_against_the_triangle_mesh(oracle, otracks, walls):
-    """Chassis-wall contacts are this framework's definition: a chassis hull vertex below the
-    hfield surface gives a contact against the plane of the surface triangle under it, dist = (z - h) n_z.  Checked from
-    first principles: the hull vertices (tests/golden/mushr_mesh.json) are posed in numpy, the triangle under each is
-    found in the explicit mesh, and the distances are compared with the `pos` of the exported contact rows."""
-    import json
-    import os
-    from conftest import GOLDEN
-    hull = np.array(json.load(open(os.path.join(GOLDEN, "mushr_mesh.json")))["chassis"]["hull"])
-    wall, svg = walls["track"]
-    t = otracks["track"]
-    tris = chunk_mesh(wall)
-    surf = tris[np.abs(np.cross(tris[:, 1] - tris[:, 0], tris[:, 2] - tris[:, 0])[:, 2]) > 1e-12]     # drop vertical side faces
-    model = oracle.Model()
-    path = t.centreline(svg)
-    q, v, w = model.reset(float(path[10, 0]), float(path[10, 1]), 0.4)
-    ctrl = np.array([3.0, 0.0])
-    checked = 0
-    for k in range(900):
-        M, qfs, J, D, R, aref, fl, ty = model.constraint_problem(t, q, v, ctrl)
-        pos = model.last_pos.copy()
-        _, info = model.step(t, q.copy(), v.copy(), w.copy(), ctrl)
-        if info[3] > 0:
-            con = np.nonzero(ty == 3)[0][4 * info[2]::4]                                                   # wall contacts follow the wheel contacts
-            qw, qx, qy, qz = q[3:7] / np.linalg.norm(q[3:7])
-            Rm = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qw * qz), 2 * (qx * qz + qw * qy)],
-                           [2 * (qx * qy + qw * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qw * qx)],
-                           [2 * (qx * qz - qw * qy), 2 * (qy * qz + qw * qx), 1 - 2 * (qx * qx + qy * qy)]])
-            dists = []
-            for hv in hull:
-                p = q[:3] + Rm @ hv
-                # the surface triangle whose xy projection contains p (barycentric test), plane height and normal there
-                a, b, c = surf[:, 0], surf[:, 1], surf[:, 2]
-                den = (b[:, 1] - c[:, 1]) * (a[:, 0] - c[:, 0]) + (c[:, 0] - b[:, 0]) * (a[:, 1] - c[:, 1])
-                l1 = ((b[:, 1] - c[:, 1]) * (p[0] - c[:, 0]) + (c[:, 0] - b[:, 0]) * (p[1] - c[:, 1])) / den
-                l2 = ((c[:, 1] - a[:, 1]) * (p[0] - c[:, 0]) + (a[:, 0] - c[:, 0]) * (p[1] - c[:, 1])) / den
-                inside = np.nonzero((l1 >= -1e-12) & (l2 >= -1e-12) & (l1 + l2 <= 1 + 1e-12))[0]
-                for tri in inside[:1]:
-                    nrm = np.cross(b[tri] - a[tri], c[tri] - a[tri]); nrm = nrm / np.linalg.norm(nrm) * np.sign(nrm[2])
-                    h = l1[tri] * a[tri, 2] + l2[tri] * b[tri, 2] + (1 - l1[tri] - l2[tri]) * c[tri, 2]
-                    d = (p[2] - h) * nrm[2]
-                    if d < 0:
-                        dists.append(d)
-            assert len(dists) >= len(con), (k, len(dists), len(con))
-            for i, row in enumerate(con):                             # contacts are generated in hull-vertex order
-                assert min(abs(pos[row] - d) for d in dists) < 1e-9, (k, i, pos[row], dists)
-                checked += 1
-        model.step(t, q, v, w, ctrl)
-        if checked >= 25:
-            break
-    assert checked >= 10
+# (the wall / ground contact set is checked against this explicit mesh in tests/test_contacts_cpu.py)

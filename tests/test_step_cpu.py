@@ -35,7 +35,7 @@ def host_quad_kernel():
     """The quad-per-car kernel source compiled for the host: four OS threads play the four lanes of a quad."""
     src = os.path.join(ROOT, "tests", "host_harness", "step_quad_host.cpp")
     out = os.path.join(ROOT, "tests", "host_harness", "libstep_quad_host.so")
-    deps = [src] + [os.path.join(ROOT, "ft_grandprix_b200", "csrc", f) for f in ("mushr_step_quad.cuh", "mushr_step.cuh", "mushr_consts.h", "mushr_mesh.h")]
+    deps = [src] + [os.path.join(ROOT, "ft_grandprix_b200", "csrc", f) for f in ("mushr_step_quad.cuh", "mushr_step.cuh", "mushr_consts.h", "mushr_mesh.h", "hfield_contact.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-pthread", "-o", out, src])
     lib = C.CDLL(out)
@@ -610,3 +610,93 @@ def test_quad_kernel_source_as_a_warp_of_quads_is_deadlock_free_and_bit_identica
     out = subprocess.run([sys.executable, script, ROOT, lib, "60"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.startswith("ok") and int(out.stdout.split()[1]) > 100          # suspensions really happened
+
+
+def _host_walls(host_quad_kernel, track_name="track"):
+    """The product's own geometry blob (ftgp_geom_blob, host memory) handed to the host build of the quad kernel."""
+    import ft_grandprix_b200 as ft
+    t = ft.Track.bundled(track_name)
+    lib = ft._lib.load()
+    arr = (C.c_void_p * 1)(t._ptr)
+    n = lib.ftgp_geom_blob(arr, None, 1, None, 0)
+    blob = np.zeros(n, dtype=np.uint32)
+    assert lib.ftgp_geom_blob(arr, None, 1, P(blob), n) == n
+    out4 = np.zeros(4, dtype=np.int32); size = np.zeros(2)
+    assert lib.ftgp_blob_track_view(P(blob), 0, P(out4), P(size)) == 0
+    host_quad_kernel.hq_set_walls.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+    base = blob.ctypes.data
+    host_quad_kernel.hq_set_walls(C.c_void_p(base + 4 * int(out4[0])), C.c_void_p(base + 4 * int(out4[1])), int(out4[2]), int(out4[3]),
+                                  float(size[0]), float(size[1]))
+    return blob, t                  # keep the blob alive while the harness points into it
+
+
+def test_quad_kernel_wall_and_ground_contacts_match_oracle(model, otracks, host_quad_kernel):
+    """The product's contact rules (csrc/hfield_contact.cuh + quad_prepare: wheel ellipsoids, chassis hull vertices and the
+    lidar cylinder against walls and ground) in the host build of the quad kernel vs the oracle's independent statement
+    (oracle/step.c car_contacts), single steps along trajectories that (a) run head-on into walls, (b) slide sideways into
+    them so that the wheels touch first, (c) land upside down."""
+    blob, t = _host_walls(host_quad_kernel)
+    try:
+        ot = otracks["track"]
+        path = t.path
+        rng = np.random.default_rng(11)
+        seen = {"wheel_wall": 0, "body_wall": 0, "ground": 0}
+        worst = 0.0
+        cases = []
+        for k in (10, 22, 37, 64, 81):
+            d = path[k + 1] - path[k]
+            yaw = float(np.arctan2(d[1], d[0]))
+            cases.append(("head-on", path[k], yaw + rng.uniform(0.5, 1.2) * rng.choice([-1, 1]), np.array([4.0, 0.0]), None, 0.0))
+            cases.append(("sideways", path[k], yaw, np.array([0.0, 0.0]), 2.0 * np.array([-np.sin(yaw), np.cos(yaw)]) * rng.choice([-1, 1]), 0.0))
+            cases.append(("flipped", path[k], yaw, np.array([1.0, 0.2]), None, np.pi + rng.normal(0, 0.2)))
+        for kind, xy, yaw, ctrl, vlat, roll in cases:
+            q, v, w = model.reset(float(xy[0]), float(xy[1]), yaw)
+            if roll:
+                q[2] = 0.12
+                q[3:7] = [np.cos(roll / 2) * np.cos(yaw / 2), np.sin(roll / 2) * np.cos(yaw / 2), np.sin(roll / 2) * np.sin(yaw / 2), np.cos(roll / 2) * np.sin(yaw / 2)]
+            for k in range(700):
+                if vlat is not None and k == 40:
+                    v[0:2] = vlat                                                # shove the settled car sideways
+                qh, vh, wh = q.copy(), v.copy(), w.copy()
+                info = np.zeros(4, dtype=np.int32)
+                host_quad_kernel.hq_step_ghost(P(qh), P(vh), P(wh), P(ctrl), 1, 1, P(info), 0, 0)
+                rc, oi = model.step(ot, q, v, w, ctrl)
+                assert info[1] == oi[2] and info[2] == oi[3], (kind, k, info, oi)    # wheel-ground and wall contact counts
+                err = max(np.abs(qh - q).max(), np.abs(vh - v).max() * 1e-2)
+                worst = max(worst, err)
+                assert err < 1e-9, (kind, k, err, oi)
+                seen["wheel_wall"] += int(oi[6]); seen["body_wall"] += int(oi[3] - oi[6]); seen["ground"] += int(oi[5])
+        assert seen["wheel_wall"] > 30 and seen["body_wall"] > 30 and seen["ground"] > 100, seen
+    finally:
+        host_quad_kernel.hq_set_walls(None, None, 0, 0, 1.0, 1.0)
+
+
+def test_quad_kernel_staged_solve_with_wall_contacts_is_bit_identical(model, otracks, host_quad_kernel):
+    """suspend / resume carries the wall contacts (body + wheel) through the record: staged == unstaged, bit for bit"""
+    blob, t = _host_walls(host_quad_kernel)
+    try:
+        host_quad_kernel.hq_step_staged.argtypes = [C.c_void_p] * 4 + [C.c_long, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        ot = otracks["track"]
+        ctrl = np.array([0.0, 0.0])
+        nsus = ncon = 0
+        for kp in (10, 22, 37, 64, 81):
+            for sgn in (-1.0, 1.0):
+                d = t.path[kp + 1] - t.path[kp]
+                yaw = float(np.arctan2(d[1], d[0]))
+                q, v, w = model.reset(float(t.path[kp, 0]), float(t.path[kp, 1]), yaw)
+                for k in range(350):
+                    if k == 40:
+                        v[0:2] = sgn * 2.5 * np.array([-np.sin(yaw), np.cos(yaw)])
+                    rc, oi = model.step(ot, q.copy(), v.copy(), w.copy(), ctrl)
+                    if oi[3] > 0:                                                # a wall contact this tick: staged vs unstaged
+                        qa, va, wa = q.copy(), v.copy(), w.copy(); qb, vb, wb = q.copy(), v.copy(), w.copy()
+                        ia = np.zeros(4, dtype=np.int32); ib = np.zeros(4, dtype=np.int32); ns = C.c_int(0)
+                        host_quad_kernel.hq_step_ghost(P(qa), P(va), P(wa), P(ctrl), 1, 1, P(ia), 0, 0)
+                        host_quad_kernel.hq_step_staged(P(qb), P(vb), P(wb), P(ctrl), 1, P(ib), 1, 1, C.byref(ns))
+                        assert np.array_equal(qa, qb) and np.array_equal(va, vb) and np.array_equal(wa, wb) and np.array_equal(ia, ib), (kp, k)
+                        assert ia[2] == oi[3]
+                        ncon += 1; nsus += ns.value
+                    model.step(ot, q, v, w, ctrl)
+        assert ncon > 20 and nsus > 10, (ncon, nsus)
+    finally:
+        host_quad_kernel.hq_set_walls(None, None, 0, 0, 1.0, 1.0)
