@@ -14,6 +14,7 @@ MAX_TRACKS, MAX_LAPTIMES = 4, 16
 LAP_FIELDS = ("offset", "completion", "laps", "start", "good_start", "finished", "ntimes",
               "off_track", "rank", "delta", "offtrack_ticks", "contact_ticks")
 DRIVER_NIDC, DRIVER_FAST, DRIVER_LOBOTOMY = 0, 1, 2
+OPT_NAIVE_FLATTEN = 1
 
 class FtgpError(RuntimeError):
     pass
@@ -25,7 +26,7 @@ class TickArgs(C.Structure):
                 ("lap", C.c_void_p), ("times", C.c_void_p), ("winners", C.c_void_p), ("status", C.c_void_p),
                 ("ncars", C.c_int64),
                 ("cars_per_world", C.c_int32), ("default_driver", C.c_int32),
-                ("lap_target", C.c_int32), ("steps", C.c_int32)]
+                ("lap_target", C.c_int32), ("steps", C.c_int32), ("options", C.c_int32), ("reserved", C.c_int32)]
 
 _vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
 # name -> (restype, argtypes); mirrors include/ftgp.h one to one
@@ -49,6 +50,7 @@ SIGNATURES = {
     "ftgp_reset": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "ftgp_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "ftgp_release_scratch": (_i, [_vp]),
+    "ftgp_naive_flatten": (_i, [_vp, _i64, _i64, _vp]),
     "ftgp_drivers": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp]),
     "ftgp_lap_update": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i, C.c_int32, C.c_int32, _vp]),
     "ftgp_tick": (_i, [C.POINTER(TickArgs), _i, _vp]),

@@ -36,6 +36,23 @@ __global__ void reset_kernel(double* __restrict__ qpos, double* __restrict__ qve
     if (ctrl) { ctrl[2 * i] = 0.0; ctrl[2 * i + 1] = 0.0; }
 }
 
+// ------------------------------------------------------------------ option naive_flatten (custom.py:981,1338-1339)
+// qpos[3:7] = euler_to_quaternion([quaternion_to_angle(*qpos[3:7]), 0, 0]) (custom.py:62-87): keep the yaw, drop pitch / roll
+__global__ void flatten_kernel(double* __restrict__ qpos, int64_t stride, int64_t ncars) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncars) return;
+    double* q = qpos + i * stride + 3;
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double yaw = atan2(2.0 * (w * z + x * y), 1.0 - 2.0 * (y * y + z * z));
+    q[0] = cos(yaw / 2); q[1] = 0.0; q[2] = 0.0; q[3] = sin(yaw / 2);
+}
+int launch_flatten(double* qpos, int64_t stride, int64_t ncars, cudaStream_t stream) {
+    flatten_kernel<<<(unsigned)((ncars + 127) / 128), 128, 0, stream>>>(qpos, stride, ncars);
+    count_launch();
+    FTGP_CUDA(cudaGetLastError());
+    return FTGP_OK;
+}
+
 // ------------------------------------------------------------------ drivers
 constexpr int NPROC = 68;             // 90 - 2 * int(90 / 8)          nidc.py:17-18
 constexpr int EIGHTH = 11;
@@ -229,6 +246,12 @@ extern "C" int ftgp_reset(double* qpos, double* qvel, double* warm, double* ctrl
     count_launch();
     FTGP_CUDA(cudaGetLastError());
     return FTGP_OK;
+}
+
+extern "C" int ftgp_naive_flatten(double* qpos, int64_t qpos_stride, int64_t ncars, void* stream) {
+    if (!qpos || ncars < 0 || qpos_stride < 7) { set_error("ftgp_naive_flatten: bad argument"); return FTGP_ERR_ARG; }
+    if (ncars == 0) return FTGP_OK;
+    return launch_flatten(qpos, qpos_stride, ncars, (cudaStream_t)stream);
 }
 
 extern "C" int ftgp_drivers(const float* ranges, const int32_t* kind, int default_kind, const int32_t* lap,

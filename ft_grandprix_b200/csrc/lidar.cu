@@ -22,10 +22,13 @@
 //   * a warp-level min-reduction yields the per-car closest obstacle (min_range).
 #include <math.h>
 #include "common.h"
+#include "mushr_mesh.h"
 
 namespace ftgp {
 
 __constant__ double c_beam_sc[FTGP_NBEAMS][2];   // (sin b, cos b), b = radians(4j - 90)
+// the chassis mesh's own 33 triangles in the car frame (mushr.em.xml:38,119): what mj_ray tests on another car
+__constant__ double c_chassis_tri[MUSHR_CHASSIS_NTRI][9];
 static bool g_beam_ready[16] = {false};
 
 constexpr float HF_RANGE = 0.3f;      // hfield elevation range: border_height + affordance (mushr.em.xml:16,22,55)
@@ -192,6 +195,61 @@ __device__ __forceinline__ double ray_cylinder(double px, double py, double pz, 
     return best;
 }
 
+// other car's wheel ellipsoid (mushr.em.xml:69), ray in the geom frame: quadratic in the scaled space (mju_rayGeom)
+__device__ __forceinline__ double ray_ellipsoid(double px, double py, double pz, double vx, double vy, double vz,
+                                                double sx, double sy, double sz) {
+    const double ix = 1.0 / (sx * sx), iy = 1.0 / (sy * sy), iz = 1.0 / (sz * sz);
+    const double a = ix * vx * vx + iy * vy * vy + iz * vz * vz, b = ix * px * vx + iy * py * vy + iz * pz * vz,
+                 c = ix * px * px + iy * py * py + iz * pz * pz - 1.0;
+    if (a < 1e-15) return -1.0;
+    double det = b * b - a * c;
+    if (det < 1e-15) return -1.0;
+    det = sqrt(det);
+    const double x0 = (-b - det) / a, x1 = (-b + det) / a;
+    return x0 >= 0 ? x0 : (x1 >= 0 ? x1 : -1.0);
+}
+// one triangle of the other car's chassis mesh (mj_rayMesh), ray in that car's frame
+__device__ __forceinline__ double ray_triangle(const double* t, double px, double py, double pz, double vx, double vy, double vz) {
+    const double e1x = t[3] - t[0], e1y = t[4] - t[1], e1z = t[5] - t[2], e2x = t[6] - t[0], e2y = t[7] - t[1], e2z = t[8] - t[2];
+    const double hx = vy * e2z - vz * e2y, hy = vz * e2x - vx * e2z, hz = vx * e2y - vy * e2x;
+    const double det = e1x * hx + e1y * hy + e1z * hz;
+    if (fabs(det) < 1e-300) return -1.0;
+    const double tx = px - t[0], ty = py - t[1], tz = pz - t[2];
+    const double u = (tx * hx + ty * hy + tz * hz) / det;
+    if (u < 0 || u > 1) return -1.0;
+    const double qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+    const double v = (vx * qx + vy * qy + vz * qz) / det;
+    if (v < 0 || u + v > 1) return -1.0;
+    const double x = (e2x * qx + e2y * qy + e2z * qz) / det;
+    return x >= 0 ? x : -1.0;
+}
+// Nearest lidar-visible geom of ANOTHER car along the ray (p, v given in that car's frame): lidar cylinder, chassis mesh
+// triangles, four wheel ellipsoids (their pose follows the suspension slide and, at the front, the steering hinge; the
+// ellipsoid is a body of revolution about the axle, so the throttle angle drops out).  jq: susp[4], steer[2].
+// Everything of the car lies inside the sphere |x - (0, 0, 0.02)| < 0.145, which culls almost every (ray, car) pair.
+__device__ __noinline__ double ray_other_car(double px, double py, double pz, double vx, double vy, double vz, const double* jq) {
+    {
+        const double cz = pz - 0.02, b = px * vx + py * vy + cz * vz, c = px * px + py * py + cz * cz - 0.145 * 0.145;
+        if (c > 0 && (b > 0 || b * b - c < 0)) return -1.0;
+    }
+    const double rx = -0.0525, rz = 0.065;
+    double best = ray_cylinder(px - rx, py, pz - (rz - 0.015 / 2), vx, vy, vz, 0.03, 0.015);
+    for (int f = 0; f < MUSHR_CHASSIS_NTRI; f++) {
+        const double x = ray_triangle(c_chassis_tri[f], px, py, pz, vx, vy, vz);
+        if (x >= 0 && (best < 0 || x < best)) best = x;
+    }
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const double cx = w < 2 ? 0.06925 : -0.079, cy = (w & 1) ? -0.0575 : 0.0575, cz = 0.0244 + jq[w];
+        double sn = 0.0, cs = 1.0;
+        if (w < 2) sincos(jq[4 + w], &sn, &cs);
+        const double qx = px - cx, qy = py - cy, qz = pz - cz;
+        const double x = ray_ellipsoid(cs * qx + sn * qy, -sn * qx + cs * qy, qz, cs * vx + sn * vy, -sn * vx + cs * vy, vz, 0.03, 0.01, 0.03);
+        if (x >= 0 && (best < 0 || x < best)) best = x;
+    }
+    return best;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Traversal as a per-lane state machine.  A warp owns a batch of cars (whole worlds) and a pool of
 // 90 x ncars rays; every lane runs IDLE -> CHUNK (one Amanatides-Woo step over the 0.5 m chunk grid)
@@ -203,7 +261,7 @@ __device__ __forceinline__ double ray_cylinder(double px, double py, double pz, 
 // (the first version traced beams l, l+32, l+64 per lane with nested loops: 6.5 of 32 lanes active).
 enum { ST_IDLE = 0, ST_CHUNK = 1, ST_SWEEP = 2, ST_ADV = 3 };
 constexpr int BATCH = 8;              // max cars per warp batch (a batch holds whole worlds of 1..8 cars)
-constexpr int FRAME_DOUBLES = 12;     // p[3], R[9]
+constexpr int FRAME_DOUBLES = 18;     // p[3], R[9], suspension travel [4], front steering angle [2]
 
 struct Lane {
     // ray
@@ -229,6 +287,8 @@ __device__ __forceinline__ void finish(Lane& L, float val, float* __restrict__ r
     L.state = ST_IDLE;
 }
 
+// MULTI: worlds of 2..8 cars (the other cars' geoms are ray targets); single-car worlds compile without that code
+template <bool MULTI>
 __global__ void __launch_bounds__(512)
 lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* __restrict__ qpos,
              int64_t stride, const int32_t* __restrict__ track_id, const uint8_t* __restrict__ visible,
@@ -271,6 +331,10 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
             F[3] = 1 - 2 * (y * y + z * z); F[4] = 2 * (x * y - w * z); F[5] = 2 * (x * z + w * y);
             F[6] = 2 * (x * y + w * z); F[7] = 1 - 2 * (x * x + z * z); F[8] = 2 * (y * z - w * x);
             F[9] = 2 * (x * z - w * y); F[10] = 2 * (y * z + w * x); F[11] = 1 - 2 * (x * x + y * y);
+            // wheel poses for the other cars' rays (full state rows only; a bare pose leaves the joints at qpos0)
+            const bool full = MULTI && stride >= FTGP_NQ;
+            F[12] = full ? q[8] : 0.0; F[13] = full ? q[15] : 0.0; F[14] = full ? q[22] : 0.0; F[15] = full ? q[28] : 0.0;
+            F[16] = full ? q[9] : 0.0; F[17] = full ? q[16] : 0.0;
             int tid = track_id ? track_id[base_car + lane] : 0;
             if (tid < 0 || tid >= gh->ntracks) tid = 0;
             // bit 8: other cars do not see this car (shadowed, custom.py:1455-1464); bit 9: its own rangefinders are
@@ -317,20 +381,20 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                         L.dgx = (float)(dwx * inv_sx); L.dgy = (float)(dwy * inv_sy);
                         L.lz = (float)(owz + 0.1); L.dz = (float)dwz;
                         float best = BIG;
-                        // other cars of the same world: their lidar cylinder (mushr.em.xml:108)
-                        if (cpw > 1) {
+                        // other cars of the same world: lidar cylinder, chassis mesh, wheels (mushr.em.xml:108,119,69)
+                        if (MULTI) {
                             const int w0 = (car / cpw) * cpw;
                             for (int oc = w0; oc < w0 + cpw && oc < nb; oc++) {
                                 if (oc == car || (meta[oc] & 0x100)) continue;      // bodyexclude / invisible
                                 const double* Q = frames + oc * FRAME_DOUBLES;
                                 const double ex = owx - Q[0], ey = owy - Q[1], ez = owz - Q[2];
-                                const double px = Q[3] * ex + Q[6] * ey + Q[9] * ez - rx;
+                                const double px = Q[3] * ex + Q[6] * ey + Q[9] * ez;
                                 const double py = Q[4] * ex + Q[7] * ey + Q[10] * ez;
-                                const double pz = Q[5] * ex + Q[8] * ey + Q[11] * ez - (rz - 0.015 / 2);
+                                const double pz = Q[5] * ex + Q[8] * ey + Q[11] * ez;
                                 const double vx = Q[3] * dwx + Q[6] * dwy + Q[9] * dwz;
                                 const double vy = Q[4] * dwx + Q[7] * dwy + Q[10] * dwz;
                                 const double vz = Q[5] * dwx + Q[8] * dwy + Q[11] * dwz;
-                                const double sc = ray_cylinder(px, py, pz, vx, vy, vz, 0.03, 0.015);
+                                const double sc = ray_other_car(px, py, pz, vx, vy, vz, Q + 12);
                                 if (sc >= 0 && (float)sc < best) best = (float)sc;
                             }
                         }
@@ -552,6 +616,8 @@ static int ensure_beams(int device) {
         h[j][0] = sin(b); h[j][1] = cos(b);
     }
     FTGP_CUDA(cudaMemcpyToSymbol(c_beam_sc, h, sizeof h));
+    const double tri[MUSHR_CHASSIS_NTRI][9] = MUSHR_CHASSIS_TRI;
+    FTGP_CUDA(cudaMemcpyToSymbol(c_chassis_tri, tri, sizeof tri));
     if (device >= 0 && device < 16) g_beam_ready[device] = true;
     return FTGP_OK;
 }
@@ -570,7 +636,8 @@ int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const i
     int dev = g->device;
     if (dev < 16 && sm_count[dev] == 0) {
         FTGP_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-        FTGP_CUDA(cudaFuncSetAttribute(lidar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FTGP_CUDA(cudaFuncSetAttribute(lidar_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FTGP_CUDA(cudaFuncSetAttribute(lidar_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     int rc = ensure_beams(dev); if (rc) return rc;
     int per_sm = (int)std::min<size_t>(4, (227 * 1024) / (smem + 1024));
@@ -583,8 +650,12 @@ int launch_lidar(const ftgp_geom* g, const double* qpos, int64_t stride, const i
     int64_t need = ((ncars + bsz - 1) / bsz + (threads / 32) - 1) / (threads / 32);
     int grid = (int)std::min<int64_t>(need, (int64_t)nsm * per_sm);
     if (grid < 1) return FTGP_OK;
-    lidar_kernel<<<grid, threads, smem, stream>>>(g->d_blob, gh.lidar_words, qpos, stride, track_id, visible, lap,
-                                                  ncars, cpw, bsz, stage, ranges, min_range);
+    if (cpw > 1)
+        lidar_kernel<true><<<grid, threads, smem, stream>>>(g->d_blob, gh.lidar_words, qpos, stride, track_id, visible, lap,
+                                                            ncars, cpw, bsz, stage, ranges, min_range);
+    else
+        lidar_kernel<false><<<grid, threads, smem, stream>>>(g->d_blob, gh.lidar_words, qpos, stride, track_id, visible, lap,
+                                                             ncars, cpw, bsz, stage, ranges, min_range);
     count_launch();
     FTGP_CUDA(cudaGetLastError());
     return FTGP_OK;

@@ -287,9 +287,13 @@ int launch_lap(const ftgp_geom* g, const double* qpos, int64_t stride, const int
                int32_t* times, int32_t* winners, const int32_t* status, int64_t ncars, int cpw, int32_t steps,
                int32_t lap_target, cudaStream_t stream, const int32_t* steps_dev);
 
+int launch_flatten(double* qpos, int64_t stride, int64_t ncars, cudaStream_t stream);
+
 // ---- one tick = custom.py:1337-1426 for the whole fleet, in the reference's order
 static int issue_tick(const ftgp_tick_args* a, int32_t steps, int32_t* steps_dev, cudaStream_t s) {
     int rc;
+    // custom.py:1338-1339 option naive_flatten
+    if ((a->options & FTGP_OPT_NAIVE_FLATTEN) && (rc = launch_flatten(a->qpos, FTGP_NQ, a->ncars, s))) return rc;
     // custom.py:1340-1372 progress + lap logic from the current pose
     if ((rc = launch_lap(a->geom, a->qpos, FTGP_NQ, a->track_id, a->lap, a->times, a->winners, a->status, a->ncars,
                          a->cars_per_world, steps, a->lap_target, s, steps_dev))) return rc;
@@ -326,7 +330,7 @@ static bool same_key(const ftgp_tick_args& x, const ftgp_tick_args& y) {
     return x.geom == y.geom && x.qpos == y.qpos && x.qvel == y.qvel && x.warm == y.warm && x.ctrl == y.ctrl && x.ranges == y.ranges &&
            x.track_id == y.track_id && x.driver_kind == y.driver_kind && x.lap == y.lap && x.times == y.times &&
            x.winners == y.winners && x.status == y.status && x.ncars == y.ncars && x.cars_per_world == y.cars_per_world &&
-           x.default_driver == y.default_driver && x.lap_target == y.lap_target;
+           x.default_driver == y.default_driver && x.lap_target == y.lap_target && x.options == y.options;
 }
 static void drop_graph(TickGraph& g) {
     if (g.exec) cudaGraphExecDestroy(g.exec);

@@ -39,7 +39,8 @@ def _ptr(t):
 
 class Fleet:
     def __init__(self, tracks, ncars, cars_per_world=1, device=0, track_id=None, driver="nidc",
-                 lap_target=10):
+                 lap_target=10, naive_flatten=False):
+        """lap_target, naive_flatten: the path-relevant options of the reference (custom.py:961,981)."""
         if not torch.cuda.is_available():
             raise _lib.FtgpError("Fleet needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -50,6 +51,7 @@ class Fleet:
             raise ValueError("ncars must be a multiple of cars_per_world")
         self.nworlds = self.ncars // self.cars_per_world
         self.lap_target = int(lap_target)
+        self.naive_flatten = bool(naive_flatten)
         self.default_driver = DRIVER_KINDS[driver] if isinstance(driver, str) else int(driver)
         dev, n = self.device, self.ncars
         with torch.cuda.device(dev):
@@ -176,8 +178,15 @@ class Fleet:
                                       _ptr(self.status), self._s), "ftgp_step")
         self.steps += int(nsteps)
 
+    def flatten(self):
+        """Option naive_flatten (custom.py:1338-1339): keep the chassis' yaw, zero its pitch and roll."""
+        _lib.check(self.lib.ftgp_naive_flatten(_ptr(self.qpos), NQ, self.ncars, self._s), "ftgp_naive_flatten")
+
     def lap_update(self):
-        """Progress / lap state machine (custom.py:1340-1372)."""
+        """Progress / lap state machine (custom.py:1340-1372); with the option naive_flatten the flattening that precedes it
+        in the reference's loop body (custom.py:1338-1339)."""
+        if self.naive_flatten:
+            self.flatten()
         _lib.check(self.lib.ftgp_lap_update(self.geom._ptr, _ptr(self.qpos), NQ, _ptr(self.track_id),
                                             _ptr(self.lap), _ptr(self.times), _ptr(self.winners),
                                             _ptr(self.status), self.ncars, self.cars_per_world, self.steps,
@@ -196,6 +205,7 @@ class Fleet:
         a.ncars = self.ncars
         a.cars_per_world, a.default_driver = self.cars_per_world, self.default_driver
         a.lap_target, a.steps = self.lap_target, self.steps
+        a.options = _lib.OPT_NAIVE_FLATTEN if self.naive_flatten else 0
         return a
 
     def tick(self, nticks=1):

@@ -166,7 +166,11 @@ typedef struct {
     int32_t *lap, *times, *winners, *status;/* device */
     int64_t ncars;
     int32_t cars_per_world, default_driver, lap_target, steps;
+    int32_t options, reserved;              /* FTGP_OPT_* bits: the path-relevant options of custom.py:946-989 */
 } ftgp_tick_args;
+enum { FTGP_OPT_NAIVE_FLATTEN = 1 };        /* custom.py:981,1338-1339: every tick, keep the chassis' yaw and zero its pitch / roll */
+/* Option naive_flatten on its own (custom.py:1338-1339): qpos[3:7] <- quaternion of (yaw, 0, 0). */
+int ftgp_naive_flatten(double* qpos, int64_t qpos_stride, int64_t ncars, void* stream);
 /* One iteration of physics_thread (custom.py:1337-1426) for the whole fleet:
  * lap update -> built-in driver on last tick's ranges -> ctrl -> [rangefinders from the
  * pre-step pose, mj_step] ; the same one-tick sensor lag as the reference.

@@ -71,6 +71,10 @@ double fto_ray(const fto_track* t, const double* pnt, const double* vec);
  * above the ray plane in level driving; wheels/chassis are tested too. */
 void fto_lidar_scan_world(const fto_track* t, const double* qpos_all, int ncars, int self,
                           const uint8_t* visible, double* out);
+/* the same with full state rows: qpos_all [ncars][stride]; stride >= 34: the other cars' wheel poses follow their
+ * suspension / steering joints; the other cars' lidar cylinder, chassis mesh triangles and wheel ellipsoids are targets */
+void fto_lidar_scan_world_stride(const fto_track* t, const double* qpos_all, int stride, int ncars, int self,
+                                 const uint8_t* visible, double* out);
 
 /* ---------------------------------------------------------------- drivers */
 /* a5: ft_grandprix/nidc.py:116-131 (kind 0), ft_grandprix/fast.py:118-139 (kind 1),

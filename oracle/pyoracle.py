@@ -121,12 +121,16 @@ class Track:
         return out
 
     def scan_world(self, poses, visible=None):
-        poses = np.ascontiguousarray(poses, dtype=np.float64).reshape(-1, 7)
-        n = len(poses)
+        """Rangefinders of every car of ONE world: poses [n, 7] (joints at qpos0) or full state rows [n, 34]."""
+        poses = np.ascontiguousarray(poses, dtype=np.float64)
+        poses = poses.reshape(-1, 34) if poses.shape[-1] == 34 else poses.reshape(-1, 7)
+        n, stride = poses.shape
         vis = None if visible is None else np.ascontiguousarray(visible, dtype=np.uint8)
         out = np.zeros((n, 90))
+        L = lib()
+        L.fto_lidar_scan_world_stride.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         for i in range(n):
-            lib().fto_lidar_scan_world(self.ptr, _p(poses), n, i, _p(vis) if vis is not None else None, _p(out[i]))
+            L.fto_lidar_scan_world_stride(self.ptr, _p(poses), stride, n, i, _p(vis) if vis is not None else None, _p(out[i]))
         return out
 
     def ray(self, pnt, vec):

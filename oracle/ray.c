@@ -10,6 +10,7 @@
  * wheel ellipsoids (mushr.em.xml:69,132).
  */
 #include "oracle_internal.h"
+#include "mushr_mesh.h"
 #include <math.h>
 #include <string.h>
 
@@ -233,9 +234,50 @@ static double ray_quadric_cyl(const double* lp, const double* lv, double r, doub
     return best;
 }
 
-void fto_lidar_scan_world(const fto_track* t, const double* qpos_all, int ncars, int self,
-                          const uint8_t* visible, double* out) {
-    const double* pose = qpos_all + (size_t)self * 7;
+/* ellipsoid with semi-axes size[], ray in the geom frame (mju_rayGeom mjGEOM_ELLIPSOID): quadratic in scaled space */
+static double ray_ellipsoid(const double* lp, const double* lv, const double* size) {
+    double a = 0, b = 0, c = -1;
+    for (int k = 0; k < 3; k++) {
+        const double s = 1.0 / (size[k] * size[k]);
+        a += s * lv[k] * lv[k]; b += s * lp[k] * lv[k]; c += s * lp[k] * lp[k];
+    }
+    if (a < FTO_MINVAL) return -1;
+    double det = b * b - a * c;
+    if (det < FTO_MINVAL) return -1;
+    det = sqrt(det);
+    const double x0 = (-b - det) / a, x1 = (-b + det) / a;
+    return x0 >= 0 ? x0 : (x1 >= 0 ? x1 : -1);
+}
+
+/* one mesh triangle (mj_rayMesh -> ray_triangle): nearest non-negative hit or -1 */
+static double ray_tri(const double* v0, const double* v1, const double* v2, const double* p, const double* d) {
+    const double e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]}, e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+    const double h[3] = {d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0]};
+    const double det = e1[0] * h[0] + e1[1] * h[1] + e1[2] * h[2];
+    if (fabs(det) < 1e-300) return -1;
+    const double tv[3] = {p[0] - v0[0], p[1] - v0[1], p[2] - v0[2]};
+    const double u = (tv[0] * h[0] + tv[1] * h[1] + tv[2] * h[2]) / det;
+    if (u < 0 || u > 1) return -1;
+    const double q[3] = {tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2], tv[0] * e1[1] - tv[1] * e1[0]};
+    const double v = (d[0] * q[0] + d[1] * q[1] + d[2] * q[2]) / det;
+    if (v < 0 || u + v > 1) return -1;
+    const double x = (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]) / det;
+    return x >= 0 ? x : -1;
+}
+
+/* Rangefinders of car `self` in an N-car world: mj_ray with bodyexclude = own root body against the walls, the ground and
+ * every lidar-visible geom of the OTHER cars: the lidar cylinder (mushr.em.xml:108), the chassis mesh's own
+ * triangles (:119) and the four wheel ellipsoids (:69; semi-axes 0.03, 0.01, 0.03 -- invariant under the throttle
+ * rotation about y, so only suspension travel and steering angle matter).  qpos_all: [ncars][stride]; with stride >= 34
+ * the wheel poses come from the joint values, with a bare pose (stride 7) the joints sit at qpos0.  (The car's OWN wheels
+ * are not excluded by mj_ray but lie below every beam, A.1; they are not tested.) */
+void fto_lidar_scan_world_stride(const fto_track* t, const double* qpos_all, int stride, int ncars, int self,
+                                 const uint8_t* visible, double* out) {
+    static const double tri[MUSHR_CHASSIS_NTRI][9] = MUSHR_CHASSIS_TRI;
+    const double wsize[3] = {0.03, 0.01, 0.03};
+    const int qsusp[4] = {8, 15, 22, 28};
+    const double wpos[4][3] = {{0.06925, 0.0575, 0.0244}, {0.06925, -0.0575, 0.0244}, {-0.079, 0.0575, 0.0244}, {-0.079, -0.0575, 0.0244}};
+    const double* pose = qpos_all + (size_t)self * stride;
     for (int j = 0; j < FTO_NBEAMS; j++) {
         double o[3], d[3], ow[3], dw[3];
         beam_local(j, o, d);
@@ -245,17 +287,36 @@ void fto_lidar_scan_world(const fto_track* t, const double* qpos_all, int ncars,
         double best = fto_ray(t, ow, dw);
         for (int c = 0; c < ncars; c++) {
             if (c == self || (visible && !visible[c])) continue;
-            /* other car's lidar cylinder: mushr.em.xml:108, pos (rx, 0, rz - lh/2), r 0.03, hh 0.015 */
-            const double* pc = qpos_all + (size_t)c * 7;
+            const double* pc = qpos_all + (size_t)c * stride;
             double qi[4] = {pc[3], -pc[4], -pc[5], -pc[6]};
             double rel[3] = {ow[0] - pc[0], ow[1] - pc[1], ow[2] - pc[2]}, lp[3], lv[3];
-            quat_rot(qi, rel, lp); quat_rot(qi, dw, lv);
-            lp[0] -= -0.0525; lp[2] -= 0.065 - 0.015 / 2;
-            double x = ray_quadric_cyl(lp, lv, 0.03, 0.015);
-            if (x >= 0 && (best < 0 || x < best)) best = x;
+            quat_rot(qi, rel, lp); quat_rot(qi, dw, lv);                  /* the ray in the other car's frame */
+            {                                                             /* lidar cylinder: pos (rx, 0, rz - lh/2), r 0.03, hh 0.015 */
+                double cp[3] = {lp[0] + 0.0525, lp[1], lp[2] - (0.065 - 0.015 / 2)};
+                double x = ray_quadric_cyl(cp, lv, 0.03, 0.015);
+                if (x >= 0 && (best < 0 || x < best)) best = x;
+            }
+            for (int f = 0; f < MUSHR_CHASSIS_NTRI; f++) {                /* chassis mesh */
+                double x = ray_tri(tri[f], tri[f] + 3, tri[f] + 6, lp, lv);
+                if (x >= 0 && (best < 0 || x < best)) best = x;
+            }
+            for (int w = 0; w < 4; w++) {                                 /* wheel ellipsoids */
+                const double susp = stride >= FTO_NQ ? pc[qsusp[w]] : 0.0, steer = (stride >= FTO_NQ && w < 2) ? pc[qsusp[w] + 1] : 0.0;
+                const double cx = wpos[w][0], cy = wpos[w][1], cz = wpos[w][2] + susp, cs = cos(steer), sn = sin(steer);
+                const double rp[3] = {lp[0] - cx, lp[1] - cy, lp[2] - cz};
+                const double wp[3] = {cs * rp[0] + sn * rp[1], -sn * rp[0] + cs * rp[1], rp[2]};      /* Rz(steer)^T */
+                const double wv[3] = {cs * lv[0] + sn * lv[1], -sn * lv[0] + cs * lv[1], lv[2]};
+                double x = ray_ellipsoid(wp, wv, wsize);
+                if (x >= 0 && (best < 0 || x < best)) best = x;
+            }
         }
         out[j] = best;
     }
+}
+
+void fto_lidar_scan_world(const fto_track* t, const double* qpos_all, int ncars, int self,
+                          const uint8_t* visible, double* out) {
+    fto_lidar_scan_world_stride(t, qpos_all, 7, ncars, self, visible, out);
 }
 
 void fto_lidar_scan(const fto_track* t, const double* pose, double* out) {

@@ -91,6 +91,40 @@ def test_lidar_multi_car_world(ft, otracks):
     assert (np.abs(alone - want) > 1e-3).sum() > 50       # the other cars really are seen
 
 
+def test_lidar_multi_car_world_pitched_cars_see_chassis_and_wheels(ft, otracks):
+    """f1: mj_ray also ends on the other cars' chassis mesh and wheel ellipsoids (suspension travel and steering angle from
+    the state rows); on level ground those lie below the beams, so the cars here are pitched, rolled and lifted."""
+    t = ft.Track.bundled("track")
+    nworlds, cpw = 48, 8
+    n = nworlds * cpw
+    rng = np.random.default_rng(12)
+    q = np.zeros((n, 34)); q[:, [11, 18, 24, 30]] = 1.0
+    for w in range(nworlds):
+        cx, cy = t.path[rng.integers(0, 100)]
+        for c in range(cpw):
+            yaw, pitch, roll = rng.uniform(-3, 3), rng.normal(0, 0.2), rng.normal(0, 0.2)
+            a, b, cc_, d, e, f = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
+            i = w * cpw + c
+            q[i, :3] = [cx + rng.normal(0, 0.22), cy + rng.normal(0, 0.22), 0.02 + rng.uniform(0, 0.06)]
+            q[i, 3:7] = [e * cc_ * a + f * d * b, f * cc_ * a - e * d * b, e * d * a + f * cc_ * b, e * cc_ * b - f * d * a]
+            q[i, [8, 15, 22, 28]] = rng.uniform(-0.03, 0, 4); q[i, [9, 16]] = rng.uniform(-0.6, 0.6, 2)
+            q[i, [10, 17, 23, 29]] = rng.uniform(-3, 3, 4)
+    vis = (rng.random(n) > 0.15).astype(np.uint8)
+    fleet = ft.Fleet(t, n, cars_per_world=cpw)
+    fleet.qpos.copy_(torch.from_numpy(q)); v = torch.from_numpy(vis).to(fleet.device)
+    torch.cuda.synchronize()
+    got = fleet.lidar(visible=v); fleet.sync()
+    got = got.cpu().numpy().astype(np.float64)
+    ot = otracks["track"]
+    want = np.concatenate([ot.scan_world(q[w * cpw:(w + 1) * cpw], vis[w * cpw:(w + 1) * cpw]) for w in range(nworlds)])
+    miss = (got < 0) != (want < 0)
+    bad = np.abs(got - want) > 1e-4
+    assert miss.sum() == 0 and bad.mean() < 2e-4, (miss.sum(), bad.sum(), np.abs(got - want).max())
+    # the new targets matter: compare with a scan that only knows the other cars' lidar cylinders' nominal neighbours
+    alone = ot.scan(q[:, :7])
+    assert (np.abs(alone - want) > 1e-3).sum() > 300
+
+
 def test_lidar_host_entry_and_ragged(ft, otracks):
     """C ABI with host buffers, ncars = 0 / 1 / non-multiple of the warp count."""
     import ctypes as C

@@ -514,3 +514,28 @@ def test_graph_replayed_tick_is_bit_identical_to_the_eager_tick(ft, n):
     a.sync(); b.sync()
     a.lib.ftgp_tick_use_graphs(prev)
     assert torch.equal(a.qpos, b.qpos) and torch.equal(a.lap, b.lap)
+
+
+def test_option_naive_flatten(ft):
+    """custom.py:1338-1339: qpos[3:7] = euler_to_quaternion([yaw, 0, 0]) at the top of every loop iteration; fused tick ==
+    separate calls; the quaternion handed to the step has no pitch / roll."""
+    t = ft.Track.bundled("track")
+    n = 64
+    from conftest import random_poses
+    poses = random_poses(t.path, n, seed=5, level=False)
+    a = ft.Fleet(t, n, naive_flatten=True); b = ft.Fleet(t, n, naive_flatten=True)
+    for f in (a, b):
+        f.reset(poses[:, :2], np.zeros(n))
+        f.qpos[:, 2:7] = torch.from_numpy(poses[:, 2:7]).to(f.device)
+    torch.cuda.synchronize()
+    q = poses[:, 3:7]
+    yaw = np.arctan2(2 * (q[:, 0] * q[:, 3] + q[:, 1] * q[:, 2]), 1 - 2 * (q[:, 2] ** 2 + q[:, 3] ** 2))     # custom.py:62-76
+    a.flatten(); a.sync()
+    got = a.qpos[:, 3:7].cpu().numpy()
+    np.testing.assert_allclose(got, np.stack([np.cos(yaw / 2), 0 * yaw, 0 * yaw, np.sin(yaw / 2)], 1), atol=1e-15)
+    b.flatten()
+    a.tick(20)
+    for _ in range(20):
+        b.lap_update(); b.drive(); b.lidar(); b.step(1)
+    a.sync(); b.sync()
+    assert torch.equal(a.qpos, b.qpos) and torch.equal(a.ranges, b.ranges)

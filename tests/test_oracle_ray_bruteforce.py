@@ -155,3 +155,105 @@ def test_oracle_world_scan_matches_bruteforce_with_other_cars(otracks, walls):
 
 
 # (the wall / ground contact set is checked against this explicit mesh in tests/test_contacts_cpu.py)
+
+
+def _rotm(q):
+    w, x, y, z = q / np.linalg.norm(q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _first_root(F, smax=3.0, n=6000):
+    """first s in [0, smax] where the implicit function F(s) crosses zero (dense sampling + bisection), or inf"""
+    s = np.linspace(0.0, smax, n)
+    f = F(s)
+    k = np.nonzero(np.sign(f[:-1]) != np.sign(f[1:]))[0]
+    if not len(k):
+        return np.inf
+    lo, hi = s[k[0]], s[k[0] + 1]
+    flo = F(np.array([lo]))[0]
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        fm = F(np.array([mid]))[0]
+        if (fm < 0) == (flo < 0):
+            lo, flo = mid, fm
+        else:
+            hi = mid
+    return 0.5 * (lo + hi)
+
+
+def test_oracle_world_scan_sees_wheels_and_chassis_of_pitched_cars(otracks, walls):
+    """f1 / mj_ray with geomgroup NULL: a ray also ends on another car's chassis mesh (its own 33 triangles,
+    mushr.em.xml:119) and wheel ellipsoids (:69), not only on its lidar cylinder.  On level ground those lie below the
+    beams, so the observer cars here are pitched / rolled / lifted.  Independent statement: the chassis triangles of
+    tests/golden (assets/meshes.npz, scaled and placed in numpy) go through the brute-force triangle caster; each
+    ellipsoid is the zero set of |S^-1 R^T (p - c)|^2 - 1, whose first crossing along the ray is bracketed by dense
+    sampling and bisected (no closed-form quadratic, no shared code)."""
+    import os
+    from conftest import ROOT
+    wall, svg = walls["track"]
+    t = otracks["track"]
+    path = t.centreline(svg)
+    tris = chunk_mesh(wall)
+    base = np.load(os.path.join(ROOT, "ft_grandprix_b200", "assets", "meshes.npz"))["simple_base_nano__tri"].astype(np.float64)
+    chassis_local = base * 0.5 + np.array([0, 0, 0.5 * 0.094655])                      # mushr.em.xml:38,119
+    wpos = np.array([[0.06925, 0.0575, 0.0244], [0.06925, -0.0575, 0.0244], [-0.079, 0.0575, 0.0244], [-0.079, -0.0575, 0.0244]])
+    S = np.array([0.03, 0.01, 0.03])
+    rng = np.random.default_rng(8)
+    n = 5
+    q = np.zeros((n, 34))
+    q[:, [11, 18, 24, 30]] = 1.0
+    off = [(0.0, 0.0), (0.30, 0.04), (-0.28, 0.16), (0.08, -0.33), (0.27, -0.25)]
+    for i in range(n):
+        yaw, pitch, roll = rng.uniform(-3, 3), rng.normal(0, 0.22), rng.normal(0, 0.22)
+        cy, sy, cp, sp, cr, sr = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
+        q[i, :3] = [path[10, 0] + off[i][0], path[10, 1] + off[i][1], 0.03 + rng.uniform(0, 0.05)]
+        q[i, 3:7] = [cr * cp * cy + sr * sp * sy, sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy]
+        q[i, [8, 15, 22, 28]] = rng.uniform(-0.03, 0, 4)
+        q[i, [9, 16]] = rng.uniform(-0.6, 0.6, 2)
+        q[i, [10, 17, 23, 29]] = rng.uniform(-3, 3, 4)                                # throttle angle: must not matter
+    vis = np.array([1, 1, 1, 0, 1], dtype=np.uint8)
+    got = t.scan_world(q, vis)
+    hits = {"chassis": 0, "wheel": 0, "cyl": 0}
+    rx, rz, lr = -0.0525, 0.065, 0.03
+    for i in range(n):
+        R = _rotm(q[i, 3:7])
+        meshes, chassis, ells = [tris], [], []
+        for c in range(n):
+            if c == i or not vis[c]:
+                continue
+            Rc = _rotm(q[c, 3:7])
+            meshes.append(cylinder_mesh(q[c, :7])); chassis.append(chassis_local @ Rc.T + q[c, :3])
+            for w in range(4):
+                st = q[c, [9, 16][w]] if w < 2 else 0.0
+                Rz = np.array([[np.cos(st), -np.sin(st), 0], [np.sin(st), np.cos(st), 0], [0, 0, 1]])
+                ells.append((q[c, :3] + Rc @ (wpos[w] + [0, 0, q[c, [8, 15, 22, 28][w]]]), Rc @ Rz))
+        mesh = np.concatenate(meshes, 0)
+        chassis = np.concatenate(chassis, 0)
+        alone = t.scan(q[i:i + 1, :7])[0]
+        for j in range(90):
+            b = np.radians(4 * j - 90)
+            d = R @ np.array([np.sin(b), -np.cos(b), 0.0])
+            o = q[i, :3] + R @ np.array([rx - lr * np.sin(b), lr * np.cos(b), rz])
+            want = brute_ray(mesh, o, d)
+            want = np.inf if want < 0 else want
+            kind = "cyl" if abs(want - alone[j]) > 1e-3 else "wall"
+            o2 = o.copy()
+            v0, e1, e2 = chassis[:, 0], chassis[:, 1] - chassis[:, 0], chassis[:, 2] - chassis[:, 0]
+            pp = np.cross(d, e2); det = (e1 * pp).sum(1); okd = np.abs(det) > 1e-300
+            inv = np.where(okd, 1.0 / np.where(okd, det, 1.0), 0.0)
+            tt = o2 - v0; uu = (tt * pp).sum(1) * inv; qq = np.cross(tt, e1); vv = (qq * d).sum(1) * inv; ss = (e2 * qq).sum(1) * inv
+            hit = okd & (uu >= 0) & (vv >= 0) & (uu + vv <= 1) & (ss >= 0)
+            if hit.any() and ss[hit].min() < want:
+                want, kind = ss[hit].min(), "chassis"
+            for cc, Re in ells:
+                F = lambda s: ((((o[None] + s[:, None] * d[None] - cc) @ Re) / S) ** 2).sum(1) - 1.0
+                se = _first_root(F)
+                if se < want:
+                    want, kind = se, "wheel"
+            want = -1.0 if not np.isfinite(want) else want
+            assert (want < 0) == (got[i, j] < 0) and abs(want - got[i, j]) < 5e-6, (i, j, want, got[i, j], kind)
+            if kind in hits:
+                hits[kind] += 1
+    assert hits["wheel"] >= 3 and hits["chassis"] >= 3 and hits["cyl"] >= 3, hits

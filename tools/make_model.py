@@ -130,6 +130,9 @@ def main():
             "#define MUSHR_CHASSIS_INERTIA {%s}" % ", ".join(repr(float(x)) for x in I.reshape(-1)),
             f"#define MUSHR_SOFTENER_RADIUS {radius!r}",
             "#define MUSHR_SOFTENER_CENTER {%s}" % ", ".join(repr(float(x)) for x in wcom),
+            f"#define MUSHR_CHASSIS_NTRI {len(base)}",
+            "/* the chassis mesh's own triangles in the car frame (STL x 0.5 + geom pos): what mj_ray tests (SURVEY B.10) */",
+            "#define MUSHR_CHASSIS_TRI {%s}" % ", ".join("{%s}" % ", ".join(repr(float(x)) for x in (t + gpos).reshape(-1)) for t in base),
             f"#define MUSHR_CHASSIS_NHULL {len(H)}",
             "#define MUSHR_CHASSIS_HULL {%s}" % ", ".join("{%r, %r, %r}" % tuple(float(x) for x in v) for v in H), ""]
     for p in ("oracle/mushr_mesh.h", "ft_grandprix_b200/csrc/mushr_mesh.h"):
