@@ -14,7 +14,7 @@ MAX_TRACKS, MAX_LAPTIMES = 4, 16
 LAP_FIELDS = ("offset", "completion", "laps", "start", "good_start", "finished", "ntimes",
               "off_track", "rank", "delta", "offtrack_ticks", "contact_ticks")
 DRIVER_NIDC, DRIVER_FAST, DRIVER_LOBOTOMY = 0, 1, 2
-OPT_NAIVE_FLATTEN = 1
+OPT_NAIVE_FLATTEN, OPT_BUBBLE_WRAP = 1, 2
 
 class FtgpError(RuntimeError):
     pass
@@ -48,7 +48,7 @@ SIGNATURES = {
     "ftgp_lidar": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "ftgp_lidar_host": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "ftgp_reset": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "ftgp_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "ftgp_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
     "ftgp_release_scratch": (_i, [_vp]),
     "ftgp_naive_flatten": (_i, [_vp, _i64, _i64, _vp]),
     "ftgp_drivers": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp]),

@@ -78,7 +78,7 @@ FT_HDN bool hf_vertex_probe(const HfView& hv, const double* p, QWallHit& h) {
 
 // support point (world) of an ellipsoid with semi-axes size[0..2] / a cylinder with radius size[0], half height size[1]
 // about its local z, in the world direction dir
-enum { HF_ELLIPSOID = 0, HF_CYLINDER = 1 };
+enum { HF_ELLIPSOID = 0, HF_CYLINDER = 1, HF_SPHERE = 2 };       // sphere: radius size[0]
 FT_HD void hf_support(int kind, const double* size, const double* pos, const double* R, const double* dir, double* out) {
     const double d0 = R[0] * dir[0] + R[3] * dir[1] + R[6] * dir[2], d1 = R[1] * dir[0] + R[4] * dir[1] + R[7] * dir[2],
                  d2 = R[2] * dir[0] + R[5] * dir[1] + R[8] * dir[2];
@@ -87,6 +87,9 @@ FT_HD void hf_support(int kind, const double* size, const double* pos, const dou
         s[0] = size[0] * d0; s[1] = size[1] * d1; s[2] = size[2] * d2;
         const double n = sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
         s[0] = size[0] * s[0] / n; s[1] = size[1] * s[1] / n; s[2] = size[2] * s[2] / n;
+    } else if (kind == HF_SPHERE) {
+        const double n = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        s[0] = size[0] * d0 / n; s[1] = size[0] * d1 / n; s[2] = size[0] * d2 / n;
     } else {
         const double hn = sqrt(d0 * d0 + d1 * d1);
         s[0] = hn > MINVAL ? size[0] * d0 / hn : 0.0; s[1] = hn > MINVAL ? size[0] * d1 / hn : 0.0;

@@ -50,10 +50,10 @@ inline ModelConsts model_constants() {
     avg3(0); avg3(3);
     for (int w = 0; w < 4; w++) avg3(NR + NC * w + 3);
     // body_invweight0 (translational): trace(Jp Minv Jp^T) / 3 at the body's CoM
-    auto tran_at = [&](const double* point, int w) {
+    auto tran_at = [&](const double* point, int w, bool soft) {
         double J[3][NP] = {{0}};
         double off[3] = {point[0] - k.com[0], point[1] - k.com[1], point[2] - k.com[2]};
-        for (int col = 0; col < (w >= 0 ? 9 : 6); col++) {
+        for (int col = 0; col < (w >= 0 ? (soft ? 12 : 9) : 6); col++) {
             int p = col < 6 ? col : NR + NC * w + (col - 6);
             if (col == 7 && !front(w)) continue;
             double jp[3];
@@ -67,8 +67,15 @@ inline ModelConsts model_constants() {
     double xi1[3];
     mat_vec3(xi1, k.R1, mc.ipos1);
     for (int a = 0; a < 3; a++) xi1[a] += k.p1[a];
-    mc.chassis_invweight0 = tran_at(xi1, -1);
-    for (int w = 0; w < 4; w++) mc.wheel_invweight0[w] = tran_at(k.pw[w], w);
+    mc.chassis_invweight0 = tran_at(xi1, -1, false);
+    for (int w = 0; w < 4; w++) mc.wheel_invweight0[w] = tran_at(k.pw[w], w, false);
+    for (int w = 0; w < 4; w++) {                              // softener body: sphere centre behind the ball joint (qpos0: ball = identity)
+        const double sc[3] = MUSHR_SOFTENER_CENTER;
+        double t[3], ps[3];
+        mat_vec3(t, k.Rw[w], sc);
+        for (int a = 0; a < 3; a++) ps[a] = k.pw[w][a] + t[a];
+        mc.soft_invweight0[w] = tran_at(ps, w, true);
+    }
     return mc;
 }
 

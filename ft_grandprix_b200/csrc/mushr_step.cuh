@@ -51,6 +51,7 @@ constexpr double PLANE_Z = 0.01;         // mushr.em.xml:94
 struct ModelConsts {
     double dof_invweight0[NP];   // padded dof space
     double wheel_invweight0[4];  // body_invweight0[wheel body].translational
+    double soft_invweight0[4];   // body_invweight0[softener body].translational (option bubble_wrap)
     double chassis_invweight0;   // body_invweight0[car body].translational
     double meaninertia;
     double mass1, ipos1[3], inertia1[9];   // car body = chassis mesh + lidar cylinder

@@ -118,15 +118,16 @@ FT_HDN void quad_const_entry(const ModelConsts& mc, int g, double* t) {      // 
 // Rare contacts owned by the lane, kept in the lane's frame (local memory) and only touched when present:
 //   * up to QMAXCH contacts of the car body's geoms (chassis hull vertices / lidar cylinder against walls and ground):
 //     MAXBODYCON = 8 over four lanes, Jacobian over the six chassis dofs only;
-//   * the lane's wheel against a wall (ww = 1): Jacobian over the six chassis dofs and chain slots 0-2.
-// All of them: condim 3, mu = 1 (hfield / chassis / cylinder friction 1 > wheel 0.3, plane 0.5).
+//   * up to two "chain contacts" against the walls (bit c of ww): c = 0 the lane's wheel ellipsoid (Jacobian over the six
+//     chassis dofs and chain slots 0-2), c = 1 its softener sphere with the option bubble_wrap (chain slots 0-5).
+// All of them: condim 3, mu = 1 (hfield / chassis / cylinder / softener friction 1 > wheel 0.3, plane 0.5).
 constexpr int QMAXCH = 2, MAXBODYCON = 4 * QMAXCH;
 struct QChassis {
     double D[QMAXCH], aref[QMAXCH][4], J[QMAXCH][3][6], dx[QMAXCH][3], ds[QMAXCH][3];
-    double wD, waref[4], wJ[3][9], wdx[3], wds[3];                      // wheel-wall contact
+    double wD[2], waref[2][4], wJ[2][3][12], wdx[2][3], wds[2][3];      // chain contacts: wheel-wall, softener-wall
 };
 struct QState { double cost, gauss, c0; unsigned mask; int nch, ww; };  // c0 = qacc_smooth' qfrc_smooth / 2
-constexpr int QB_FR = 0, QB_FR6 = 6, QB_LIM = 7, QB_LIM6 = 9, QB_WC = 10, QB_CH = 14, QB_WW = 22;
+constexpr int QB_FR = 0, QB_FR6 = 6, QB_LIM = 7, QB_LIM6 = 9, QB_WC = 10, QB_CH = 14, QB_WW = 22;   // QB_WW + 4 c + rr
 constexpr double WC_MU = 0.5, CH_MU = 1.0;
 constexpr double REF_B = 2 / (0.95 * 0.02);          // kbi(): B of the default solref with dmax 0.95
 
@@ -231,18 +232,19 @@ FT_QN double rows_eval(const Q& qd, const QChassis& ch, int nch, int ww, QVec X,
             for (int col = 0; col < 6; col++) fr[col] += (ch.J[s][0][col] + sg * ch.J[s][ta][col]) * f;
         }
     }
-    if (ww) {                                                            // the lane's wheel against a wall
+    for (int c = 0; c < 2; c++) {                                        // the lane's wheel / softener against a wall
+        if (!(ww >> c & 1)) continue;
         double d3[3];
-        for (int a = 0; a < 3; a++) d3[a] = dot6q(ch.wJ[a], xr) + ch.wJ[a][6] * xc[0] + ch.wJ[a][7] * xc[1] + ch.wJ[a][8] * xc[2];
+        for (int a = 0; a < 3; a++) d3[a] = dot6q(ch.wJ[c][a], xr) + dot6q(ch.wJ[c][a] + 6, xc);
         for (int rr = 0; rr < 4; rr++) {
             const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-            const double jar = d3[0] + sg * d3[ta] - ch.waref[rr];
+            const double jar = d3[0] + sg * d3[ta] - ch.waref[c][rr];
             if (jar >= 0) continue;
-            cost += 0.5 * ch.wD * jar * jar;
-            mask |= 1u << (QB_WW + rr);
-            const double f = -ch.wD * jar;
-            for (int col = 0; col < 6; col++) fr[col] += (ch.wJ[0][col] + sg * ch.wJ[ta][col]) * f;
-            for (int k = 0; k < 3; k++) fc[k] += (ch.wJ[0][6 + k] + sg * ch.wJ[ta][6 + k]) * f;
+            cost += 0.5 * ch.wD[c] * jar * jar;
+            mask |= 1u << (QB_WW + 4 * c + rr);
+            const double f = -ch.wD[c] * jar;
+            for (int col = 0; col < 6; col++) fr[col] += (ch.wJ[c][0][col] + sg * ch.wJ[c][ta][col]) * f;
+            for (int k = 0; k < NC; k++) fc[k] += (ch.wJ[c][0][6 + k] + sg * ch.wJ[c][ta][6 + k]) * f;
         }
     }
     mask_out = mask;
@@ -382,19 +384,23 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
                 }
             }
         }
-        if (st.ww) {                                                     // wheel-wall rows: root block, chain block and border
+        for (int c = 0; c < 2; c++) {                                    // chain contacts: root block, chain block and border
+            if (!(st.ww >> c & 1)) continue;
             for (int rr = 0; rr < 4; rr++) {
-                if (!(mask >> (QB_WW + rr) & 1u)) continue;
+                if (!(mask >> (QB_WW + 4 * c + rr) & 1u)) continue;
                 const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-                double Jr[9];
-                for (int col = 0; col < 9; col++) Jr[col] = ch.wJ[0][col] + sg * ch.wJ[ta][col];
+                double Jr[12];
+                for (int col = 0; col < 12; col++) Jr[col] = ch.wJ[c][0][col] + sg * ch.wJ[c][ta][col];
                 for (int i = 0; i < 6; i++) {
-                    const double di = ch.wD * Jr[i];
+                    const double di = ch.wD[c] * Jr[i];
                     for (int j = 0; j <= i; j++) Pp[tri(i, j)] += di * Jr[j];
                 }
-                for (int l = 0; l < 3; l++) {
-                    const double dl = ch.wD * Jr[6 + l];
+#pragma unroll
+                for (int l = 0; l < NC; l++) {
+                    const double dl = ch.wD[c] * Jr[6 + l];
+#pragma unroll
                     for (int k = 0; k <= l; k++) W[tri(l, k)] += dl * Jr[6 + k];
+#pragma unroll
                     for (int j = 0; j < 6; j++) B[l][j] += dl * Jr[j];
                 }
             }
@@ -502,14 +508,18 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
 #pragma unroll
             for (int l = 0; l < 3; l++) t[l] -= qd.P(QP_CJ + 3 + l) * u[0] + qd.P(QP_CJ + 9 + l) * u[1] + qd.P(QP_CJ + 15 + l) * u[2];
         }
-        if (mode == 1 && st.ww) {                                        // (the wheel-wall rows' share of the border, as above)
-            for (int rr = 0; rr < 4; rr++) {
-                if (!(st.mask >> (QB_WW + rr) & 1u)) continue;
-                const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-                double sacc = 0;
-                for (int col = 0; col < 6; col++) sacc += (ch.wJ[0][col] + sg * ch.wJ[ta][col]) * xr[col];
-                sacc *= ch.wD;
-                for (int l = 0; l < 3; l++) t[l] -= (ch.wJ[0][6 + l] + sg * ch.wJ[ta][6 + l]) * sacc;
+        if (mode == 1 && st.ww) {                                        // (the chain contacts' share of the border, as above)
+            for (int c = 0; c < 2; c++) {
+                if (!(st.ww >> c & 1)) continue;
+                for (int rr = 0; rr < 4; rr++) {
+                    if (!(st.mask >> (QB_WW + 4 * c + rr) & 1u)) continue;
+                    const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+                    double sacc = 0;
+                    for (int col = 0; col < 6; col++) sacc += (ch.wJ[c][0][col] + sg * ch.wJ[c][ta][col]) * xr[col];
+                    sacc *= ch.wD[c];
+#pragma unroll
+                    for (int l = 0; l < NC; l++) t[l] -= (ch.wJ[c][0][6 + l] + sg * ch.wJ[c][ta][6 + l]) * sacc;
+                }
             }
         }
 #pragma unroll
@@ -589,11 +599,12 @@ FT_HD void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, int ww, const 
             if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
         }
     }
-    if (ww) {
-        const double D = ch.wD;
+    for (int c = 0; c < 2; c++) {
+        if (!(ww >> c & 1)) continue;
+        const double D = ch.wD[c];
         for (int rr = 0; rr < 4; rr++) {
             const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-            const double jar = ch.wdx[0] + sg * ch.wdx[ta] - ch.waref[rr], jv = ch.wds[0] + sg * ch.wds[ta];
+            const double jar = ch.wdx[c][0] + sg * ch.wdx[c][ta] - ch.waref[c][rr], jv = ch.wds[c][0] + sg * ch.wds[c][ta];
             if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
         }
     }
@@ -663,11 +674,12 @@ FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, doubl
         }
         for (int s = 0; s < st.nch; s++)
             for (int a = 0; a < 3; a++) { ch.dx[s][a] = dot6q(ch.J[s][a], xr); ch.ds[s][a] = dot6q(ch.J[s][a], sr); }
-        if (st.ww)
-            for (int a = 0; a < 3; a++) {
-                ch.wdx[a] = dot6q(ch.wJ[a], xr) + ch.wJ[a][6] * xc[0] + ch.wJ[a][7] * xc[1] + ch.wJ[a][8] * xc[2];
-                ch.wds[a] = dot6q(ch.wJ[a], sr) + ch.wJ[a][6] * sc[0] + ch.wJ[a][7] * sc[1] + ch.wJ[a][8] * sc[2];
-            }
+        for (int c = 0; c < 2; c++)
+            if (st.ww >> c & 1)
+                for (int a = 0; a < 3; a++) {
+                    ch.wdx[c][a] = dot6q(ch.wJ[c][a], xr) + dot6q(ch.wJ[c][a] + 6, xc);
+                    ch.wds[c][a] = dot6q(ch.wJ[c][a], sr) + dot6q(ch.wJ[c][a] + 6, sc);
+                }
     }
     const int nch = st.nch, ww = st.ww;
     const double gtol = SOLVER_TOL * LS_TOL * snorm / scale;
@@ -741,10 +753,12 @@ struct QNoWalls {                    // open ground
     FT_HD bool enabled() const { return false; }
     FT_HD bool vertex(const double*, QWallHit&) const { return false; }
     FT_HD bool convex(int, const double*, double, const double*, const double*, QWallHit&) const { return false; }
+    FT_HD bool bubble_wrap() const { return false; }
 };
-struct QHfWalls {                    // walls of one compiled track
-    HfView hv; bool on;
+struct QHfWalls {                    // walls of one compiled track; bubble: option bubble_wrap (softener spheres collide with them)
+    HfView hv; bool on, bubble;
     FT_HD bool enabled() const { return on; }
+    FT_HD bool bubble_wrap() const { return bubble; }
     FT_HD bool vertex(const double* p, QWallHit& h) const { return hf_vertex_probe(hv, p, h); }
     FT_HD bool convex(int kind, const double* size, double bound, const double* pos, const double* R, QWallHit& h) const {
         return hf_convex(hv, kind, size, bound, pos, R, h);
@@ -1015,31 +1029,41 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
     const bool wall_on = walls.enabled();
     if (qd.wany(wall_on)) {
         if (wall_on) {
-            QWallHit h;
-            const double wsz[3] = {WS0, WS1, WS2};
-            if (walls.convex(HF_ELLIPSOID, wsz, 0.03, pw, Rw, h)) {
-                st.ww = 1;
+            const double wsz[3] = {WS0, WS1, WS2}, ssz[1] = {MUSHR_SOFTENER_RADIUS};
+            for (int c = 0; c < (walls.bubble_wrap() ? 2 : 1); c++) {
+                QWallHit h;
+                // c = 0: wheel ellipsoid (body of the wheel, chain slots 0-2); c = 1: softener sphere behind the ball joint
+                // (mushr.em.xml:66, option bubble_wrap: conaffinity 4 against the walls' contype 4; chain slots 0-5)
+                const bool hit = c == 0 ? walls.convex(HF_ELLIPSOID, wsz, 0.03, pw, Rw, h)
+                                        : walls.convex(HF_SPHERE, ssz, MUSHR_SOFTENER_RADIUS, ps, Rs, h);
+                if (!hit) continue;
+                st.ww |= 1 << c;
+                const int ncol = c == 0 ? 9 : 12;
                 const double o[3] = {h.pnt[0] - com[0], h.pnt[1] - com[1], h.pnt[2] - com[2]};
                 double vel[3] = {0, 0, 0};
-                for (int col = 0; col < 9; col++) {
-                    const double* ax = col < 6 ? cdr[col] : cd[col - 6];
-                    double jp[3];
-                    cross3(jp, ax, o);
-                    for (int a = 0; a < 3; a++) jp[a] += ax[3 + a];
-                    const double j0 = dot3(h.nrm, jp), j1 = dot3(h.t1, jp), j2 = dot3(h.t2, jp), vk = col < 6 ? vr[col] : vc[col - 6];
-                    ch.wJ[0][col] = j0; ch.wJ[1][col] = j1; ch.wJ[2][col] = j2;
-                    vel[0] += j0 * vk; vel[1] += j1 * vk; vel[2] += j2 * vk;
+                for (int col = 0; col < 12; col++) {
+                    double j0 = 0, j1 = 0, j2 = 0;
+                    if (col < ncol) {
+                        const double* ax = col < 6 ? cdr[col] : cd[col - 6];
+                        double jp[3];
+                        cross3(jp, ax, o);
+                        for (int a = 0; a < 3; a++) jp[a] += ax[3 + a];
+                        j0 = dot3(h.nrm, jp); j1 = dot3(h.t1, jp); j2 = dot3(h.t2, jp);
+                        const double vk = col < 6 ? vr[col] : vc[col - 6];
+                        vel[0] += j0 * vk; vel[1] += j1 * vk; vel[2] += j2 * vk;
+                    }
+                    ch.wJ[c][0][col] = j0; ch.wJ[c][1][col] = j1; ch.wJ[c][2][col] = j2;
                 }
-                kbi(0.45, h.dist, mc.wheel_invweight0[w], K, B, imp, R);
+                kbi(c == 0 ? 0.45 : 0.9, h.dist, c == 0 ? mc.wheel_invweight0[w] : mc.soft_invweight0[w], K, B, imp, R);
                 double Rpy = 2 * CH_MU * CH_MU * R; if (Rpy < MINVAL) Rpy = MINVAL;
-                ch.wD = 1 / Rpy;
+                ch.wD[c] = 1 / Rpy;
                 for (int rr = 0; rr < 4; rr++) {
                     const double sg = (rr & 1) ? -1.0 : 1.0;
-                    ch.waref[rr] = -B * (vel[0] + sg * CH_MU * vel[1 + (rr >> 1)]) - K * imp * h.dist;
+                    ch.waref[c][rr] = -B * (vel[0] + sg * CH_MU * vel[1 + (rr >> 1)]) - K * imp * h.dist;
                 }
             }
         }
-        info.ncon_wall = popc4(qd.ballot(st.ww != 0));
+        info.ncon_wall = popc4(qd.ballot(st.ww & 1)) + popc4(qd.ballot(st.ww & 2));
     }
     // ---- contacts of the car body's geoms: candidate c = 2 v (hull vertex v against the walls, rule V), 2 v + 1 (vertex v
     // below the ground plane), 20 (lidar cylinder against the walls, rule S), 21 (cylinder below the ground plane); in that
@@ -1130,7 +1154,7 @@ FT_HD void quad_store_chain(int w, double* dst, const double* c, int base) {   /
 // packs the suspended cars of the whole fleet into fresh CTAs and goes on.  A CTA runs its cars in lock-step, so
 // without this every car pays for the slowest of its 54 neighbours: measured mean 2.1 Newton iterations per car,
 // 4.5 per CTA (tools/iteration_stats.py).  The arithmetic a car sees does not change (results are bit-identical).
-constexpr int QREC_CH = QMAXCH * (1 + 4 + 18), QREC_WW = 1 + 4 + 27;
+constexpr int QREC_CH = QMAXCH * (1 + 4 + 18), QREC_W1 = 1 + 4 + 36, QREC_WW = 2 * QREC_W1;
 constexpr int QREC_LANE = QP_N + QREC_CH + QREC_WW + 2;    // per lane: private slots, body contacts, wheel-wall contact, (cost, gauss)
 constexpr int QREC_DOUBLES = 4 * QREC_LANE + QC_N + 10;    // + per-car slots + (c0, mask[4], nch[4], ww[4], info) packed below
 struct QStage {
@@ -1153,11 +1177,13 @@ FT_HD void quad_suspend(const Q& qd, const QChassis& ch, const QState& st, const
                 for (int a = 0; a < 3; a++) for (int c = 0; c < 6; c++) r2[4 * k++ + w] = ch.J[s][a][c];
             } else k += 1 + 4 + 18;
         }
-        if (st.ww) {
-            r2[4 * k++ + w] = ch.wD;
-            for (int rr = 0; rr < 4; rr++) r2[4 * k++ + w] = ch.waref[rr];
-            for (int a = 0; a < 3; a++) for (int c = 0; c < 9; c++) r2[4 * k++ + w] = ch.wJ[a][c];
-        } else k += QREC_WW;
+        for (int c2 = 0; c2 < 2; c2++) {
+            if (st.ww >> c2 & 1) {
+                r2[4 * k++ + w] = ch.wD[c2];
+                for (int rr = 0; rr < 4; rr++) r2[4 * k++ + w] = ch.waref[c2][rr];
+                for (int a = 0; a < 3; a++) for (int c = 0; c < 12; c++) r2[4 * k++ + w] = ch.wJ[c2][a][c];
+            } else k += QREC_W1;
+        }
         r2[4 * k++ + w] = st.cost; r2[4 * k++ + w] = st.gauss;
     }
     double* r3 = rec + 4 * QREC_LANE;
@@ -1191,11 +1217,13 @@ FT_HD void quad_resume(const Q& qd, QChassis& ch, QState& st, StepInfo& info, co
                 for (int a = 0; a < 3; a++) for (int c = 0; c < 6; c++) ch.J[s][a][c] = r2[4 * k++ + w];
             } else k += 1 + 4 + 18;
         }
-        if (st.ww) {
-            ch.wD = r2[4 * k++ + w];
-            for (int rr = 0; rr < 4; rr++) ch.waref[rr] = r2[4 * k++ + w];
-            for (int a = 0; a < 3; a++) for (int c = 0; c < 9; c++) ch.wJ[a][c] = r2[4 * k++ + w];
-        } else k += QREC_WW;
+        for (int c2 = 0; c2 < 2; c2++) {
+            if (st.ww >> c2 & 1) {
+                ch.wD[c2] = r2[4 * k++ + w];
+                for (int rr = 0; rr < 4; rr++) ch.waref[c2][rr] = r2[4 * k++ + w];
+                for (int a = 0; a < 3; a++) for (int c = 0; c < 12; c++) ch.wJ[c2][a][c] = r2[4 * k++ + w];
+            } else k += QREC_W1;
+        }
         st.cost = r2[4 * k++ + w]; st.gauss = r2[4 * k++ + w];
     }
 }

@@ -32,8 +32,9 @@ static int ensure_model(int device) {
 }
 
 // the walls of the car's track as the contact rules see them (hfield_contact.cuh); read from global memory (L2-resident, ~50 KB)
-__device__ __forceinline__ QHfWalls track_walls(const uint32_t* blob, const int32_t* track_id, int64_t car, bool shadowed) {
+__device__ __forceinline__ QHfWalls track_walls(const uint32_t* blob, const int32_t* track_id, int64_t car, bool shadowed, int options) {
     QHfWalls w;
+    w.bubble = (options & FTGP_OPT_BUBBLE_WRAP) != 0;       // softener spheres collide with the walls (custom.py:1041-1055)
     w.on = false; w.hv.index = nullptr; w.hv.chunks = nullptr; w.hv.hc = w.hv.vc = 0; w.hv.size_x = w.hv.size_y = 1;
     if (!blob || shadowed) return w;        // a finished ("shadowed") car no longer collides with walls (custom.py:1455-1464)
     const GeomHeader* gh = reinterpret_cast<const GeomHeader*>(blob);
@@ -62,7 +63,7 @@ step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
                  double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
                  const int32_t* __restrict__ lap, const int32_t* __restrict__ perm, int64_t ncars, int nsteps,
                  int32_t* __restrict__ status, double* __restrict__ recs, int32_t* __restrict__ list_out,
-                 int32_t* __restrict__ count_out, int max_rounds) {
+                 int32_t* __restrict__ count_out, int max_rounds, int options) {
     const int tid = threadIdx.x, cib = tid >> 2;
     constexpr int KO = NT * QP_N + NT / 4 * QC_N;
     for (int g = tid; g < 25; g += NT) quad_const_entry(c_model, g, quad_sm + KO);
@@ -74,7 +75,7 @@ step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
     QuadDev<NT, NT / 4, LOCK> qd;
     qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.qs = tid & 28;
     const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
-    const QHfWalls walls = track_walls(blob, track_id, car, shadowed);
+    const QHfWalls walls = track_walls(blob, track_id, car, shadowed, options);
     int st = 0;
     for (int s = 0; s < nsteps; s++) {
         StepInfo info;
@@ -107,7 +108,7 @@ step_quad_resume_kernel(double* __restrict__ qpos, double* __restrict__ qvel, do
     const int n = *count_in;
     QuadDev<NT, NT / 4, true> qd;
     qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.qs = tid & 28;
-    const QHfWalls walls = track_walls(nullptr, nullptr, 0, true);   // (the position stage, which probes the walls, is behind us)
+    const QHfWalls walls = track_walls(nullptr, nullptr, 0, true, 0);   // (the position stage, which probes the walls, is behind us)
     for (int base = blockIdx.x * CARS; base < n; base += gridDim.x * CARS) {
         const int e = base + cib;
         const bool live = e < n;
@@ -205,7 +206,7 @@ constexpr int64_t ORDER_MIN_CARS = 1024, STAGE_MIN_CARS = 4096;
 
 int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
                 const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
-                cudaStream_t stream) {
+                int options, cudaStream_t stream) {
     int dev = 0;
     FTGP_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 16) { set_error("ftgp_step: device index %d not supported", dev); return FTGP_ERR_UNSUPPORTED; }
@@ -267,7 +268,7 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     }
     constexpr int CARS = STEP_NT / 4;
     step_quad_kernel<STEP_NT, true><<<(unsigned)((ncars + CARS - 1) / CARS), STEP_NT, smem, stream>>>(
-        blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status, recs, lists, counts, STAGE_ROUNDS);
+        blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status, recs, lists, counts, STAGE_ROUNDS, options);
     count_launch();
     if (recs) {
         step_quad_resume_kernel<STEP_NT><<<g_sm_count[dev], STEP_NT, smem, stream>>>(
@@ -302,7 +303,7 @@ static int issue_tick(const ftgp_tick_args* a, int32_t steps, int32_t* steps_dev
     // custom.py:1425 mj_step: rangefinders are evaluated from the pre-step pose, then the state advances
     if ((rc = launch_lidar(a->geom, a->qpos, FTGP_NQ, a->track_id, nullptr, a->lap, a->ncars, a->cars_per_world, a->ranges,
                            nullptr, s))) return rc;
-    return launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, 1, a->status, s);
+    return launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, 1, a->status, a->options, s);
 }
 
 // ---- small fleets: the tick is launch-bound (4-9 launches of a few microseconds of work each), so it is captured once
@@ -397,11 +398,11 @@ using namespace ftgp;
 
 extern "C" int ftgp_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
                          const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
-                         void* stream) {
+                         int options, void* stream) {
     if (!qpos || !qvel || !warm || !ctrl || ncars < 0 || nsteps < 0) { set_error("ftgp_step: bad argument"); return FTGP_ERR_ARG; }
     if (ncars == 0 || nsteps == 0) return FTGP_OK;
     if (g) FTGP_CUDA(cudaSetDevice(g->device));
-    return launch_step(g, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status, (cudaStream_t)stream);
+    return launch_step(g, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status, options, (cudaStream_t)stream);
 }
 
 extern "C" int ftgp_release_scratch(void* stream) {

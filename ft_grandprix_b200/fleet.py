@@ -39,8 +39,8 @@ def _ptr(t):
 
 class Fleet:
     def __init__(self, tracks, ncars, cars_per_world=1, device=0, track_id=None, driver="nidc",
-                 lap_target=10, naive_flatten=False):
-        """lap_target, naive_flatten: the path-relevant options of the reference (custom.py:961,981)."""
+                 lap_target=10, naive_flatten=False, bubble_wrap=False):
+        """lap_target, naive_flatten, bubble_wrap: the path-relevant options of the reference (custom.py:961,981,970)."""
         if not torch.cuda.is_available():
             raise _lib.FtgpError("Fleet needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -52,6 +52,7 @@ class Fleet:
         self.nworlds = self.ncars // self.cars_per_world
         self.lap_target = int(lap_target)
         self.naive_flatten = bool(naive_flatten)
+        self.bubble_wrap = bool(bubble_wrap)
         self.default_driver = DRIVER_KINDS[driver] if isinstance(driver, str) else int(driver)
         dev, n = self.device, self.ncars
         with torch.cuda.device(dev):
@@ -69,6 +70,10 @@ class Fleet:
         self.driver_kind = None
         self.steps = 0
         torch.cuda.synchronize(dev)
+
+    @property
+    def options(self):
+        return (_lib.OPT_NAIVE_FLATTEN if self.naive_flatten else 0) | (_lib.OPT_BUBBLE_WRAP if self.bubble_wrap else 0)
 
     def close(self):
         """Free the step kernel's per-stream scratch (about 6 KB per car)."""
@@ -175,7 +180,7 @@ class Fleet:
         _lib.check(self.lib.ftgp_step(self.geom._ptr, _ptr(self.qpos), _ptr(self.qvel), _ptr(self.warm),
                                       _ptr(self.ctrl), _ptr(self.track_id),
                                       _ptr(self.lap) if shadow_finished else None, self.ncars, int(nsteps),
-                                      _ptr(self.status), self._s), "ftgp_step")
+                                      _ptr(self.status), self.options, self._s), "ftgp_step")
         self.steps += int(nsteps)
 
     def flatten(self):
@@ -205,7 +210,7 @@ class Fleet:
         a.ncars = self.ncars
         a.cars_per_world, a.default_driver = self.cars_per_world, self.default_driver
         a.lap_target, a.steps = self.lap_target, self.steps
-        a.options = _lib.OPT_NAIVE_FLATTEN if self.naive_flatten else 0
+        a.options = self.options
         return a
 
     def tick(self, nticks=1):

@@ -44,6 +44,7 @@ enum {
 };
 
 enum { FTGP_DRIVER_NIDC = 0, FTGP_DRIVER_FAST = 1, FTGP_DRIVER_LOBOTOMY = 2 };
+enum { FTGP_OPT_NAIVE_FLATTEN = 1, FTGP_OPT_BUBBLE_WRAP = 2 };   /* path-relevant options of custom.py:946-989 */
 
 const char* ftgp_last_error(void);
 int ftgp_abi_version(void);
@@ -123,10 +124,12 @@ int ftgp_reset(double* qpos, double* qvel, double* warm, double* ctrl, const dou
  * vertices, lidar cylinder), bits 24-27 wheel-ground contacts, bits 28-30 chassis / lidar-cylinder
  * contacts with the ground (a flipped car).  g may be NULL (open ground plane, no walls).  lap: device lap state
  * (FTGP_LAP_* rows, see below) or NULL; a car whose FTGP_LAP_FINISHED field is set has been
- * shadow()ed (custom.py:1455-1464: conaffinity 0 / contype 2): it no longer collides with walls. */
+ * shadow()ed (custom.py:1455-1464: conaffinity 0 / contype 2): it no longer collides with walls.
+ * options: FTGP_OPT_* bits; FTGP_OPT_BUBBLE_WRAP = the reference's option bubble_wrap (custom.py:970-972,
+ * 1041-1055: the softener spheres of mushr.em.xml:66 get conaffinity 4 and collide with the walls). */
 int ftgp_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
               const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
-              void* stream);
+              int options, void* stream);
 /* The step keeps per-(device, stream) scratch (regrouping lists, records of the staged solve: about
  * 6 KB per car).  Frees the scratch of `stream` on the current device; call when a fleet is destroyed. */
 int ftgp_release_scratch(void* stream);
@@ -168,7 +171,8 @@ typedef struct {
     int32_t cars_per_world, default_driver, lap_target, steps;
     int32_t options, reserved;              /* FTGP_OPT_* bits: the path-relevant options of custom.py:946-989 */
 } ftgp_tick_args;
-enum { FTGP_OPT_NAIVE_FLATTEN = 1 };        /* custom.py:981,1338-1339: every tick, keep the chassis' yaw and zero its pitch / roll */
+/* FTGP_OPT_NAIVE_FLATTEN: custom.py:981,1338-1339, every tick keep the chassis' yaw and zero its pitch / roll;
+ * FTGP_OPT_BUBBLE_WRAP: custom.py:970-972,1041-1055, the softener spheres collide with the walls */
 /* Option naive_flatten on its own (custom.py:1338-1339): qpos[3:7] <- quaternion of (yaw, 0, 0). */
 int ftgp_naive_flatten(double* qpos, int64_t qpos_stride, int64_t ncars, void* stream);
 /* One iteration of physics_thread (custom.py:1337-1426) for the whole fleet:

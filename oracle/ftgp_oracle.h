@@ -130,6 +130,8 @@ int fto_constraint_problem(const fto_model* m, const fto_track* t, const double*
 
 /* N-car world (BASELINE config 5): one Newton problem over all cars, car-car contacts by this framework's definition
  * (oracle/step.c).  Ground work for the coupled solve; not used by the product yet. */
+/* option bubble_wrap (custom.py:970-972,1041-1055): the softener spheres collide with the walls */
+void fto_model_set_bubble_wrap(fto_model* m, int on);
 /* TEST SUPPORT: contact set of one car (10 doubles per contact: body, dist, pos[3], normal[3], mu, solimp d0) */
 int fto_contacts(const fto_model* m, const fto_track* t, const double* qpos, double* out, int maxcon);
 int fto_world_step(const fto_model* m, const fto_track* t, int ncars, double* qpos, double* qvel, double* warm,

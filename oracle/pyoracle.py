@@ -161,6 +161,10 @@ class Model:
     def __del__(self):
         if getattr(self, "ptr", None):
             lib().fto_model_destroy(self.ptr); self.ptr = None
+    def set_bubble_wrap(self, on):
+        """option bubble_wrap (custom.py:970-972): softener spheres collide with the walls"""
+        lib().fto_model_set_bubble_wrap.argtypes = [C.c_void_p, C.c_int]
+        lib().fto_model_set_bubble_wrap(self.ptr, int(bool(on)))
     def constants(self):
         dinv = np.zeros(29); binv = np.zeros((11, 2)); mass = np.zeros(11)
         inertia = np.zeros((11, 3, 3)); ipos = np.zeros((11, 3)); mean = np.zeros(1)

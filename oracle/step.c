@@ -29,7 +29,7 @@
 #define NV FTO_NV
 #define NQ FTO_NQ
 #define NEQ 2
-#define MAXCON 16           /* framework rule: 4 wheel-ground + 4 wheel-wall + up to MAXBODYCON contacts of the car body's geoms */
+#define MAXCON 20           /* framework rule: 4 wheel-ground + 4 wheel-wall + 4 softener-wall + up to MAXBODYCON contacts of the car body's geoms */
 #define MAXBODYCON 8
 #define MAXEFC (NEQ + 23 + 7 + 4 * MAXCON)
 
@@ -73,6 +73,7 @@ struct fto_model {
     double eq_poly[NEQ][5];
     int eq_dof1[NEQ], eq_dof2[NEQ], eq_q1[NEQ], eq_q2[NEQ];
     double hull[MUSHR_CHASSIS_NHULL][3];
+    int bubble_wrap;            /* option bubble_wrap (custom.py:970-972,1041-1055): softener spheres collide with the walls */
 };
 
 /* ------------------------------------------------------------------ small math */
@@ -329,6 +330,7 @@ fto_model* fto_model_create(void) {
     return m;
 }
 void fto_model_destroy(fto_model* m) { free(m); }
+void fto_model_set_bubble_wrap(fto_model* m, int on) { m->bubble_wrap = on ? 1 : 0; }
 
 void fto_model_constants(const fto_model* m, double* dinv, double* binv, double* mass, double* inertia,
                          double* ipos, double* meaninertia) {
@@ -587,17 +589,22 @@ static int wheel_plane(const fto_model* m, const kin_t* k, contact_t* con) {
  *   every contact: condim 3, dist = signed distance to the plane, pos = point - n dist / 2, frame = mju_makeFrame(n);
  *   friction = max of the two geoms (hfield / chassis / cylinder default 1, plane 0.5, wheel 0.3), solref default,
  *   solimp[0] = mean (0.45 with a wheel, else 0.9).
- *   order and caps: wheel-ground (<= 4), wheel-wall (<= 1 per wheel), then the car body's contacts, at most MAXBODYCON:
+ *   option bubble_wrap: the softener spheres (mushr.em.xml:66, conaffinity 4 against the walls' contype 4; radius and centre
+ *   fitted to the wheel mesh, mushr_mesh.h) against the walls by rule S, one contact per softener on the softener body.
+ *   order and caps: wheel-ground (<= 4), wheel-wall (<= 1 per wheel), softener-wall (<= 1 per wheel), then the car body's contacts, at most MAXBODYCON:
  *   per hull vertex in mesh order its wall then its ground contact, then cylinder-wall, then cylinder-ground.
  *   A shadowed (finished) car has contype 2: ground contacts only (custom.py:1455-1464). */
 static void hfield_plane_at(const fto_track* t, double x, double y, double* nrm, double* h);
-enum { G_ELLIPSOID, G_CYLINDER };
+enum { G_ELLIPSOID, G_CYLINDER, G_SPHERE };
 static void support_local(int kind, const double* size, const double* d, double* s) {   /* support point in direction d, geom frame */
     if (kind == G_ELLIPSOID) {
         double n = 0;
         for (int a = 0; a < 3; a++) { s[a] = size[a] * d[a]; n += s[a] * s[a]; }
         n = sqrt(n);
         for (int a = 0; a < 3; a++) s[a] = size[a] * s[a] / n;
+    } else if (kind == G_SPHERE) {
+        const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        for (int a = 0; a < 3; a++) s[a] = size[0] * d[a] / n;
     } else {                                                                            /* cylinder: radius size[0], half height size[1] */
         double h = sqrt(d[0] * d[0] + d[1] * d[1]);
         s[0] = h > FTO_MINVAL ? size[0] * d[0] / h : 0; s[1] = h > FTO_MINVAL ? size[0] * d[1] / h : 0;
@@ -664,7 +671,7 @@ static void contact_fill(contact_t* c, int body, const double* point, const doub
     const double si[5] = {d0, 0.95, 0.001, 0.5, 2};
     memcpy(c->solimp, si, sizeof si);
 }
-/* appends to con[n..]; counts[0] = wheel-wall, [1] = body-wall, [2] = body-ground contacts */
+/* appends to con[n..]; counts[0] = wheel-wall, [1] = body-wall, [2] = body-ground, [3] = softener-wall contacts */
 static int car_contacts(const fto_model* m, const fto_track* t, const kin_t* k, contact_t* con, int n, int* counts) {
     const double up[3] = {0, 0, 1}, down[3] = {0, 0, -1};
     counts[0] = counts[1] = counts[2] = 0;
@@ -674,6 +681,17 @@ static int car_contacts(const fto_model* m, const fto_track* t, const kin_t* k, 
         if (!convex_hfield(t, G_ELLIPSOID, m->wheel_size, 0.03, k->xpos[b], k->xmat[b], nrm, sp, &dist)) continue;
         contact_fill(&con[n++], b, sp, nrm, dist, 1.0, 0.45);
         counts[0]++;
+    }
+    counts[3] = 0;
+    if (t && m->bubble_wrap) for (int w = 0; w < 4; w++) {                             /* softener spheres vs walls (rule S) */
+        const int b = m->wheel_body[w] + 1;
+        const double sc[3] = MUSHR_SOFTENER_CENTER, size[1] = {MUSHR_SOFTENER_RADIUS};
+        double pos[3], nrm[3], sp[3], dist;
+        mat_vec(pos, k->xmat[b], sc);
+        for (int a = 0; a < 3; a++) pos[a] += k->xpos[b][a];
+        if (!convex_hfield(t, G_SPHERE, size, MUSHR_SOFTENER_RADIUS, pos, k->xmat[b], nrm, sp, &dist)) continue;
+        contact_fill(&con[n++], b, sp, nrm, dist, 1.0, 0.9);
+        counts[3]++;
     }
     int nb = 0;
     for (int v = 0; v < MUSHR_CHASSIS_NHULL; v++) {                                   /* chassis hull vertices (rule V) */
@@ -1036,7 +1054,7 @@ int fto_step(const fto_model* m, const fto_track* t, double* qpos, double* qvel,
     /* ---- position stage */
     kinematics(m, qpos, k); com_pos(m, k); crb(m, k);
     contact_t con[MAXCON];
-    int nwheel = wheel_plane(m, k, con), cnt[3];
+    int nwheel = wheel_plane(m, k, con), cnt[4];
     int ncon = car_contacts(m, t, k, con, nwheel, cnt);
     make_constraint(m, k, qpos, con, ncon, e);
     /* ---- velocity stage */
@@ -1079,7 +1097,7 @@ int fto_step(const fto_model* m, const fto_track* t, double* qpos, double* qvel,
     for (int d = 0; d < NV; d++) qvel[d] += TIMESTEP * qa[d];
     integrate_pos(m, qpos, qvel, TIMESTEP);
     /* info[3] = contacts with walls (wheels + chassis + lidar cylinder), info[5] = chassis / cylinder contacts with the ground */
-    if (info) { info[0] = iters; info[1] = e->n; info[2] = nwheel; info[3] = cnt[0] + cnt[1]; info[4] = 0; info[5] = cnt[2]; info[6] = cnt[0]; }
+    if (info) { info[0] = iters; info[1] = e->n; info[2] = nwheel; info[3] = cnt[0] + cnt[1] + cnt[3]; info[4] = 0; info[5] = cnt[2]; info[6] = cnt[0]; info[7] = cnt[3]; }
     free(k); free(e);
     return rc;
 }
@@ -1090,7 +1108,7 @@ int fto_contacts(const fto_model* m, const fto_track* t, const double* qpos, dou
     kin_t* k = (kin_t*)malloc(sizeof(kin_t));
     kinematics(m, qpos, k); com_pos(m, k);
     contact_t con[MAXCON];
-    int cnt[3];
+    int cnt[4];
     int n = car_contacts(m, t, k, con, wheel_plane(m, k, con), cnt);
     if (n > maxcon) n = maxcon;
     for (int c = 0; c < n; c++) {
@@ -1165,7 +1183,7 @@ int fto_constraint_problem(const fto_model* m, const fto_track* t, const double*
     efc_t* e = (efc_t*)malloc(sizeof(efc_t));
     kinematics(m, qpos, k); com_pos(m, k); crb(m, k);
     contact_t con[MAXCON];
-    int nwheel = wheel_plane(m, k, con), cnt[3];
+    int nwheel = wheel_plane(m, k, con), cnt[4];
     int ncon = car_contacts(m, t, k, con, nwheel, cnt);
     make_constraint(m, k, qpos, con, ncon, e);
     com_vel(m, qvel, k);
@@ -1423,7 +1441,7 @@ static int world_assemble(const fto_model* m, const fto_track* t, int ncars, con
         const double* q = qpos + (size_t)c * NQ; const double* v = qvel + (size_t)c * NV; const double* u = ctrl + 2 * (size_t)c;
         kinematics(m, q, k); com_pos(m, k); crb(m, k);
         contact_t con[MAXCON];
-        int nwheel = wheel_plane(m, k, con), cnt[3];
+        int nwheel = wheel_plane(m, k, con), cnt[4];
         int ncon = car_contacts(m, (shadowed && shadowed[c]) ? 0 : t, k, con, nwheel, cnt);    /* custom.py:1455-1464 */
         if (nwheel_out) nwheel_out[c] = nwheel;
         make_constraint(m, k, q, con, ncon, e);

@@ -48,11 +48,12 @@ struct QuadHost : QuadMem<4, 1> {
 static ModelConsts g_mc;
 static bool g_ready = false;
 // walls: one compiled track of the product's geometry blob (ftgp_geom_blob / ftgp_blob_track_view), or none
-static QHfWalls g_walls = {{nullptr, nullptr, 0, 0, 1.0, 1.0}, false};
+static QHfWalls g_walls = {{nullptr, nullptr, 0, 0, 1.0, 1.0}, false, false};
 extern "C" void hq_set_walls(const uint16_t* index, const uint32_t* chunks, int hc, int vc, double size_x, double size_y) {
     g_walls.on = index != nullptr;
     g_walls.hv.index = index; g_walls.hv.chunks = chunks; g_walls.hv.hc = hc; g_walls.hv.vc = vc; g_walls.hv.size_x = size_x; g_walls.hv.size_y = size_y;
 }
+extern "C" void hq_set_bubble_wrap(int on) { g_walls.bubble = on != 0; }
 extern "C" int hq_step_ghost(double* qpos, double* qvel, double* warm, const double* ctrl, long n, int nsteps, int* info4, int ghost_w, int ghost_c) {
     if (!g_ready) { g_mc = model_constants(); g_ready = true; }
     QuadHostShared sh;

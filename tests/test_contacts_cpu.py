@@ -174,6 +174,57 @@ def test_contact_set_matches_bruteforce_over_the_explicit_mesh(oracle, otracks, 
     assert compared > 300 and kinds["wheel_wall"] > 20 and kinds["body_wall"] > 50 and kinds["body_ground"] > 5, (compared, kinds)
 
 
+def test_bubble_wrap_softener_contacts_match_bruteforce(oracle, otracks, walls):
+    """option bubble_wrap: rule S for the softener spheres (radius / centre fitted to the wheel mesh, tests/golden/
+    mushr_mesh.json) on the softener bodies 4, 6, 8, 10, between the wheel-wall and the car-body contacts"""
+    wall, svg = walls["small-circle"]
+    t = otracks["small-circle"]
+    model = oracle.Model(); model.set_bubble_wrap(True)
+    mesh = json.load(open(os.path.join(GOLDEN, "mushr_mesh.json")))
+    radius, centre = mesh["softener"]["radius"], np.array(mesh["softener"]["center"])
+    tris, nrm = surface_triangles(chunk_mesh(wall))
+    H, W = wall.shape
+    hc, vc = -(-W // 20), -(-H // 20)
+    sx, sy = 40.0 / hc, 40.0 / vc
+    py, px = np.nonzero(wall)
+    wx = sx * (px // 20 - 0.5 + (px % 20) / 19); wy = -sy * (py // 20 - 0.5 + (py % 20) / 19)
+    poses = _poses_into_walls(None, np.stack([wx, wy], 1), 60, seed=9)
+    rng = np.random.default_rng(10)
+    seen = 0
+    for ps in poses:
+        q, _, _ = model.reset(0.0, 0.0, 0.0)
+        q[:7] = ps
+        q[8], q[15], q[22], q[28] = rng.uniform(-0.03, 0, 4); q[9], q[16] = rng.uniform(-0.5, 0.5, 2)
+        for a in (11, 18, 24, 30):
+            q[a:a + 4] = rng.normal(size=4); q[a:a + 4] /= np.linalg.norm(q[a:a + 4])
+        got = [c for c in model.contacts(t, q, maxcon=20) if int(c[0]) in (4, 6, 8, 10)]
+        R1, p1 = rot(q[3:7]), q[:3]
+        want = []
+        for w, (qa, steer) in enumerate(((8, True), (15, True), (22, False), (28, False))):
+            ang = q[qa + 1] if steer else 0.0
+            thr = q[qa + 2] if steer else q[qa + 1]
+            Rz = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+            Ry = np.array([[np.cos(thr), 0, np.sin(thr)], [0, 1, 0], [-np.sin(thr), 0, np.cos(thr)]])
+            Rs = R1 @ Rz @ Ry @ rot(q[qa + (3 if steer else 2):qa + (7 if steer else 6)])
+            c = p1 + R1 @ (WHEEL_POS[w] + [0, 0, q[qa]]) + Rs @ centre
+            near = (np.abs(tris[:, :, 0] - c[0]).min(1) < 0.11) & (np.abs(tris[:, :, 1] - c[1]).min(1) < 0.11)
+            T, N = tris[near], nrm[near]
+            if not len(T):
+                continue
+            s = c - radius * N                                         # sphere support point against each plane
+            dist = ((s - T[:, 0]) * N).sum(1)
+            ok = inside_xy(T, s) & (dist < 0)
+            if ok.any():
+                k = np.argmin(np.where(ok, dist, np.inf))
+                want.append((4 + 2 * w, dist[k], s[k] - N[k] * dist[k] / 2, N[k]))
+        assert len(got) == len(want), (len(got), len(want))
+        for g, (b, d, pos, n) in zip(got, want):
+            assert int(g[0]) == b and abs(g[1] - d) < 1e-9 and np.abs(g[2:5] - pos).max() < 1e-9 and np.abs(g[5:8] - n).max() < 1e-9
+            assert g[8] == 1.0 and g[9] == 0.9
+            seen += 1
+    assert seen > 40
+
+
 def test_level_driving_car_has_only_wheel_ground_contacts(oracle, otracks, walls):
     """on the open track the new rules add nothing: 4 wheel-ground contacts, as before"""
     wall, svg = walls["track"]

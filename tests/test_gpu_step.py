@@ -44,7 +44,7 @@ def test_single_step_parity_1e5(ft, oracle):
     _load(fleet, Q, V, W, U)
     # open ground (no walls): pure MuJoCo-restated dynamics
     ft._lib.check(fleet.lib.ftgp_step(None, fleet.qpos.data_ptr(), fleet.qvel.data_ptr(), fleet.warm.data_ptr(),
-                                      fleet.ctrl.data_ptr(), None, None, n, 1, fleet.status.data_ptr(), fleet._s), "ftgp_step")
+                                      fleet.ctrl.data_ptr(), None, None, n, 1, fleet.status.data_ptr(), 0, fleet._s), "ftgp_step")
     fleet.sync()
     info = model.step_n(None, Q, V, W, U)
     np.testing.assert_allclose(fleet.qpos.cpu().numpy(), Q, rtol=1e-5, atol=1e-10)
@@ -69,7 +69,7 @@ def test_trajectory_divergence_over_1000_ticks_is_reported(ft, oracle, capsys):
             U = np.stack([rng.uniform(0.5, 4, n), rng.uniform(-0.5, 0.5, n)], 1)
             fleet.ctrl.copy_(torch.from_numpy(U)); torch.cuda.synchronize()
         ft._lib.check(fleet.lib.ftgp_step(None, fleet.qpos.data_ptr(), fleet.qvel.data_ptr(), fleet.warm.data_ptr(),
-                                          fleet.ctrl.data_ptr(), None, None, n, 1, None, fleet._s), "ftgp_step")
+                                          fleet.ctrl.data_ptr(), None, None, n, 1, None, 0, fleet._s), "ftgp_step")
         model.step_n(None, Q, V, W, U)
         if k % 100 == 99:
             fleet.sync()
@@ -539,3 +539,36 @@ def test_option_naive_flatten(ft):
         b.lap_update(); b.drive(); b.lidar(); b.step(1)
     a.sync(); b.sync()
     assert torch.equal(a.qpos, b.qpos) and torch.equal(a.ranges, b.ranges)
+
+
+def test_option_bubble_wrap_on_device(ft, oracle, otracks):
+    """Option bubble_wrap (custom.py:970-972,1041-1055) on the GPU: softener spheres touch the walls; vs the oracle."""
+    model = oracle.Model(); model.set_bubble_wrap(True)
+    t = ft.Track.bundled("track")
+    ot = otracks["track"]
+    n = 96
+    from conftest import random_poses
+    poses = random_poses(t.path, n, seed=14, level=True)
+    Q = np.zeros((n, 34)); V = np.zeros((n, 29)); W = np.zeros((n, 29)); U = np.tile([0.5, 0.0], (n, 1))
+    rng = np.random.default_rng(15)
+    for i in range(n):
+        yaw = 2 * np.arctan2(poses[i, 6], poses[i, 3])
+        Q[i], V[i], W[i] = model.reset(poses[i, 0], poses[i, 1], yaw)
+    for k in range(40):
+        model.step_n(ot, Q, V, W, U, nthreads=8)
+    ang = rng.uniform(-np.pi, np.pi, n)
+    V[:, 0] = 2.5 * np.cos(ang); V[:, 1] = 2.5 * np.sin(ang)            # shove every settled car in a random direction
+    fleet = ft.Fleet(t, n, bubble_wrap=True)
+    _load(fleet, Q, V, W, U)
+    soft = 0
+    for k in range(300):
+        fleet.step(1)
+        info = model.step_n(ot, Q, V, W, U, nthreads=8)
+        soft += int(info[:, 7].sum())
+        if k % 25 == 24:
+            fleet.sync()
+            st = fleet.status.cpu().numpy()
+            assert (((st >> 16) & 0xFF) == info[:, 3]).all()
+            assert np.abs(fleet.qpos.cpu().numpy() - Q).max() < 1e-6
+            _load(fleet, Q, V, W, U)
+    assert soft > 200

@@ -700,3 +700,42 @@ def test_quad_kernel_staged_solve_with_wall_contacts_is_bit_identical(model, otr
         assert ncon > 20 and nsus > 10, (ncon, nsus)
     finally:
         host_quad_kernel.hq_set_walls(None, None, 0, 0, 1.0, 1.0)
+
+
+def test_quad_kernel_bubble_wrap_softener_contacts_match_oracle(model, otracks, host_quad_kernel, host_kernel):
+    """Option bubble_wrap (custom.py:970-972,1041-1055): the softener spheres (radius 0.0435 > the wheel's 0.03) touch
+    the walls before the wheels do.  Host build of the quad kernel vs the oracle, sideways slides into walls; also the
+    compile-time constant body_invweight0 of the softener bodies."""
+    blob, t = _host_walls(host_quad_kernel)
+    bw = oracle_model_with_bubble_wrap = model.__class__()
+    bw.set_bubble_wrap(True)
+    host_quad_kernel.hq_set_bubble_wrap(1)
+    try:
+        ot = otracks["track"]
+        rng = np.random.default_rng(13)
+        soft = total = 0
+        for kp in (10, 22, 37, 64, 81):
+            d = t.path[kp + 1] - t.path[kp]
+            yaw = float(np.arctan2(d[1], d[0]))
+            q, v, w = bw.reset(float(t.path[kp, 0]), float(t.path[kp, 1]), yaw)
+            ctrl = np.array([0.5, 0.0])
+            sgn = rng.choice([-1.0, 1.0])
+            for k in range(450):
+                if k == 40:
+                    v[0:2] = sgn * 2.5 * np.array([-np.sin(yaw), np.cos(yaw)])
+                qh, vh, wh = q.copy(), v.copy(), w.copy()
+                info = np.zeros(4, dtype=np.int32)
+                host_quad_kernel.hq_step_ghost(P(qh), P(vh), P(wh), P(ctrl), 1, 1, P(info), 0, 0)
+                rc, oi = bw.step(ot, q, v, w, ctrl)
+                assert info[1] == oi[2] and info[2] == oi[3], (kp, k, info, oi)
+                err = max(np.abs(qh - q).max(), np.abs(vh - v).max() * 1e-2)
+                assert err < 1e-9, (kp, k, err, oi)
+                soft += int(oi[7]); total += int(oi[3])
+        assert soft > 50 and total > soft, (soft, total)
+        # without the option the same slide has no softener contacts
+        q, v, w = model.reset(float(t.path[10, 0]), float(t.path[10, 1]), 0.3)
+        _, oi = model.step(ot, q, v, w, np.zeros(2))
+        assert oi[7] == 0
+    finally:
+        host_quad_kernel.hq_set_bubble_wrap(0)
+        host_quad_kernel.hq_set_walls(None, None, 0, 0, 1.0, 1.0)
