@@ -48,7 +48,7 @@ SIGNATURES = {
     "ftgp_lidar": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "ftgp_lidar_host": (_i, [_vp, _vp, _i64, _vp, _i64, _vp]),
     "ftgp_reset": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "ftgp_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _i, _vp]),
+    "ftgp_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp, _i, _vp]),
     "ftgp_release_scratch": (_i, [_vp]),
     "ftgp_naive_flatten": (_i, [_vp, _i64, _i64, _vp]),
     "ftgp_drivers": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp]),

@@ -14,6 +14,14 @@
 #pragma once
 #include "mushr_step.cuh"
 
+// the probes are rarely executed (a car near a wall) and long: kept out of line on the device so that the step kernel's
+// hot path does not carry four inlined copies of them
+#if defined(__CUDACC__)
+#define FT_HDNI __host__ __device__ __noinline__
+#else
+#define FT_HDNI inline
+#endif
+
 namespace ftgp {
 namespace mushr {
 
@@ -48,8 +56,28 @@ FT_HD double hf_bit(const uint32_t* m, int ncol, int r, int c) {      // vertex 
     return (double)((m[b >> 5] >> (b & 31)) & 1u) * HF_ELEV;
 }
 
+// Can anything within `radius` of (x, y) touch a wall?  Corner k (0..3) of the square selects one of the (at most four)
+// chunks under it; true if that chunk has raised vertices whose cells (one cell of slope around them) reach the square.
+// The four corners together are a conservative gate for every probe below.
+FT_HD bool hf_near_corner(const HfView& hv, double x, double y, double radius, int k) {
+    const double xs = (k & 1) ? x + radius : x - radius, ys = (k & 2) ? y + radius : y - radius;
+    const int i = (int)floor(xs / hv.size_x + 0.5), j = (int)floor(-ys / hv.size_y + 0.5);
+    if (i < 0 || i >= hv.hc || j < 0 || j >= hv.vc) return false;
+    const unsigned cid = hv.index[(hv.vc - 1 - j) * hv.hc + i];
+    if (cid == HF_EMPTY) return false;
+    const uint32_t* m = hv.chunks + cid * HF_CHUNK_WORDS;
+    const int ncol = m[13] & 0xFF, nrow = (m[13] >> 8) & 0xFF;
+    const uint32_t bb = m[14];
+    const int cmin = bb & 0xFF, cmax = (bb >> 8) & 0xFF, rmin = (bb >> 16) & 0xFF, rmax = bb >> 24;
+    if (cmin > cmax) return false;
+    const double dx = hv.size_x / (ncol - 1), dy = hv.size_y / (nrow - 1);
+    const double x0 = hv.size_x * i - 0.5 * hv.size_x, y0 = -hv.size_y * j - 0.5 * hv.size_y;
+    return x + radius >= x0 + (cmin - 1) * dx && x - radius <= x0 + (cmax + 1) * dx &&
+           y + radius >= y0 + (rmin - 1) * dy && y - radius <= y0 + (rmax + 1) * dy;
+}
+
 // rule V: world point p against the surface triangle under it
-FT_HDN bool hf_vertex_probe(const HfView& hv, const double* p, QWallHit& h) {
+FT_HDNI bool hf_vertex_probe(const HfView& hv, const double* p, QWallHit& h) {
     const int i = (int)floor(p[0] / hv.size_x + 0.5), j = (int)floor(-p[1] / hv.size_y + 0.5);
     if (i < 0 || i >= hv.hc || j < 0 || j >= hv.vc) return false;
     const unsigned cid = hv.index[(hv.vc - 1 - j) * hv.hc + i];
@@ -100,7 +128,7 @@ FT_HD void hf_support(int kind, const double* size, const double* pos, const dou
 }
 
 // rule S: the geom's one wall contact (deepest candidate), or false
-FT_HDN bool hf_convex(const HfView& hv, int kind, const double* size, double bound, const double* pos, const double* R, QWallHit& h) {
+FT_HDNI bool hf_convex(const HfView& hv, int kind, const double* size, double bound, const double* pos, const double* R, QWallHit& h) {
     bool found = false;
     double best = 0, bp[3] = {0, 0, 0};
     const int i0 = (int)floor((pos[0] - bound) / hv.size_x + 0.5), i1 = (int)floor((pos[0] + bound) / hv.size_x + 0.5);

@@ -332,9 +332,11 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
             F[6] = 2 * (x * y + w * z); F[7] = 1 - 2 * (x * x + z * z); F[8] = 2 * (y * z - w * x);
             F[9] = 2 * (x * z - w * y); F[10] = 2 * (y * z + w * x); F[11] = 1 - 2 * (x * x + y * y);
             // wheel poses for the other cars' rays (full state rows only; a bare pose leaves the joints at qpos0)
-            const bool full = MULTI && stride >= FTGP_NQ;
-            F[12] = full ? q[8] : 0.0; F[13] = full ? q[15] : 0.0; F[14] = full ? q[22] : 0.0; F[15] = full ? q[28] : 0.0;
-            F[16] = full ? q[9] : 0.0; F[17] = full ? q[16] : 0.0;
+            if (MULTI) {
+                const bool full = stride >= FTGP_NQ;
+                F[12] = full ? q[8] : 0.0; F[13] = full ? q[15] : 0.0; F[14] = full ? q[22] : 0.0; F[15] = full ? q[28] : 0.0;
+                F[16] = full ? q[9] : 0.0; F[17] = full ? q[16] : 0.0;
+            }
             int tid = track_id ? track_id[base_car + lane] : 0;
             if (tid < 0 || tid >= gh->ntracks) tid = 0;
             // bit 8: other cars do not see this car (shadowed, custom.py:1455-1464); bit 9: its own rangefinders are

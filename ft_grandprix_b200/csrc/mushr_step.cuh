@@ -36,7 +36,7 @@ constexpr int NV = 29, NQ = 34;
 constexpr int NR = 7;            // root dofs
 constexpr int NC = 6;            // chain slots per wheel
 constexpr int NP = NR + 4 * NC;  // padded dof space (31): rear wheels carry a dummy steering slot
-constexpr int MAXCON = 8;        // 4 wheel-ground + up to 4 chassis contacts
+constexpr int MAXCON = 20;       // 4 wheel-ground + 4 wheel-wall + 4 softener-wall + up to 8 contacts of the car body's geoms
 constexpr int NBODY = 11;
 
 constexpr double TIMESTEP = 0.004;       // mushr.em.xml:30
@@ -251,9 +251,10 @@ FT_HDN void arrow_solve(const Arrow& A, double* x) {
 
 // ---- per-step workspace ---------------------------------------------------------------------------------
 struct Contact {
-    double J[3][9];     // rows: normal, tangent1, tangent2; cols: chassis dofs 0-5, chain slots 0-2 (susp, steer, throttle)
-    double dist, mu, dmin;      // solimp d0 (0.45 wheel-ground, 0.9 chassis)
+    double J[3][12];    // rows: normal, tangent1, tangent2; cols: chassis dofs 0-5, chain slots 0-5 (susp, steer, throttle, ball)
+    double dist, mu, dmin;      // solimp d0 (0.45 with a wheel, else 0.9)
     int wheel;          // 0..3, or -1: contact on the car body itself (chain columns unused)
+    int nchain;         // chain columns in use: 3 (wheel body), 6 (softener body behind the ball joint), 0 (car body)
     double tran;        // body_invweight0 translational
 };
 
@@ -263,6 +264,7 @@ struct Kin {
     double cinert1[10], cinert_sw[10], cinert_w[4][10], cinert_s[4][10];
     double cdof[NP][6];         // padded dof space; rows 0-2 are implicit unit translations but stored for uniformity
     double pw[4][3], Rw[4][9];  // wheel position / orientation
+    double ps[4][3], Rs[4][9];  // softener sphere centre / softener body orientation
 };
 
 struct Rows {
@@ -319,7 +321,8 @@ FT_HDN void kinematics(const ModelConsts& mc, const double* qpos, Kin& k) {
         mat_mul3(Rs[w], k.Rw[w], Rb);
         double t[3];
         mat_vec3(t, Rs[w], sc);
-        for (int a = 0; a < 3; a++) ps[w][a] = k.pw[w][a] + t[a];
+        for (int a = 0; a < 3; a++) { ps[w][a] = k.pw[w][a] + t[a]; k.ps[w][a] = ps[w][a]; }
+        for (int a = 0; a < 9; a++) k.Rs[w][a] = Rs[w][a];
     }
     // centre of mass of the whole car (subtree_com of the root body)
     double xi1[3];
@@ -507,7 +510,7 @@ FT_HDN void wheel_contacts(const ModelConsts& mc, const Kin& k, Rows& r) {
         double dist = sw[2] - PLANE_Z;
         if (dist > 0 || r.ncon >= MAXCON) continue;
         Contact& c = r.con[r.ncon++];
-        c.dist = dist; c.mu = 0.5; c.dmin = 0.45; c.wheel = w; c.tran = mc.wheel_invweight0[w];
+        c.dist = dist; c.mu = 0.5; c.dmin = 0.45; c.wheel = w; c.nchain = 3; c.tran = mc.wheel_invweight0[w];
         double off[3] = {sw[0] - k.com[0], sw[1] - k.com[1], sw[2] - 0.5 * dist - k.com[2]};   // contact point - com
         // frame: n = (0,0,1), t1 = (0,1,0), t2 = (-1,0,0)  (mju_makeFrame)
         for (int col = 0; col < 9; col++) {
@@ -568,7 +571,7 @@ FT_HDN void make_rows(const ModelConsts& mc, const double* qpos, const double* v
         for (int a = 0; a < 3; a++) {
             double s = 0;
             for (int col = 0; col < 6; col++) s += ct.J[a][col] * v[col];
-            if (ct.wheel >= 0) for (int col = 6; col < 9; col++) s += ct.J[a][col] * v[NR + NC * ct.wheel + col - 6];
+            for (int col = 0; col < ct.nchain; col++) s += ct.J[a][6 + col] * v[NR + NC * ct.wheel + col];
             vel[a] = s;
         }
         for (int rr = 0; rr < 4; rr++) {
@@ -587,7 +590,7 @@ FT_HD void contact_dots(const Contact& ct, const double* x, double* d3) {
     for (int a = 0; a < 3; a++) {
         double s = 0;
         for (int col = 0; col < 6; col++) s += ct.J[a][col] * x[col];
-        if (ct.wheel >= 0) { const double* xc = x + NR + NC * ct.wheel; for (int col = 0; col < 3; col++) s += ct.J[a][6 + col] * xc[col]; }
+        if (ct.nchain > 0) { const double* xc = x + NR + NC * ct.wheel; for (int col = 0; col < ct.nchain; col++) s += ct.J[a][6 + col] * xc[col]; }
         d3[a] = s;
     }
 }
@@ -642,18 +645,18 @@ FT_HDN double rows_cost(const Rows& r, const double* x, double* qfrc, Arrow* H) 
             if (jar >= 0) continue;
             cost += 0.5 * D * jar * jar;
             if (WITH_FORCE || WITH_H) {
-                double Jr[9];
-                for (int col = 0; col < 9; col++) Jr[col] = ct.J[0][col] + sg * ct.mu * ct.J[ta][col];
+                double Jr[12];
+                for (int col = 0; col < 6 + ct.nchain; col++) Jr[col] = ct.J[0][col] + sg * ct.mu * ct.J[ta][col];
                 if (WITH_FORCE) {
                     const double f = -D * jar;
                     for (int col = 0; col < 6; col++) qfrc[col] += Jr[col] * f;
-                    if (ct.wheel >= 0) for (int col = 0; col < 3; col++) qfrc[NR + NC * ct.wheel + col] += Jr[6 + col] * f;
+                    for (int col = 0; col < ct.nchain; col++) qfrc[NR + NC * ct.wheel + col] += Jr[6 + col] * f;
                 }
                 if (WITH_H) {
                     for (int i = 0; i < 6; i++) for (int j = 0; j <= i; j++) H->R[tri(i, j)] += D * Jr[i] * Jr[j];
-                    if (ct.wheel >= 0) {
+                    if (ct.nchain > 0) {
                         const int w = ct.wheel;
-                        for (int l = 0; l < 3; l++) {
+                        for (int l = 0; l < ct.nchain; l++) {
                             for (int kk = 0; kk <= l; kk++) H->W[w][tri(l, kk)] += D * Jr[6 + l] * Jr[6 + kk];
                             for (int j = 0; j < 6; j++) H->B[w][l][j] += D * Jr[6 + l] * Jr[j];
                         }
@@ -669,9 +672,10 @@ FT_HDN double rows_cost(const Rows& r, const double* x, double* qfrc, Arrow* H) 
 struct LsPoint { double alpha, cost, d0, d1; };
 struct LsCtx { const Rows* r; const double* x; const double* s; double qg0, qg1, qg2; double cdx[MAXCON][3], cds[MAXCON][3]; };
 
-FT_HDN void ls_eval(const LsCtx& c, LsPoint& pt, double alpha) {
+// the car's share of the cost along the line, as the coefficients of a quadratic in alpha (added to q0, q1, q2)
+FT_HDN void ls_quad(const LsCtx& c, double alpha, double& q0, double& q1, double& q2) {
     const Rows& r = *c.r; const double* x = c.x; const double* s = c.s;
-    double q0 = c.qg0, q1 = c.qg1, q2 = c.qg2;
+    q0 += c.qg0; q1 += c.qg1; q2 += c.qg2;
     for (int w = 0; w < 2; w++) {
         const int p1 = NR + NC * w + 1;
         const double jar = x[p1] - r.eq_der[w] * x[6] - r.eq_aref[w], jv = s[p1] - r.eq_der[w] * s[6], D = r.eq_D[w];
@@ -703,9 +707,16 @@ FT_HDN void ls_eval(const LsCtx& c, LsPoint& pt, double alpha) {
             if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
         }
     }
+}
+FT_HD void ls_point(LsPoint& pt, double alpha, double q0, double q1, double q2) {
     pt.alpha = alpha; pt.cost = alpha * alpha * q2 + alpha * q1 + q0;
     pt.d0 = 2 * alpha * q2 + q1; pt.d1 = 2 * q2;
     if (pt.d1 <= 0) pt.d1 = MINVAL;
+}
+FT_HDN void ls_eval(const LsCtx& c, LsPoint& pt, double alpha) {
+    double q0 = 0, q1 = 0, q2 = 0;
+    ls_quad(c, alpha, q0, q1, q2);
+    ls_point(pt, alpha, q0, q1, q2);
 }
 
 // exact line search (PrimalSearch): Newton on the derivative, then bracketing

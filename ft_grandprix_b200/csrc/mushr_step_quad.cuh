@@ -754,17 +754,20 @@ struct QNoWalls {                    // open ground
     FT_HD bool vertex(const double*, QWallHit&) const { return false; }
     FT_HD bool convex(int, const double*, double, const double*, const double*, QWallHit&) const { return false; }
     FT_HD bool bubble_wrap() const { return false; }
+    FT_HD bool near_corner(double, double, double, int) const { return false; }
 };
 struct QHfWalls {                    // walls of one compiled track; bubble: option bubble_wrap (softener spheres collide with them)
     HfView hv; bool on, bubble;
     FT_HD bool enabled() const { return on; }
     FT_HD bool bubble_wrap() const { return bubble; }
+    FT_HD bool near_corner(double x, double y, double radius, int k) const { return hf_near_corner(hv, x, y, radius, k); }
     FT_HD bool vertex(const double* p, QWallHit& h) const { return hf_vertex_probe(hv, p, h); }
     FT_HD bool convex(int kind, const double* size, double bound, const double* pos, const double* R, QWallHit& h) const {
         return hf_convex(hv, kind, size, bound, pos, R, h);
     }
 };
 constexpr double LIDAR_CYL_BOUND = 0.0336;       // > sqrt(0.03^2 + 0.015^2): bounding radius of the lidar cylinder
+constexpr double CAR_BOUND = 0.15;               // every geom of the car lies within this distance of the car body's origin, in any pose
 
 template <class Q, class WallFn>
 FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, const double* qc, const double* vr, const double* vc,
@@ -1026,7 +1029,8 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
     // ---- the lane's wheel ellipsoid vs the walls (rule S): one contact, Jacobian over chassis dofs + chain slots 0-2
     st.ww = 0; st.nch = 0;
     info.ncon_wall = 0; info.ncon_ground = 0;
-    const bool wall_on = walls.enabled();
+    // (gate: lane k looks at the chunk under corner k of the car's bounding square; most cars are nowhere near a wall)
+    const bool wall_on = walls.enabled() && qd.any(walls.enabled() && walls.near_corner(p1[0], p1[1], CAR_BOUND, w));
     if (qd.wany(wall_on)) {
         if (wall_on) {
             const double wsz[3] = {WS0, WS1, WS2}, ssz[1] = {MUSHR_SOFTENER_RADIUS};

@@ -10,6 +10,7 @@
 #include "common.h"
 #include "mushr_consts.h"
 #include "mushr_step_quad.cuh"
+#include "mushr_world.cuh"
 #include <cstdlib>
 #include <atomic>
 #include <mutex>
@@ -63,15 +64,17 @@ step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, d
                  double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
                  const int32_t* __restrict__ lap, const int32_t* __restrict__ perm, int64_t ncars, int nsteps,
                  int32_t* __restrict__ status, double* __restrict__ recs, int32_t* __restrict__ list_out,
-                 int32_t* __restrict__ count_out, int max_rounds, int options) {
+                 int32_t* __restrict__ count_out, int max_rounds, int options, const uint8_t* __restrict__ world_flag, int cpw) {
     const int tid = threadIdx.x, cib = tid >> 2;
     constexpr int KO = NT * QP_N + NT / 4 * QC_N;
     for (int g = tid; g < 25; g += NT) quad_const_entry(c_model, g, quad_sm + KO);
     __syncthreads();
     int64_t car = (int64_t)blockIdx.x * (NT / 4) + cib;
-    const bool live = car < ncars;
+    bool live = car < ncars;
     if (!live) car = ncars - 1;                     // padding quad: same collectives, no stores
     if (perm) car = perm[car];                      // cars grouped by their last Newton iteration count
+    // a world whose cars touch each other this tick is one coupled problem: world_step_kernel advances it, not this kernel
+    if (world_flag && world_flag[car / cpw]) live = false;
     QuadDev<NT, NT / 4, LOCK> qd;
     qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.qs = tid & 28;
     const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
@@ -162,6 +165,7 @@ struct StepScratch {
     int dev = -1; cudaStream_t stream = nullptr; uint64_t used = 0;
     int32_t* perm = nullptr; int32_t* counters = nullptr; int64_t cap = 0;                                          // regrouping
     double* recs = nullptr; int32_t* lists = nullptr; int32_t* stage_counts = nullptr; int64_t stage_cap = 0;      // staged solve
+    WorldWork* world_ws = nullptr; int32_t* world_list = nullptr; uint8_t* world_flag = nullptr; int64_t world_cap = 0; int world_slots = 0;   // coupled worlds
     uint64_t generation = 0;     // bumped whenever a buffer is (re)allocated or freed: captured graphs hold these pointers
     void release() {
         if (dev < 0) return;
@@ -172,6 +176,9 @@ struct StepScratch {
         if (recs) cudaFree(recs);
         if (lists) cudaFree(lists);
         if (stage_counts) cudaFree(stage_counts);
+        if (world_ws) cudaFree(world_ws);
+        if (world_list) cudaFree(world_list);
+        if (world_flag) cudaFree(world_flag);
         cudaSetDevice(cur);
         const uint64_t gen = generation + 1;
         *this = StepScratch();
@@ -195,6 +202,59 @@ static StepScratch* step_scratch(int dev, cudaStream_t stream) {       // caller
     return lru;
 }
 
+// ---- worlds of 2..8 cars (BASELINE config 5): cars that touch each other are ONE constraint problem (mushr_world.cuh).
+// world_flag_kernel finds the worlds with a car-car contact this tick (a thread per world, poses only); the quad kernel
+// skips their cars; world_step_kernel advances them, one warp per flagged world, lane c = car c, workspace in global memory.
+__global__ void world_flag_kernel(const double* __restrict__ qpos, const int32_t* __restrict__ lap, int64_t nworlds, int cpw,
+                                  uint8_t* __restrict__ flag, int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    const int64_t wld = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wld >= nworlds) return;
+    const double* q[WMAXCARS]; bool sh[WMAXCARS];
+    for (int c = 0; c < cpw; c++) {
+        const int64_t car = wld * cpw + c;
+        q[c] = qpos + car * NQ;
+        sh[c] = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
+    }
+    const bool hit = world_has_contact(cpw, q, sh);
+    flag[wld] = hit ? 1 : 0;
+    if (hit) list[atomicAdd(count, 1)] = (int32_t)wld;
+}
+
+struct WarpComm {                                   // one warp per world: lane c = car c (lanes >= cars idle along)
+    int lane, nlanes;
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
+__global__ void __launch_bounds__(32)
+world_step_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel, double* __restrict__ warm,
+                  const double* __restrict__ ctrl, const int32_t* __restrict__ track_id, const int32_t* __restrict__ lap, int cpw,
+                  int32_t* __restrict__ status, const int32_t* __restrict__ list, const int32_t* __restrict__ count,
+                  WorldWork* __restrict__ ws, int options) {
+    const int n = *count;
+    WorldWork& W = ws[blockIdx.x];
+    WarpComm cm{(int)threadIdx.x, 32};
+    Kin kin;                                        // this lane's position-stage scratch (local memory)
+    for (int e = blockIdx.x; e < n; e += gridDim.x) {
+        const int64_t wld = list[e];
+        double *q[WMAXCARS], *v[WMAXCARS], *wm[WMAXCARS]; const double* u[WMAXCARS];
+        QHfWalls walls[WMAXCARS]; bool sh[WMAXCARS];
+        for (int c = 0; c < cpw; c++) {
+            const int64_t car = wld * cpw + c;
+            q[c] = qpos + car * NQ; v[c] = qvel + car * NV; wm[c] = warm + car * NV; u[c] = ctrl + 2 * car;
+            sh[c] = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
+            walls[c] = track_walls(blob, track_id, car, sh[c], options);
+        }
+        WorldInfo wi;
+        world_step(cm, c_model, cpw, q, v, wm, u, walls, sh, W, kin, wi);
+        if (status && (int)threadIdx.x < cpw) {
+            const CarWork& C = W.car[threadIdx.x];
+            StepInfo si; si.iters = wi.iters; si.reset = wi.reset; si.ncon_wheel = C.nwheel; si.ncon_wall = C.nwall; si.ncon_ground = C.nground;
+            status[wld * cpw + threadIdx.x] = status_word(si, 0) | 0x200;       // bit 9: advanced by the coupled world solver
+        }
+        __syncwarp();
+    }
+}
+
 // The production mapping is frozen: 216-thread CTAs (54 cars, 6 warps + 24 lanes), CTA-level lock-step of the Newton
 // loop, cars regrouped by (last Newton iteration count, wall contact), staged solve with two Newton rounds in the first
 // launch (DESIGN.md 8 lists the measured alternatives; the A/B variants live in tests/host_harness, not in this library).
@@ -204,9 +264,13 @@ constexpr int STEP_NT = 216;
 constexpr int STAGE_ROUNDS = 2;
 constexpr int64_t ORDER_MIN_CARS = 1024, STAGE_MIN_CARS = 4096;
 
+constexpr int WORLD_SLOTS = 2048;                   // flagged worlds advanced concurrently (the rest queue behind them)
+
 int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
-                const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
+                const int32_t* track_id, const int32_t* lap, int64_t ncars, int cpw, int nsteps, int32_t* status,
                 int options, cudaStream_t stream) {
+    if (cpw < 1 || cpw > WMAXCARS || ncars % cpw) { set_error("ftgp_step: cars_per_world must be 1..8 and divide ncars"); return FTGP_ERR_ARG; }
+    if (cpw > 1 && nsteps != 1) { set_error("ftgp_step: worlds of several cars are stepped one step per call"); return FTGP_ERR_UNSUPPORTED; }
     int dev = 0;
     FTGP_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 16) { set_error("ftgp_step: device index %d not supported", dev); return FTGP_ERR_UNSUPPORTED; }
@@ -225,7 +289,26 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     const bool big = ncars < (int64_t)1 << 31;
     const bool reorder = status && big && ncars >= ORDER_MIN_CARS;
     const bool staged = nsteps == 1 && big && ncars >= STAGE_MIN_CARS;
-    StepScratch* o = (reorder || staged) ? step_scratch(dev, stream) : nullptr;
+    StepScratch* o = (reorder || staged || cpw > 1) ? step_scratch(dev, stream) : nullptr;
+    // worlds of several cars: flag the worlds whose cars touch (they leave the fast path)
+    const int64_t nworlds = ncars / cpw;
+    if (cpw > 1) {
+        if (o->world_cap < nworlds) {
+            if (o->world_ws) cudaFree(o->world_ws);
+            if (o->world_list) cudaFree(o->world_list);
+            if (o->world_flag) cudaFree(o->world_flag);
+            o->world_ws = nullptr; o->world_list = nullptr; o->world_flag = nullptr; o->world_cap = 0; o->generation++;
+            o->world_slots = (int)std::min<int64_t>(nworlds, WORLD_SLOTS);
+            FTGP_CUDA(cudaMalloc(&o->world_ws, (size_t)o->world_slots * sizeof(WorldWork)));
+            FTGP_CUDA(cudaMalloc(&o->world_list, (size_t)(nworlds + 1) * sizeof(int32_t)));
+            FTGP_CUDA(cudaMalloc(&o->world_flag, (size_t)nworlds));
+            o->world_cap = nworlds;
+        }
+        FTGP_CUDA(cudaMemsetAsync(o->world_list + nworlds, 0, sizeof(int32_t), stream));        // the counter sits behind the list
+        world_flag_kernel<<<(unsigned)((nworlds + 127) / 128), 128, 0, stream>>>(qpos, lap, nworlds, cpw, o->world_flag, o->world_list,
+                                                                               o->world_list + nworlds);
+        count_launch();
+    }
     // cars grouped by (last Newton iteration count, wall contact) for the kernel that runs 54 cars in lock-step
     const int32_t* perm = nullptr;
     if (reorder) {
@@ -268,11 +351,18 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     }
     constexpr int CARS = STEP_NT / 4;
     step_quad_kernel<STEP_NT, true><<<(unsigned)((ncars + CARS - 1) / CARS), STEP_NT, smem, stream>>>(
-        blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status, recs, lists, counts, STAGE_ROUNDS, options);
+        blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status, recs, lists, counts, STAGE_ROUNDS, options,
+        cpw > 1 ? o->world_flag : nullptr, cpw);
     count_launch();
     if (recs) {
         step_quad_resume_kernel<STEP_NT><<<g_sm_count[dev], STEP_NT, smem, stream>>>(
             qpos, qvel, warm, ctrl, status, recs, lists, counts, lists + ncars, counts + 1, 0);
+        count_launch();
+    }
+    if (cpw > 1) {                                  // the coupled worlds (reads the poses the fast path left untouched)
+        const int slots = std::min<int64_t>(nworlds, o->world_slots);
+        world_step_kernel<<<slots, 32, 0, stream>>>(blob, qpos, qvel, warm, ctrl, track_id, lap, cpw, status, o->world_list,
+                                                    o->world_list + nworlds, o->world_ws, options);
         count_launch();
     }
     FTGP_CUDA(cudaGetLastError());
@@ -303,7 +393,7 @@ static int issue_tick(const ftgp_tick_args* a, int32_t steps, int32_t* steps_dev
     // custom.py:1425 mj_step: rangefinders are evaluated from the pre-step pose, then the state advances
     if ((rc = launch_lidar(a->geom, a->qpos, FTGP_NQ, a->track_id, nullptr, a->lap, a->ncars, a->cars_per_world, a->ranges,
                            nullptr, s))) return rc;
-    return launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, 1, a->status, a->options, s);
+    return launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, a->cars_per_world, 1, a->status, a->options, s);
 }
 
 // ---- small fleets: the tick is launch-bound (4-9 launches of a few microseconds of work each), so it is captured once
@@ -397,12 +487,12 @@ static int graph_ticks(const ftgp_tick_args* a, int nticks, cudaStream_t s, int*
 using namespace ftgp;
 
 extern "C" int ftgp_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
-                         const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
-                         int options, void* stream) {
+                         const int32_t* track_id, const int32_t* lap, int64_t ncars, int cars_per_world, int nsteps,
+                         int32_t* status, int options, void* stream) {
     if (!qpos || !qvel || !warm || !ctrl || ncars < 0 || nsteps < 0) { set_error("ftgp_step: bad argument"); return FTGP_ERR_ARG; }
     if (ncars == 0 || nsteps == 0) return FTGP_OK;
     if (g) FTGP_CUDA(cudaSetDevice(g->device));
-    return launch_step(g, qpos, qvel, warm, ctrl, track_id, lap, ncars, nsteps, status, options, (cudaStream_t)stream);
+    return launch_step(g, qpos, qvel, warm, ctrl, track_id, lap, ncars, cars_per_world, nsteps, status, options, (cudaStream_t)stream);
 }
 
 extern "C" int ftgp_release_scratch(void* stream) {

@@ -179,8 +179,8 @@ class Fleet:
         (custom.py:1455-1464: they pass through walls) unless shadow_finished is False."""
         _lib.check(self.lib.ftgp_step(self.geom._ptr, _ptr(self.qpos), _ptr(self.qvel), _ptr(self.warm),
                                       _ptr(self.ctrl), _ptr(self.track_id),
-                                      _ptr(self.lap) if shadow_finished else None, self.ncars, int(nsteps),
-                                      _ptr(self.status), self.options, self._s), "ftgp_step")
+                                      _ptr(self.lap) if shadow_finished else None, self.ncars, self.cars_per_world,
+                                      int(nsteps), _ptr(self.status), self.options, self._s), "ftgp_step")
         self.steps += int(nsteps)
 
     def flatten(self):

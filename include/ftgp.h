@@ -126,10 +126,14 @@ int ftgp_reset(double* qpos, double* qvel, double* warm, double* ctrl, const dou
  * (FTGP_LAP_* rows, see below) or NULL; a car whose FTGP_LAP_FINISHED field is set has been
  * shadow()ed (custom.py:1455-1464: conaffinity 0 / contype 2): it no longer collides with walls.
  * options: FTGP_OPT_* bits; FTGP_OPT_BUBBLE_WRAP = the reference's option bubble_wrap (custom.py:970-972,
- * 1041-1055: the softener spheres of mushr.em.xml:66 get conaffinity 4 and collide with the walls). */
+ * 1041-1055: the softener spheres of mushr.em.xml:66 get conaffinity 4 and collide with the walls).
+ * cars_per_world in 1..8: consecutive cars form one world = one MjModel of the reference (mushr.em.xml:95,
+ * template/cars/*.json).  Cars of a world that touch each other (a chassis hull vertex inside the other chassis' hull
+ * box) are advanced as ONE constraint problem, as mj_step does for the model (one search direction, one step length,
+ * one stopping rule); status bit 9 marks cars advanced that way.  cars_per_world > 1 needs nsteps == 1. */
 int ftgp_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
-              const int32_t* track_id, const int32_t* lap, int64_t ncars, int nsteps, int32_t* status,
-              int options, void* stream);
+              const int32_t* track_id, const int32_t* lap, int64_t ncars, int cars_per_world, int nsteps,
+              int32_t* status, int options, void* stream);
 /* The step keeps per-(device, stream) scratch (regrouping lists, records of the staged solve: about
  * 6 KB per car).  Frees the scratch of `stream` on the current device; call when a fleet is destroyed. */
 int ftgp_release_scratch(void* stream);
@@ -178,8 +182,8 @@ int ftgp_naive_flatten(double* qpos, int64_t qpos_stride, int64_t ncars, void* s
 /* One iteration of physics_thread (custom.py:1337-1426) for the whole fleet:
  * lap update -> built-in driver on last tick's ranges -> ctrl -> [rangefinders from the
  * pre-step pose, mj_step] ; the same one-tick sensor lag as the reference.
- * cars_per_world > 1: the cars of a world see each other's lidar cylinder and are ranked
- * together, but car-car CONTACTS are not generated yet (they pass through each other).
+ * cars_per_world > 1: the cars of a world see each other (lidar cylinder, chassis mesh, wheels), are ranked together
+ * and collide with each other (see ftgp_step).
  * Fleets of up to 16 384 cars are launch-bound: from the second call with the same arguments and a non-NULL stream the
  * tick is replayed from a CUDA graph captured once (same kernels, same order, bit-identical results; self.steps
  * lives in a device counter).  ftgp_release_graphs() drops the cached graphs. */

@@ -1226,10 +1226,10 @@ int fto_constraint_problem(const fto_model* m, const fto_track* t, const double*
  * meshes cannot be restated without the library): a chassis hull vertex of car A that lies inside the bounding box of
  * car B's chassis hull (in B's frame) gives one condim-3 contact, normal = B's box face of least penetration pointing
  * out of B, dist = -penetration, point = midway, mu = 1, default solref / solimp, pyramidal rows J = J_A(p) - J_B(p).
- * Not used by the product yet: ground work for the coupled solve, tested on the CPU.
+ * The product's counterpart is csrc/mushr_world.cuh (per-car block-arrow factors + Woodbury over the car-car rows).
  * ================================================================================================================== */
 #define WMAXCARS 8
-#define WMAXCC 32                       /* car-car contacts per world */
+#define WMAXCC 16                       /* car-car contacts per world (framework rule, same cap in the product) */
 
 typedef struct {
     int nv, n;

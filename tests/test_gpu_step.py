@@ -44,7 +44,7 @@ def test_single_step_parity_1e5(ft, oracle):
     _load(fleet, Q, V, W, U)
     # open ground (no walls): pure MuJoCo-restated dynamics
     ft._lib.check(fleet.lib.ftgp_step(None, fleet.qpos.data_ptr(), fleet.qvel.data_ptr(), fleet.warm.data_ptr(),
-                                      fleet.ctrl.data_ptr(), None, None, n, 1, fleet.status.data_ptr(), 0, fleet._s), "ftgp_step")
+                                      fleet.ctrl.data_ptr(), None, None, n, 1, 1, fleet.status.data_ptr(), 0, fleet._s), "ftgp_step")
     fleet.sync()
     info = model.step_n(None, Q, V, W, U)
     np.testing.assert_allclose(fleet.qpos.cpu().numpy(), Q, rtol=1e-5, atol=1e-10)
@@ -69,7 +69,7 @@ def test_trajectory_divergence_over_1000_ticks_is_reported(ft, oracle, capsys):
             U = np.stack([rng.uniform(0.5, 4, n), rng.uniform(-0.5, 0.5, n)], 1)
             fleet.ctrl.copy_(torch.from_numpy(U)); torch.cuda.synchronize()
         ft._lib.check(fleet.lib.ftgp_step(None, fleet.qpos.data_ptr(), fleet.qvel.data_ptr(), fleet.warm.data_ptr(),
-                                          fleet.ctrl.data_ptr(), None, None, n, 1, None, 0, fleet._s), "ftgp_step")
+                                          fleet.ctrl.data_ptr(), None, None, n, 1, 1, None, 0, fleet._s), "ftgp_step")
         model.step_n(None, Q, V, W, U)
         if k % 100 == 99:
             fleet.sync()
@@ -572,3 +572,46 @@ def test_option_bubble_wrap_on_device(ft, oracle, otracks):
             assert np.abs(fleet.qpos.cpu().numpy() - Q).max() < 1e-6
             _load(fleet, Q, V, W, U)
     assert soft > 200
+
+
+def test_car_car_contacts_match_the_oracle_world_solver(ft, oracle, otracks):
+    """BASELINE config 5 physics (f1): worlds of 8 cars on the device; cars that touch are advanced as one coupled
+    Newton problem (csrc/mushr_world.cuh, Woodbury over the per-car factors) and must agree with the oracle's dense world
+    solver (oracle/step.c fto_world_step) to 1e-5 relative per step; worlds whose cars do not touch stay on the fast path."""
+    model = oracle.Model()
+    t = ft.Track.bundled("track")
+    ot = otracks["track"]
+    cpw, nworlds = 8, 24
+    n = cpw * nworlds
+    rng = np.random.default_rng(31)
+    Q = np.zeros((n, 34)); V = np.zeros((n, 29)); W = np.zeros((n, 29)); U = np.zeros((n, 2))
+    for w in range(nworlds):
+        k = int(rng.integers(0, 100)); d = t.path[(k + 1) % 100] - t.path[k]
+        yaw = float(np.arctan2(d[1], d[0]))
+        spacing = 0.19 if w % 3 else 0.6                              # every third world: cars far apart (fast path)
+        for c in range(cpw):
+            x = t.path[k, 0] + np.cos(yaw) * spacing * c; y = t.path[k, 1] + np.sin(yaw) * spacing * c
+            i = w * cpw + c
+            Q[i], V[i], W[i] = model.reset(x, y, yaw + rng.normal(0, 0.05))
+            Q[i, 2] = rng.uniform(0, 0.004)
+            U[i] = [max(0.0, 3.0 - 0.4 * c), rng.normal(0, 0.1)]
+    fleet = ft.Fleet(t, n, cars_per_world=cpw)
+    _load(fleet, Q, V, W, U)
+    ncc_total = coupled = 0
+    for k in range(150):
+        fleet.step(1)
+        for w in range(nworlds):
+            s = slice(w * cpw, (w + 1) * cpw)
+            q, v, wm = Q[s].copy(), V[s].copy(), W[s].copy()
+            _, info = model.world_step(ot, q, v, wm, U[s])
+            Q[s], V[s], W[s] = q, v, wm
+            ncc_total += int(info[2])
+        fleet.sync()
+        gq, gv = fleet.qpos.cpu().numpy(), fleet.qvel.cpu().numpy()
+        np.testing.assert_allclose(gq, Q, rtol=1e-5, atol=1e-8, err_msg=f"tick {k}")
+        np.testing.assert_allclose(gv, V, rtol=1e-5, atol=1e-6, err_msg=f"tick {k}")
+        coupled += int(((fleet.status.cpu().numpy() >> 9) & 1).sum())
+        _load(fleet, Q, V, W, U)                                       # lock-step: one-step comparisons
+    assert ncc_total > 500 and coupled > 500
+    far = np.arange(n).reshape(nworlds, cpw)[::3].ravel()
+    assert ((fleet.status.cpu().numpy()[far] >> 9) & 1).sum() == 0    # the spread-out worlds never left the fast path

@@ -739,3 +739,76 @@ def test_quad_kernel_bubble_wrap_softener_contacts_match_oracle(model, otracks, 
     finally:
         host_quad_kernel.hq_set_bubble_wrap(0)
         host_quad_kernel.hq_set_walls(None, None, 0, 0, 1.0, 1.0)
+
+
+@pytest.fixture(scope="module")
+def host_world_kernel():
+    """The product's world step (csrc/mushr_world.cuh: per-car block-arrow factors + Woodbury over the car-car rows)
+    compiled for the host."""
+    src = os.path.join(ROOT, "tests", "host_harness", "world_host.cpp")
+    out = os.path.join(ROOT, "tests", "host_harness", "libworld_host.so")
+    deps = [src] + [os.path.join(ROOT, "ft_grandprix_b200", "csrc", f) for f in ("mushr_world.cuh", "mushr_step_quad.cuh", "mushr_step.cuh", "mushr_consts.h", "mushr_mesh.h", "hfield_contact.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-o", out, src])
+    lib = C.CDLL(out)
+    lib.hw_world_step.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p]
+    lib.hw_world_has_contact.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    return lib
+
+
+def test_product_world_step_matches_the_oracle_world_solver(model, host_world_kernel):
+    """BASELINE config 5 physics (f1): cars of one world that touch are ONE Newton problem (one direction, one step length,
+    one stopping rule).  The product solves it from the per-car block-arrow factors with the Woodbury identity; the oracle
+    with a dense Cholesky over 29 N dofs.  Same contact definition, independent code: trajectories of pile-ups of 2..6
+    cars agree to 1e-9 per step, with identical Newton iteration counts and contact counts."""
+    rng = np.random.default_rng(21)
+    total_cc = 0
+    for ncars, steps in ((2, 120), (3, 100), (6, 80)):
+        Q = np.zeros((ncars, 34)); V = np.zeros((ncars, 29)); W = np.zeros((ncars, 29)); U = np.zeros((ncars, 2))
+        for c in range(ncars):                                            # a queue of cars; the rear ones drive into the front ones
+            Q[c], V[c], W[c] = model.reset(10.0 + 0.19 * c + rng.normal(0, 0.005), -10.0 + rng.normal(0, 0.01), rng.normal(0, 0.08))
+            # (cars spawned at exactly the same height and level have hull vertices exactly ON the other car's box faces:
+            # inside / outside is then a matter of the last bit; give every car its own height and a small tilt)
+            Q[c, 2] = rng.uniform(0.0, 0.004)
+            Q[c, 3:7] += rng.normal(0, 0.01, 4); Q[c, 3:7] /= np.linalg.norm(Q[c, 3:7])
+            U[c] = [max(0.0, 3.0 - 0.8 * c), rng.normal(0, 0.1)]
+        worst = 0.0
+        for k in range(steps):
+            Qh, Vh, Wh = Q.copy(), V.copy(), W.copy()
+            info = np.zeros(4, dtype=np.int32)
+            assert host_world_kernel.hw_world_step(P(Qh), P(Vh), P(Wh), P(U), ncars, None, P(info)) == 0
+            flagged = host_world_kernel.hw_world_has_contact(P(Q), ncars, None)
+            _, oi = model.world_step(None, Q, V, W, U)
+            assert info[1] == oi[2], (ncars, k, info, oi)                # car-car contacts
+            assert flagged == (oi[2] > 0)                                  # the cheap pre-test agrees with the contact list
+            assert info[0] == oi[0], (ncars, k, info, oi)                # Newton iterations
+            err = max(np.abs(Qh - Q).max(), np.abs(Vh - V).max() * 1e-2, np.abs(Wh - W).max() * 1e-4)
+            worst = max(worst, err)
+            assert err < 1e-9, (ncars, k, err, oi)
+            total_cc += int(oi[2])
+    assert total_cc > 200
+
+
+def test_product_world_step_without_contacts_and_with_shadowed_cars(model, host_world_kernel):
+    """a world of distant cars == the oracle's world step (shared line search, no coupling rows); shadowed cars are passed through"""
+    Q = np.zeros((4, 34)); V = np.zeros((4, 29)); W = np.zeros((4, 29))
+    for c in range(4):
+        Q[c], V[c], W[c] = model.reset(10.0 + 2.0 * c, -10.0, 0.3 * c)
+    U = np.array([[2.0, 0.1], [1.0, -0.2], [3.0, 0.0], [0.0, 0.0]])
+    for k in range(60):
+        Qh, Vh, Wh = Q.copy(), V.copy(), W.copy()
+        info = np.zeros(4, dtype=np.int32)
+        host_world_kernel.hw_world_step(P(Qh), P(Vh), P(Wh), P(U), 4, None, P(info))
+        model.world_step(None, Q, V, W, U)
+        assert info[1] == 0 and np.abs(Qh - Q).max() < 1e-10 and np.abs(Vh - V).max() < 1e-8
+    Q = np.zeros((2, 34)); V = np.zeros((2, 29)); W = np.zeros((2, 29))
+    Q[0], V[0], W[0] = model.reset(10.0, -10.0, 0.0)
+    Q[1], V[1], W[1] = model.reset(10.17, -10.01, 0.1)
+    U = np.array([[2.0, 0.0], [0.0, 0.0]])
+    sh = np.array([0, 1], dtype=np.uint8)
+    for k in range(60):
+        Qh, Vh, Wh = Q.copy(), V.copy(), W.copy()
+        info = np.zeros(4, dtype=np.int32)
+        host_world_kernel.hw_world_step(P(Qh), P(Vh), P(Wh), P(U), 2, P(sh), P(info))
+        _, oi = model.world_step(None, Q, V, W, U, shadowed=[0, 1])
+        assert info[1] == 0 and oi[2] == 0 and np.abs(Qh - Q).max() < 1e-10
