@@ -12,8 +12,9 @@ One "step" = one pass of the hot path over the whole fleet:
   workload step  : vehicle step only, 65,536 cars
   workload episode (BASELINE config 4): 1,048,576 cars IN TOTAL over the N ranks (strong scaling) on circle /
                  small-circle alternating by world index, full tick, lap statistics gathered once at the end
-  workload race  (BASELINE config 5, partial): 32,768 worlds x 8 cars IN TOTAL on track.png's start grid, the cars
-                 see each other's lidar cylinders and are ranked per world; car-car contacts are NOT generated
+  workload race  (BASELINE config 5): 32,768 worlds x 8 cars IN TOTAL on track.png's start grid; the cars of a world see
+                 each other (lidar cylinder, chassis mesh, wheels), collide with each other (worlds whose cars touch are
+                 advanced as one coupled Newton problem) and are ranked per world
 Cars are sharded over the N ranks with no collective on the step path (weak scaling: the per-GPU
 fleet is fixed); only the final timing / stats are gathered.
 
@@ -519,9 +520,8 @@ def run_episode(args, kind="episode"):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = ft._lib.load()
     if kind == "race":
-        # BASELINE config 5 (without car-car contacts, which this round does not generate): worlds of 8 cars on the
-        # reference start grid of track.png (custom.py:1232-1245), drivers alternating nidc / fast as in
-        # template/cars/cars.json; the cars see each other's lidar cylinders and are ranked per world
+        # BASELINE config 5: worlds of 8 cars on the reference start grid of track.png (custom.py:1232-1245), drivers
+        # alternating nidc / fast as in template/cars/cars.json; the cars see and hit each other and are ranked per world
         cpw, tracks = 8, [ft.Track.bundled("track")]
         nworlds = args.cars // cpw
         race = ShardedRace(nworlds, cpw, 1, lambda n, tid, first: ft.Fleet(Geometry(tracks, device=local), n, cars_per_world=cpw,
@@ -624,7 +624,7 @@ def run_episode(args, kind="episode"):
             "config": {"workload": (f"sharded episode, {nworlds} cars in total on circle/small-circle alternating by world index, "
                                     f"full tick, stats gathered once (BASELINE config 4)") if kind == "episode" else
                                    (f"race worlds, {nworlds} worlds x 8 cars in total on track.png, start grid, nidc/fast alternating, cars see "
-                                    f"each other's lidar cylinders, per-world ranking; NO car-car contacts (BASELINE config 5, partial)"),
+                                    f"and hit each other (coupled world solve for touching cars), per-world ranking (BASELINE config 5)"),
                        "cars_total": ncars_total,
                        "cars_per_gpu": n, "beams": 90, "driver": "nidc (device)",
                        "l2": "fleet state per GPU (>= 190 MB at 8 GPUs) exceeds the 126 MB L2", "timing": "CUDA events around the K ticks; max over ranks",
@@ -640,7 +640,8 @@ def run_episode(args, kind="episode"):
             "episode": {"gather_ms": gather_ms, "stats_rows": int(stats.shape[0]), "stats_bytes": int(stats.numel() * 4),
                         "laps_max": int(laps.max()), "ticks": ticks_max, "to_completion": full, "lap_target": args.lap_target,
                         "finished_cars": int(stats[:, STAT_FIELDS.index("finished")].sum()) if "finished" in STAT_FIELDS else None,
-                        "cars_moved_5cm_this_rank": int(((fleet.qpos[:, :2] - xy0).norm(dim=1) > 0.05).sum())}}
+                        "cars_moved_5cm_this_rank": int(((fleet.qpos[:, :2] - xy0).norm(dim=1) > 0.05).sum()),
+                        "cars_in_coupled_worlds_last_tick_this_rank": int(((fleet.status >> 9) & 1).sum())}}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -21,7 +21,7 @@ for graphs in (0, 1):
         eager.sync()
         out = []
         for name in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "status"):
-            a = getattr(part, name).double(); b = getattr(whole, name)[:2048].double(); c = getattr(eager, name).double()
+            a = getattr(part, name).double().reshape(2048, -1); b = getattr(whole, name)[:2048].double().reshape(2048, -1); c = getattr(eager, name).double().reshape(2048, -1)
             out.append(f"{name}: part-whole {int((a != b).any(1).sum())} cars max {float((a - b).abs().max()):.2e}; part-eager {int((a != c).any(1).sum())} cars")
         print(f"graphs={graphs} ticks={ticks}: " + " | ".join(out), flush=True)
         bad = (part.qpos != whole.qpos[:2048]).any(1).nonzero().flatten()[:5].tolist()
