@@ -608,12 +608,20 @@ def run_episode(args, kind="episode"):
         fleet.sync_readback()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    tt = torch.tensor([dev_ms, e2e_ms, float(launches), gather_ms, float(ticks_done)], dtype=torch.float64, device=fleet.device)
+    # the same with the lap state only (what an episode's consumer reads per tick; the ranges stay on the device for the drivers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fleet.tick_readback(None, lap_h)
+        fleet.sync_readback()
+    barrier()
+    e2e_lap_ms = (time.perf_counter() - t0) * 1e3
+    tt = torch.tensor([dev_ms, e2e_ms, float(launches), gather_ms, float(ticks_done), e2e_lap_ms], dtype=torch.float64, device=fleet.device)
     cs = torch.tensor([car_steps], dtype=torch.float64, device=fleet.device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cs, op=dist.ReduceOp.SUM)
-    dev_ms, e2e_ms, launches, gather_ms, ticks_max = float(tt[0]), float(tt[1]), int(tt[2]), float(tt[3]), int(tt[4])
+    dev_ms, e2e_ms, launches, gather_ms, ticks_max, e2e_lap_ms = float(tt[0]), float(tt[1]), int(tt[2]), float(tt[3]), int(tt[4]), float(tt[5])
     value = float(cs[0]) / (dev_ms * 1e-3)
     peak, peak_src = peaks()
     achieved = value * BYTES["tick"] / 1e9
@@ -635,7 +643,9 @@ def run_episode(args, kind="episode"):
                          "note": "latency/issue-bound path: algorithmic HBM traffic is far below peak by construction (SURVEY 8d)"},
             "e2e": {"value": ncars_total * e2e_steps / (e2e_ms * 1e-3), "unit": "car-steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": n * 90 * 4 + fleet.lap.numel() * 4, "steps": e2e_steps,
-                    "how": "Fleet.tick_readback: ranges and lap state to pinned host memory every tick (host waits for them), wall clock"},
+                    "how": "Fleet.tick_readback: ranges and lap state to pinned host memory every tick (host waits for them), wall clock",
+                    "lap_state_only": {"value": ncars_total * e2e_steps / (e2e_lap_ms * 1e-3), "d2h_bytes_per_step": fleet.lap.numel() * 4,
+                                       "how": "Fleet.tick_readback(None, lap_host): only the lap state crosses PCIe"}},
             "gpu_launches": launches, "clocks": clocks, "rays_per_s": value * 90,
             "episode": {"gather_ms": gather_ms, "stats_rows": int(stats.shape[0]), "stats_bytes": int(stats.numel() * 4),
                         "laps_max": int(laps.max()), "ticks": ticks_max, "to_completion": full, "lap_target": args.lap_target,

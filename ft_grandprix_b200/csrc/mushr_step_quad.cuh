@@ -1030,7 +1030,9 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
     st.ww = 0; st.nch = 0;
     info.ncon_wall = 0; info.ncon_ground = 0;
     // (gate: lane k looks at the chunk under corner k of the car's bounding square; most cars are nowhere near a wall)
-    const bool wall_on = walls.enabled() && qd.any(walls.enabled() && walls.near_corner(p1[0], p1[1], CAR_BOUND, w));
+    // NB the vote is a warp-wide collective: EVERY quad takes part, also one whose car has no walls (a shadowed car)
+    const bool near_wall = qd.any(walls.enabled() && walls.near_corner(p1[0], p1[1], CAR_BOUND, w));
+    const bool wall_on = walls.enabled() && near_wall;
     if (qd.wany(wall_on)) {
         if (wall_on) {
             const double wsz[3] = {WS0, WS1, WS2}, ssz[1] = {MUSHR_SOFTENER_RADIUS};
@@ -1235,8 +1237,17 @@ FT_HD void quad_resume(const Q& qd, QChassis& ch, QState& st, StepInfo& info, co
 // ---- the step -----------------------------------------------------------------------------------------------------
 // live = false: a padding quad (it re-does the last car so that it can take part in the collectives, and stores
 // nothing to global memory)
+// Out of line on the device: the first launch and the continuation kernel of the staged solve then run the SAME machine
+// code, so a car that is suspended and resumed gets bit-identical results to one that converges in one launch (with the
+// step inlined into each kernel the compiler contracted some multiply-adds differently in the two copies: 1e-15
+// differences between a 6,144-car fleet (staged) and its 2,048-car shards (unstaged)).
+#if defined(__CUDACC__)
+#define FT_STEP __host__ __device__ __noinline__
+#else
+#define FT_STEP inline
+#endif
 template <class Q, class WallFn>
-FT_HDN bool step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, double* qvel, double* warm, const double* ctrl,
+FT_STEP bool step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, double* qvel, double* warm, const double* ctrl,
                           const WallFn& walls, bool live, StepInfo& info, const QStage& stage) {
     const int w = qd.lane();
     const bool fr = front(w);

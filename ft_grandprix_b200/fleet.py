@@ -219,8 +219,10 @@ class Fleet:
         _lib.check(self.lib.ftgp_tick(C.byref(a), int(nticks), self._s), "ftgp_tick")
         self.steps += int(nticks)
 
-    def tick_readback(self, ranges_host, lap_host):
-        """One iteration of the physics loop with this tick's ranges and lap state delivered to pinned host buffers,
+    def tick_readback(self, ranges_host, lap_host, cars=None):
+        """One iteration of the physics loop with this tick's ranges and lap state delivered to pinned host buffers
+        (ranges_host = None: lap state only; cars = (lo, hi): only that slice of the fleet's ranges, e.g. the cars a host
+        driver or a viewer is interested in -- at 1 M cars the full ranges tensor is 94 % of the per-tick PCIe traffic),
         the copies overlapped with the kernels that do not touch those arrays: the lap state leaves right after the
         lap kernel, the ranges right after the lidar kernel (the vehicle step runs meanwhile), and only the NEXT
         tick's lidar / lap kernels wait for the copies.  Call sync_readback() before reading the host buffers."""
@@ -236,7 +238,8 @@ class Fleet:
             self.lap_update()
             lap_ready.record(s)
             self.drive()
-            s.wait_event(ranges_copied)              # ... and of the ranges
+            if ranges_host is not None:
+                s.wait_event(ranges_copied)          # ... and of the ranges
             self.lidar()
             ranges_ready.record(s)
             self.step(1)
@@ -244,9 +247,11 @@ class Fleet:
             c.wait_event(lap_ready)
             lap_host.copy_(self.lap, non_blocking=True)
             lap_copied.record(c)
-            c.wait_event(ranges_ready)
-            ranges_host.copy_(self.ranges, non_blocking=True)
-            ranges_copied.record(c)
+            if ranges_host is not None:
+                c.wait_event(ranges_ready)
+                src = self.ranges if cars is None else self.ranges[cars[0]:cars[1]]
+                ranges_host.copy_(src, non_blocking=True)
+                ranges_copied.record(c)
 
     def sync_readback(self):
         self.stream.synchronize()

@@ -164,6 +164,8 @@ struct WarpQuadHost {
 
 // NQ cars stepped together as one warp / CTA with a staged solve: k1 Newton rounds, then the suspended cars (alone or
 // with finished neighbours idling as dead quads) to convergence.  Returns the number of suspensions.
+static unsigned g_shadow_mask = 0;      // bit q: quad q of the host "warp" steps a shadowed car (no walls)
+extern "C" void hq_set_shadow_mask(unsigned m) { g_shadow_mask = m; }
 template <int NQ_>
 static int warp_step(double* qpos, double* qvel, double* warm, const double* ctrl, int* info4, int k1) {
     WarpHostShared sh; sh.bar.nthreads = 4 * NQ_; sh.nq = NQ_;
@@ -177,6 +179,8 @@ static int warp_step(double* qpos, double* qvel, double* warm, const double* ctr
             WarpQuadHost<NQ_> q; q.s = &sh; q.tid = tid; q.w = tid & 3; q.quad = tid >> 2;
             const int i = q.quad;
             StepInfo si;
+            QHfWalls g_walls = ::g_walls;                                  // (shadows the global: this quad's walls)
+            if (g_shadow_mask >> i & 1u) g_walls.on = false;
             bool sus = step_car_quad(q, g_mc, qpos + i * NQ, qvel + i * NV, warm + i * NV, ctrl + 2 * i, g_walls, true, si,
                                      QStage{k1, false, recs.data() + (size_t)i * QREC_DOUBLES});
             q.sync();

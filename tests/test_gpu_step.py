@@ -240,6 +240,18 @@ def test_tick_readback_equals_tick_and_delivers_host_copies(ft):
     assert torch.equal(lap_h, a.lap.cpu())               # the lap state of the last tick (written by its lap kernel only)
     for k in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "times", "status"):
         assert torch.equal(getattr(a, k), getattr(b, k)), k
+    # delivery options: lap state only / a slice of the fleet's ranges (the rest stays on the device for the drivers)
+    sub_h = torch.empty(100, 90, dtype=torch.float32).pin_memory()
+    for k in range(5):
+        a.tick(1)
+        if k % 2:
+            b.tick_readback(None, lap_h)
+        else:
+            b.tick_readback(sub_h, lap_h, cars=(300, 400))
+        b.sync_readback()
+    a.sync()
+    assert torch.equal(sub_h, b.ranges[300:400].cpu()) and torch.equal(lap_h, a.lap.cpu())
+    assert torch.equal(a.qpos, b.qpos) and torch.equal(a.ranges, b.ranges)
 
 
 def test_two_fleets_on_two_streams_do_not_share_scratch(ft):
@@ -598,7 +610,7 @@ def test_car_car_contacts_match_the_oracle_world_solver(ft, oracle, otracks):
     fleet = ft.Fleet(t, n, cars_per_world=cpw)
     _load(fleet, Q, V, W, U)
     ncc_total = coupled = 0
-    for k in range(150):
+    for k in range(100):
         fleet.step(1)
         for w in range(nworlds):
             s = slice(w * cpw, (w + 1) * cpw)
@@ -612,6 +624,6 @@ def test_car_car_contacts_match_the_oracle_world_solver(ft, oracle, otracks):
         np.testing.assert_allclose(gv, V, rtol=1e-5, atol=1e-6, err_msg=f"tick {k}")
         coupled += int(((fleet.status.cpu().numpy() >> 9) & 1).sum())
         _load(fleet, Q, V, W, U)                                       # lock-step: one-step comparisons
-    assert ncc_total > 500 and coupled > 500
+    assert ncc_total > 300 and coupled > 300
     far = np.arange(n).reshape(nworlds, cpw)[::3].ravel()
     assert ((fleet.status.cpu().numpy()[far] >> 9) & 1).sum() == 0    # the spread-out worlds never left the fast path

@@ -812,3 +812,15 @@ def test_product_world_step_without_contacts_and_with_shadowed_cars(model, host_
         host_world_kernel.hw_world_step(P(Qh), P(Vh), P(Wh), P(U), 2, P(sh), P(info))
         _, oi = model.world_step(None, Q, V, W, U, shadowed=[0, 1])
         assert info[1] == 0 and oi[2] == 0 and np.abs(Qh - Q).max() < 1e-10
+
+
+def test_warp_of_quads_with_walls_and_shadowed_cars_is_deadlock_free(host_quad_kernel):
+    """Four quads as one warp (every collective a barrier over all 16 threads), cars sliding into walls, option
+    bubble_wrap on, some quads stepping shadowed cars (no walls): a collective reached only by the quads with walls hangs
+    here -- in round 2 exactly that hung a B200 until the job's time limit.  Results equal the cars stepped alone."""
+    import sys
+    script = os.path.join(ROOT, "tests", "host_harness", "warp_walls_check.py")
+    lib = os.path.join(ROOT, "tests", "host_harness", "libstep_quad_host.so")
+    out = subprocess.run([sys.executable, script, ROOT, lib, "160"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.startswith("ok") and int(out.stdout.split()[1]) > 50          # wall contacts really happened
