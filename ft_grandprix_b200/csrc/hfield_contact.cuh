@@ -56,6 +56,13 @@ FT_HD double hf_bit(const uint32_t* m, int ncol, int r, int c) {      // vertex 
     return (double)((m[b >> 5] >> (b & 31)) & 1u) * HF_ELEV;
 }
 
+// n (<= 21) consecutive vertex bits of hfield row r starting at column c (two mask words, one shift)
+FT_HD uint32_t hf_row_bits(const uint32_t* m, int ncol, int r, int c, int n) {
+    const int b = r * ncol + c, w = b >> 5, sh = b & 31;
+    const uint64_t two = ((uint64_t)m[w + 1 < 13 ? w + 1 : 12] << 32) | m[w];
+    return (uint32_t)(two >> sh) & ((1u << n) - 1u);
+}
+
 // Can anything within `radius` of (x, y) touch a wall?  Corner k (0..3) of the square selects one of the (at most four)
 // chunks under it; true if that chunk has raised vertices whose cells (one cell of slope around them) reach the square.
 // The four corners together are a conservative gate for every probe below.
@@ -90,7 +97,9 @@ FT_HDNI bool hf_vertex_probe(const HfView& hv, const double* p, QWallHit& h) {
     int cc = (int)floor(u), rr = (int)floor(vv);
     cc = cc < 0 ? 0 : (cc > ncol - 2 ? ncol - 2 : cc); rr = rr < 0 ? 0 : (rr > nrow - 2 ? nrow - 2 : rr);
     const double fu = u - cc, fv = vv - rr;
-    const double z00 = hf_bit(m, ncol, rr, cc), z10 = hf_bit(m, ncol, rr, cc + 1), z01 = hf_bit(m, ncol, rr + 1, cc), z11 = hf_bit(m, ncol, rr + 1, cc + 1);
+    const uint32_t la = hf_row_bits(m, ncol, rr, cc, 2), lb = hf_row_bits(m, ncol, rr + 1, cc, 2);
+    if ((la | lb) == 0) return false;                                        // flat floor cell: below the ground plane
+    const double z00 = (la & 1u) * HF_ELEV, z10 = (la >> 1) * HF_ELEV, z01 = (lb & 1u) * HF_ELEV, z11 = (lb >> 1) * HF_ELEV;
     double gx, gy, z;
     if (fv <= fu) { gx = (z10 - z00) / dx; gy = (z11 - z10) / dy; z = z00 + (z10 - z00) * fu + (z11 - z10) * fv; }
     else { gx = (z11 - z01) / dx; gy = (z01 - z00) / dy; z = z00 + (z11 - z01) * fu + (z01 - z00) * fv; }
@@ -152,11 +161,15 @@ FT_HDNI bool hf_convex(const HfView& hv, int kind, const double* size, double bo
             r0 = r0 < rmin - 1 ? rmin - 1 : r0; r0 = r0 < 0 ? 0 : r0;
             c1 = c1 > cmax ? cmax : c1; c1 = c1 > ncol - 2 ? ncol - 2 : c1;
             r1 = r1 > rmax ? rmax : r1; r1 = r1 > nrow - 2 ? nrow - 2 : r1;
-            for (int rr = r0; rr <= r1; rr++)
+            if (c0 > c1) continue;
+            for (int rr = r0; rr <= r1; rr++) {
+                // vertex bits of rows rr and rr + 1 over columns c0 .. c1 + 1: two loads per row instead of four per cell
+                const uint32_t la = hf_row_bits(m, ncol, rr, c0, c1 - c0 + 2), lb = hf_row_bits(m, ncol, rr + 1, c0, c1 - c0 + 2);
+                if ((la | lb) == 0) continue;
                 for (int cc = c0; cc <= c1; cc++) {
-                    const double z00 = hf_bit(m, ncol, rr, cc), z10 = hf_bit(m, ncol, rr, cc + 1), z01 = hf_bit(m, ncol, rr + 1, cc),
-                                 z11 = hf_bit(m, ncol, rr + 1, cc + 1);
-                    if (z00 + z10 + z01 + z11 == 0) continue;
+                    const uint32_t qa = (la >> (cc - c0)) & 3u, qb = (lb >> (cc - c0)) & 3u;
+                    if ((qa | qb) == 0) continue;
+                    const double z00 = (qa & 1u) * HF_ELEV, z10 = (qa >> 1) * HF_ELEV, z01 = (qb & 1u) * HF_ELEV, z11 = (qb >> 1) * HF_ELEV;
                     for (int tri = 0; tri < 2; tri++) {
                         double gx, gy;
                         if (tri == 0) { if (z00 + z10 + z11 == 0) continue; gx = (z10 - z00) / dx; gy = (z11 - z10) / dy; }
@@ -176,6 +189,7 @@ FT_HDNI bool hf_convex(const HfView& hv, int kind, const double* size, double bo
                         bp[0] = sp[0]; bp[1] = sp[1]; bp[2] = sp[2];
                     }
                 }
+            }
         }
     if (found) hf_frame(h, bp);
     return found;

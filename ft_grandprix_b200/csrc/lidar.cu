@@ -523,7 +523,10 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                         float ta = fmaxf(L.t0, L.tz0), tb = fminf(L.t1, L.tend);
                         if (ta <= tb) {
                             const float za0 = L.lz + ta * L.dz;
-                            L.floor_reach = fminf(za0, za0 + (tb - ta) * L.dz) <= 0.f;
+                            // (a ray that ENDS on the base plane -- it started below the ground plane, so nothing stops it before
+                            // z = -0.1 -- reaches height 0 only up to fp32 rounding: without the margin the flat floor cells were
+                            // sometimes not candidates and the ray was reported as a miss where mj_rayHfield hits the floor)
+                            L.floor_reach = fminf(za0, za0 + (tb - ta) * L.dz) <= 1e-5f;
                             if (!L.floor_reach) {
                                 // only cells with a wall vertex can be hit: clip to the chunk's wall bounding box (+1 cell)
                                 const uint32_t bb = m[14];

@@ -789,7 +789,7 @@ FT_HDN void newton_direction(const Rows& r, const Arrow& M, Solver& s, Arrow& H)
 // ========================================================================================================
 // the step
 // ========================================================================================================
-struct StepInfo { int iters, ncon_wheel, ncon_wall, reset, ncon_ground; };   // ncon_wall: wheels + chassis + lidar cylinder against walls
+struct StepInfo { int iters, ncon_wheel, ncon_wall, reset, ncon_ground, near_wall; };   // ncon_wall: wheels + chassis + lidar cylinder against walls
 
 FT_HD bool bad_value(double x) { return !(x <= 1e10 && x >= -1e10); }
 

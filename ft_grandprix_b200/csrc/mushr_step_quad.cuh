@@ -162,6 +162,154 @@ FT_HD void wc_dots(const Q& qd, const double* xr, const double* xc, double* d3) 
     }
 }
 
+
+// ---- rare contacts, out of line ------------------------------------------------------------------------------------
+// The contacts of the car body's geoms and the chain contacts (a wheel / softener against a wall) exist for a few per cent
+// of the cars.  Their code is kept OUT OF LINE (one call behind a branch) so that the Newton loop every car runs stays
+// small: with it inlined the loop no longer fitted the instruction cache (stall_no_inst 0.7 -> 4.1 cycles per issue, first
+// launch 0.93 -> 1.99 ms; profiles/ncu_summary_r11.md).  The helpers take the vectors from shared memory themselves and
+// return small structs by value, so that no register array of the caller has its address taken.
+#if defined(__CUDACC__)
+#define FT_RARE __host__ __device__ __noinline__
+#else
+#define FT_RARE inline
+#endif
+struct RareRows { double cost, fr[6], fc[NC]; unsigned mask; };
+struct RareHess { double P[21], W[21], B[NC][6]; };
+struct RareVec6 { double v[NC]; };
+struct RareQuad { double q0, q1, q2; };
+
+// cost / forces / active-row mask of the rare rows at the vector X (root part xr[0..5], chain part xc)
+template <class Q>
+FT_RARE RareRows rare_rows(const Q& qd, const QChassis& ch, int nch, int ww, QVec X) {
+    RareRows o;
+    o.cost = 0; o.mask = 0;
+    double xr[6], xc[NC];
+    for (int i = 0; i < 6; i++) { o.fr[i] = 0; xr[i] = qd.C(X.c + i); }
+    for (int l = 0; l < NC; l++) { o.fc[l] = 0; xc[l] = qd.P(X.p + l); }
+    for (int s = 0; s < nch; s++) {                                      // contacts of the car body's geoms: root dofs only
+        double d3[3];
+        for (int a = 0; a < 3; a++) d3[a] = dot6q(ch.J[s][a], xr);
+        const double D = ch.D[s];
+        for (int rr = 0; rr < 4; rr++) {
+            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+            const double jar = d3[0] + sg * d3[ta] - ch.aref[s][rr];
+            if (jar >= 0) continue;
+            o.cost += 0.5 * D * jar * jar;
+            o.mask |= 1u << (QB_CH + 4 * s + rr);
+            const double f = -D * jar;
+            for (int col = 0; col < 6; col++) o.fr[col] += (ch.J[s][0][col] + sg * ch.J[s][ta][col]) * f;
+        }
+    }
+    for (int c = 0; c < 2; c++) {                                        // the lane's wheel / softener against a wall
+        if (!(ww >> c & 1)) continue;
+        double d3[3];
+        for (int a = 0; a < 3; a++) d3[a] = dot6q(ch.wJ[c][a], xr) + dot6q(ch.wJ[c][a] + 6, xc);
+        for (int rr = 0; rr < 4; rr++) {
+            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+            const double jar = d3[0] + sg * d3[ta] - ch.waref[c][rr];
+            if (jar >= 0) continue;
+            o.cost += 0.5 * ch.wD[c] * jar * jar;
+            o.mask |= 1u << (QB_WW + 4 * c + rr);
+            const double f = -ch.wD[c] * jar;
+            for (int col = 0; col < 6; col++) o.fr[col] += (ch.wJ[c][0][col] + sg * ch.wJ[c][ta][col]) * f;
+            for (int k = 0; k < NC; k++) o.fc[k] += (ch.wJ[c][0][6 + k] + sg * ch.wJ[c][ta][6 + k]) * f;
+        }
+    }
+    return o;
+}
+
+// J' D J of the active rare rows: root block (6 x 6 lower triangle), chain block (lower triangle), border (chain x root)
+FT_RARE RareHess rare_hessian(const QChassis& ch, int nch, int ww, unsigned mask) {
+    RareHess o;
+    for (int i = 0; i < 21; i++) { o.P[i] = 0; o.W[i] = 0; }
+    for (int l = 0; l < NC; l++) for (int j = 0; j < 6; j++) o.B[l][j] = 0;
+    for (int s = 0; s < nch; s++) {
+        const double D = ch.D[s];
+        for (int rr = 0; rr < 4; rr++) {
+            if (!(mask >> (QB_CH + 4 * s + rr) & 1u)) continue;
+            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+            double Jr[6];
+            for (int col = 0; col < 6; col++) Jr[col] = ch.J[s][0][col] + sg * ch.J[s][ta][col];
+            for (int i = 0; i < 6; i++) { const double di = D * Jr[i]; for (int j = 0; j <= i; j++) o.P[tri(i, j)] += di * Jr[j]; }
+        }
+    }
+    for (int c = 0; c < 2; c++) {
+        if (!(ww >> c & 1)) continue;
+        for (int rr = 0; rr < 4; rr++) {
+            if (!(mask >> (QB_WW + 4 * c + rr) & 1u)) continue;
+            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+            double Jr[12];
+            for (int col = 0; col < 12; col++) Jr[col] = ch.wJ[c][0][col] + sg * ch.wJ[c][ta][col];
+            for (int i = 0; i < 6; i++) { const double di = ch.wD[c] * Jr[i]; for (int j = 0; j <= i; j++) o.P[tri(i, j)] += di * Jr[j]; }
+            for (int l = 0; l < NC; l++) {
+                const double dl = ch.wD[c] * Jr[6 + l];
+                for (int k = 0; k <= l; k++) o.W[tri(l, k)] += dl * Jr[6 + k];
+                for (int j = 0; j < 6; j++) o.B[l][j] += dl * Jr[j];
+            }
+        }
+    }
+    return o;
+}
+
+// the chain contacts' share of (border of H) x_r, x_r = the first six entries of the root part of V
+template <class Q>
+FT_RARE RareVec6 rare_border(const Q& qd, const QChassis& ch, int ww, unsigned mask, const double* xr6) {
+    RareVec6 o;
+    for (int l = 0; l < NC; l++) o.v[l] = 0;
+    for (int c = 0; c < 2; c++) {
+        if (!(ww >> c & 1)) continue;
+        for (int rr = 0; rr < 4; rr++) {
+            if (!(mask >> (QB_WW + 4 * c + rr) & 1u)) continue;
+            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+            double sacc = 0;
+            for (int col = 0; col < 6; col++) sacc += (ch.wJ[c][0][col] + sg * ch.wJ[c][ta][col]) * xr6[col];
+            sacc *= ch.wD[c];
+            for (int l = 0; l < NC; l++) o.v[l] += (ch.wJ[c][0][6 + l] + sg * ch.wJ[c][ta][6 + l]) * sacc;
+        }
+    }
+    return o;
+}
+
+// line search: J x and J s of the rare contacts (x = VX, s = VS in shared memory) ...
+template <class Q>
+FT_RARE void rare_ls_init(const Q& qd, QChassis& ch, int nch, int ww) {
+    double xr[6], xc[NC], sr[6], sc[NC];
+    for (int i = 0; i < 6; i++) { xr[i] = qd.C(VX.c + i); sr[i] = qd.C(VS.c + i); }
+    for (int l = 0; l < NC; l++) { xc[l] = qd.P(VX.p + l); sc[l] = qd.P(VS.p + l); }
+    for (int s = 0; s < nch; s++)
+        for (int a = 0; a < 3; a++) { ch.dx[s][a] = dot6q(ch.J[s][a], xr); ch.ds[s][a] = dot6q(ch.J[s][a], sr); }
+    for (int c = 0; c < 2; c++)
+        if (ww >> c & 1)
+            for (int a = 0; a < 3; a++) {
+                ch.wdx[c][a] = dot6q(ch.wJ[c][a], xr) + dot6q(ch.wJ[c][a] + 6, xc);
+                ch.wds[c][a] = dot6q(ch.wJ[c][a], sr) + dot6q(ch.wJ[c][a] + 6, sc);
+            }
+}
+// ... and their share of the cost along the line at alpha
+FT_RARE RareQuad rare_ls(const QChassis& ch, int nch, int ww, double alpha) {
+    RareQuad o;
+    o.q0 = o.q1 = o.q2 = 0;
+    for (int s = 0; s < nch; s++) {
+        const double D = ch.D[s];
+        for (int rr = 0; rr < 4; rr++) {
+            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+            const double jar = ch.dx[s][0] + sg * ch.dx[s][ta] - ch.aref[s][rr], jv = ch.ds[s][0] + sg * ch.ds[s][ta];
+            if (jar + alpha * jv < 0) { o.q0 += 0.5 * D * jar * jar; o.q1 += D * jar * jv; o.q2 += 0.5 * D * jv * jv; }
+        }
+    }
+    for (int c = 0; c < 2; c++) {
+        if (!(ww >> c & 1)) continue;
+        const double D = ch.wD[c];
+        for (int rr = 0; rr < 4; rr++) {
+            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
+            const double jar = ch.wdx[c][0] + sg * ch.wdx[c][ta] - ch.waref[c][rr], jv = ch.wds[c][0] + sg * ch.wds[c][ta];
+            if (jar + alpha * jv < 0) { o.q0 += 0.5 * D * jar * jar; o.q1 += D * jar * jv; o.q2 += 0.5 * D * jv * jv; }
+        }
+    }
+    return o;
+}
+
 // ---- cost of this lane's rows at the vector X: forces J^T f into fr (root, lane's share) / fc (chain), zone mask --
 template <class Q>
 FT_QN double rows_eval(const Q& qd, const QChassis& ch, int nch, int ww, QVec X, double* fr, double* fc, unsigned& mask_out) {
@@ -218,34 +366,13 @@ FT_QN double rows_eval(const Q& qd, const QChassis& ch, int nch, int ww, QVec X,
             fc[k] += qd.P(QP_CJ + 3 + k) * F[0] + qd.P(QP_CJ + 9 + k) * F[1] + qd.P(QP_CJ + 15 + k) * F[2];
         }
     }
-    for (int s = 0; s < nch; s++) {                                      // chassis contacts (walls): root dofs only
-        double d3[3];
-        for (int a = 0; a < 3; a++) d3[a] = dot6q(ch.J[s][a], xr);
-        const double D = ch.D[s];
-        for (int rr = 0; rr < 4; rr++) {
-            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-            const double jar = d3[0] + sg * d3[ta] - ch.aref[s][rr];
-            if (jar >= 0) continue;
-            cost += 0.5 * D * jar * jar;
-            mask |= 1u << (QB_CH + 4 * s + rr);
-            const double f = -D * jar;
-            for (int col = 0; col < 6; col++) fr[col] += (ch.J[s][0][col] + sg * ch.J[s][ta][col]) * f;
-        }
-    }
-    for (int c = 0; c < 2; c++) {                                        // the lane's wheel / softener against a wall
-        if (!(ww >> c & 1)) continue;
-        double d3[3];
-        for (int a = 0; a < 3; a++) d3[a] = dot6q(ch.wJ[c][a], xr) + dot6q(ch.wJ[c][a] + 6, xc);
-        for (int rr = 0; rr < 4; rr++) {
-            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-            const double jar = d3[0] + sg * d3[ta] - ch.waref[c][rr];
-            if (jar >= 0) continue;
-            cost += 0.5 * ch.wD[c] * jar * jar;
-            mask |= 1u << (QB_WW + 4 * c + rr);
-            const double f = -ch.wD[c] * jar;
-            for (int col = 0; col < 6; col++) fr[col] += (ch.wJ[c][0][col] + sg * ch.wJ[c][ta][col]) * f;
-            for (int k = 0; k < NC; k++) fc[k] += (ch.wJ[c][0][6 + k] + sg * ch.wJ[c][ta][6 + k]) * f;
-        }
+    if (nch | ww) {                                                      // rare contacts (out of line)
+        const RareRows o = rare_rows(qd, ch, nch, ww, X);
+        cost += o.cost; mask |= o.mask;
+#pragma unroll
+        for (int i = 0; i < 6; i++) fr[i] += o.fr[i];
+#pragma unroll
+        for (int l = 0; l < NC; l++) fc[l] += o.fc[l];
     }
     mask_out = mask;
     return cost;
@@ -368,42 +495,14 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
                 for (int j = 0; j < 6; j++) B[l][j] += J[0][6 + l] * T[0][j] + J[1][6 + l] * T[1][j] + J[2][6 + l] * T[2][j];
             }
         }
-        for (int s = 0; s < st.nch; s++) {
-            const double D = ch.D[s];
-            for (int rr = 0; rr < 4; rr++) {
-                if (!(mask >> (QB_CH + 4 * s + rr) & 1u)) continue;
-                const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-                double Jr[6];
+        if (st.nch | st.ww) {                                            // rare contacts (out of line)
+            const RareHess o = rare_hessian(ch, st.nch, st.ww, mask);
 #pragma unroll
-                for (int col = 0; col < 6; col++) Jr[col] = ch.J[s][0][col] + sg * ch.J[s][ta][col];
+            for (int i = 0; i < 21; i++) { Pp[i] += o.P[i]; W[i] += o.W[i]; }
 #pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    const double di = D * Jr[i];
+            for (int l = 0; l < NC; l++)
 #pragma unroll
-                    for (int j = 0; j <= i; j++) Pp[tri(i, j)] += di * Jr[j];
-                }
-            }
-        }
-        for (int c = 0; c < 2; c++) {                                    // chain contacts: root block, chain block and border
-            if (!(st.ww >> c & 1)) continue;
-            for (int rr = 0; rr < 4; rr++) {
-                if (!(mask >> (QB_WW + 4 * c + rr) & 1u)) continue;
-                const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-                double Jr[12];
-                for (int col = 0; col < 12; col++) Jr[col] = ch.wJ[c][0][col] + sg * ch.wJ[c][ta][col];
-                for (int i = 0; i < 6; i++) {
-                    const double di = ch.wD[c] * Jr[i];
-                    for (int j = 0; j <= i; j++) Pp[tri(i, j)] += di * Jr[j];
-                }
-#pragma unroll
-                for (int l = 0; l < NC; l++) {
-                    const double dl = ch.wD[c] * Jr[6 + l];
-#pragma unroll
-                    for (int k = 0; k <= l; k++) W[tri(l, k)] += dl * Jr[6 + k];
-#pragma unroll
-                    for (int j = 0; j < 6; j++) B[l][j] += dl * Jr[j];
-                }
-            }
+                for (int j = 0; j < 6; j++) B[l][j] += o.B[l][j];
         }
     }
     // chain block: W = L L^T, diagonal keeps 1 / L_jj
@@ -509,18 +608,10 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
             for (int l = 0; l < 3; l++) t[l] -= qd.P(QP_CJ + 3 + l) * u[0] + qd.P(QP_CJ + 9 + l) * u[1] + qd.P(QP_CJ + 15 + l) * u[2];
         }
         if (mode == 1 && st.ww) {                                        // (the chain contacts' share of the border, as above)
-            for (int c = 0; c < 2; c++) {
-                if (!(st.ww >> c & 1)) continue;
-                for (int rr = 0; rr < 4; rr++) {
-                    if (!(st.mask >> (QB_WW + 4 * c + rr) & 1u)) continue;
-                    const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-                    double sacc = 0;
-                    for (int col = 0; col < 6; col++) sacc += (ch.wJ[c][0][col] + sg * ch.wJ[c][ta][col]) * xr[col];
-                    sacc *= ch.wD[c];
+            const double x6[6] = {xr[0], xr[1], xr[2], xr[3], xr[4], xr[5]};
+            const RareVec6 o = rare_border(qd, ch, st.ww, st.mask, x6);
 #pragma unroll
-                    for (int l = 0; l < NC; l++) t[l] -= (ch.wJ[c][0][6 + l] + sg * ch.wJ[c][ta][6 + l]) * sacc;
-                }
-            }
+            for (int l = 0; l < NC; l++) t[l] -= o.v[l];
         }
 #pragma unroll
         for (int l = 0; l < NC; l++) {
@@ -591,23 +682,7 @@ FT_HD void quad_ls_eval(const Q& qd, const QChassis& ch, int nch, int ww, const 
             if (jar + alpha * jv < 0) { q0 += 0.5 * L.wD * jar * jar; q1 += L.wD * jar * jv; q2 += 0.5 * L.wD * jv * jv; }
         }
     }
-    for (int s = 0; s < nch; s++) {
-        const double D = ch.D[s];
-        for (int rr = 0; rr < 4; rr++) {
-            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-            const double jar = ch.dx[s][0] + sg * ch.dx[s][ta] - ch.aref[s][rr], jv = ch.ds[s][0] + sg * ch.ds[s][ta];
-            if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
-        }
-    }
-    for (int c = 0; c < 2; c++) {
-        if (!(ww >> c & 1)) continue;
-        const double D = ch.wD[c];
-        for (int rr = 0; rr < 4; rr++) {
-            const double sg = (rr & 1) ? -CH_MU : CH_MU; const int ta = 1 + (rr >> 1);
-            const double jar = ch.wdx[c][0] + sg * ch.wdx[c][ta] - ch.waref[c][rr], jv = ch.wds[c][0] + sg * ch.wds[c][ta];
-            if (jar + alpha * jv < 0) { q0 += 0.5 * D * jar * jar; q1 += D * jar * jv; q2 += 0.5 * D * jv * jv; }
-        }
-    }
+    if (nch | ww) { const RareQuad o = rare_ls(ch, nch, ww, alpha); q0 += o.q0; q1 += o.q1; q2 += o.q2; }     // rare contacts (out of line)
     q0 = qd.sum(q0) + L.g0; q1 = qd.sum(q1) + L.g1; q2 = qd.sum(q2) + L.g2;
     pt.alpha = alpha; pt.cost = alpha * alpha * q2 + alpha * q1 + q0;
     pt.d0 = 2 * alpha * q2 + q1; pt.d1 = 2 * q2;
@@ -672,14 +747,7 @@ FT_QN double quad_line_search(const Q& qd, QChassis& ch, const QState& st, doubl
 #pragma unroll
             for (int rr = 0; rr < 4; rr++) { L.wj[rr] = 0; L.wv[rr] = 0; }
         }
-        for (int s = 0; s < st.nch; s++)
-            for (int a = 0; a < 3; a++) { ch.dx[s][a] = dot6q(ch.J[s][a], xr); ch.ds[s][a] = dot6q(ch.J[s][a], sr); }
-        for (int c = 0; c < 2; c++)
-            if (st.ww >> c & 1)
-                for (int a = 0; a < 3; a++) {
-                    ch.wdx[c][a] = dot6q(ch.wJ[c][a], xr) + dot6q(ch.wJ[c][a] + 6, xc);
-                    ch.wds[c][a] = dot6q(ch.wJ[c][a], sr) + dot6q(ch.wJ[c][a] + 6, sc);
-                }
+        if (st.nch | st.ww) rare_ls_init(qd, ch, st.nch, st.ww);        // (reads x and s from shared memory itself)
     }
     const int nch = st.nch, ww = st.ww;
     const double gtol = SOLVER_TOL * LS_TOL * snorm / scale;
@@ -1033,6 +1101,7 @@ FT_QN void quad_prepare(const Q& qd, const ModelConsts& mc, const double* qr, co
     // NB the vote is a warp-wide collective: EVERY quad takes part, also one whose car has no walls (a shadowed car)
     const bool near_wall = qd.any(walls.enabled() && walls.near_corner(p1[0], p1[1], CAR_BOUND, w));
     const bool wall_on = walls.enabled() && near_wall;
+    info.near_wall = wall_on ? 1 : 0;
     if (qd.wany(wall_on)) {
         if (wall_on) {
             const double wsz[3] = {WS0, WS1, WS2}, ssz[1] = {MUSHR_SOFTENER_RADIUS};
@@ -1198,7 +1267,7 @@ FT_HD void quad_suspend(const Q& qd, const QChassis& ch, const QState& st, const
     int* ii = reinterpret_cast<int*>(r4 + 1);
     if (w == 0) {
         r4[0] = st.c0;
-        ii[12] = info.iters; ii[13] = info.ncon_wheel; ii[14] = info.ncon_wall; ii[15] = info.reset; ii[16] = info.ncon_ground;
+        ii[12] = info.iters; ii[13] = info.ncon_wheel; ii[14] = info.ncon_wall; ii[15] = info.reset; ii[16] = info.ncon_ground | (info.near_wall << 8);
     }
     ii[w] = (int)st.mask; ii[4 + w] = st.nch; ii[8 + w] = st.ww;
 }
@@ -1212,7 +1281,7 @@ FT_HD void quad_resume(const Q& qd, QChassis& ch, QState& st, StepInfo& info, co
     st.c0 = r4[0];
     const int* ii = reinterpret_cast<const int*>(r4 + 1);
     st.mask = (unsigned)ii[w]; st.nch = ii[4 + w]; st.ww = ii[8 + w];
-    info.iters = ii[12]; info.ncon_wheel = ii[13]; info.ncon_wall = ii[14]; info.reset = ii[15]; info.ncon_ground = ii[16];
+    info.iters = ii[12]; info.ncon_wheel = ii[13]; info.ncon_wall = ii[14]; info.reset = ii[15]; info.ncon_ground = ii[16] & 0xFF; info.near_wall = ii[16] >> 8;
     const double* r2 = rec + 4 * QP_N;
     {
         int k = 0;
@@ -1237,15 +1306,8 @@ FT_HD void quad_resume(const Q& qd, QChassis& ch, QState& st, StepInfo& info, co
 // ---- the step -----------------------------------------------------------------------------------------------------
 // live = false: a padding quad (it re-does the last car so that it can take part in the collectives, and stores
 // nothing to global memory)
-// Out of line on the device: the first launch and the continuation kernel of the staged solve then run the SAME machine
-// code, so a car that is suspended and resumed gets bit-identical results to one that converges in one launch (with the
-// step inlined into each kernel the compiler contracted some multiply-adds differently in the two copies: 1e-15
-// differences between a 6,144-car fleet (staged) and its 2,048-car shards (unstaged)).
-#if defined(__CUDACC__)
-#define FT_STEP __host__ __device__ __noinline__
-#else
-#define FT_STEP inline
-#endif
+// (inlined into the one kernel that serves both launches of the staged solve, step.cu)
+#define FT_STEP FT_HDN
 template <class Q, class WallFn>
 FT_STEP bool step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, double* qvel, double* warm, const double* ctrl,
                           const WallFn& walls, bool live, StepInfo& info, const QStage& stage) {
@@ -1255,7 +1317,7 @@ FT_STEP bool step_car_quad(const Q& qd, const ModelConsts& mc, double* qpos, dou
     QChassis ch;
     QState st;
     st.cost = 0; st.gauss = 0; st.mask = 0; st.c0 = 0; st.nch = 0; st.ww = 0;
-    info.reset = 0; info.iters = 0; info.ncon_wheel = 0; info.ncon_wall = 0; info.ncon_ground = 0;
+    info.reset = 0; info.iters = 0; info.ncon_wheel = 0; info.ncon_wall = 0; info.ncon_ground = 0; info.near_wall = 0;
     qd.sync();                                                             // previous step's root state is in memory
     if (stage.resume) {
         if (live) quad_resume(qd, ch, st, info, stage.rec);

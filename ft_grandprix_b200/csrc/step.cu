@@ -50,7 +50,7 @@ __device__ __forceinline__ QHfWalls track_walls(const uint32_t* blob, const int3
 }
 __device__ __forceinline__ int status_word(const StepInfo& info, int prev) {
     return (info.iters & 0xFF) | (info.reset ? 0x100 : (prev & 0x100)) | ((info.ncon_wall & 0xFF) << 16) | ((info.ncon_wheel & 0xF) << 24) |
-           ((info.ncon_ground > 7 ? 7 : info.ncon_ground) << 28);
+           ((info.ncon_ground > 7 ? 7 : info.ncon_ground) << 28) | (info.near_wall ? 0x400 : 0);
 }
 
 // Quad-per-car: four lanes (one per wheel chain) advance one car, 8 cars per warp; see mushr_step_quad.cuh.
@@ -58,72 +58,54 @@ __device__ __forceinline__ int status_word(const StepInfo& info, int prev) {
 // friction-loss row constants.  1 072 B per lane: one 216-thread CTA (54 cars) per SM.
 template <int NT> constexpr size_t quad_smem_bytes() { return (size_t)(NT * QP_N + NT / 4 * QC_N + QK_N + 1) * sizeof(double); }
 
+// ONE kernel serves both launches of the staged solve, with ONE inlined copy of the step:
+//   resume = 0  the first launch: CTA b steps cars [54 b, 54 b + 54) of the (regrouped) fleet; a car that is not done after
+//               max_rounds Newton rounds of its CTA is parked in its record (recs != NULL) and listed in list_out;
+//   resume = 1  the continuation: a persistent grid (one CTA per SM) packs the cars listed in list_in, 54 at a time,
+//               restores their solver state from the records and goes on (max_rounds <= 0: to convergence).
+// Both paths run the same machine code for the solver, so a suspended and resumed car gets bit-identical results to one that
+// converges in a single launch: with two kernels (two inlined copies) the compiler contracted a few multiply-adds
+// differently and a 6,144-car fleet (staged) differed from its 2,048-car shards (unstaged) by 1e-15; with the step out of
+// line (one shared function) the results were identical but the step took 2.50 ms instead of 1.3 (round 2 measurements).
 template <int NT, bool LOCK>
 __global__ void __launch_bounds__(NT, 1)
 step_quad_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, double* __restrict__ qvel,
                  double* __restrict__ warm, const double* __restrict__ ctrl, const int32_t* __restrict__ track_id,
                  const int32_t* __restrict__ lap, const int32_t* __restrict__ perm, int64_t ncars, int nsteps,
-                 int32_t* __restrict__ status, double* __restrict__ recs, int32_t* __restrict__ list_out,
-                 int32_t* __restrict__ count_out, int max_rounds, int options, const uint8_t* __restrict__ world_flag, int cpw) {
-    const int tid = threadIdx.x, cib = tid >> 2;
-    constexpr int KO = NT * QP_N + NT / 4 * QC_N;
-    for (int g = tid; g < 25; g += NT) quad_const_entry(c_model, g, quad_sm + KO);
-    __syncthreads();
-    int64_t car = (int64_t)blockIdx.x * (NT / 4) + cib;
-    bool live = car < ncars;
-    if (!live) car = ncars - 1;                     // padding quad: same collectives, no stores
-    if (perm) car = perm[car];                      // cars grouped by their last Newton iteration count
-    // a world whose cars touch each other this tick is one coupled problem: world_step_kernel advances it, not this kernel
-    if (world_flag && world_flag[car / cpw]) live = false;
-    QuadDev<NT, NT / 4, LOCK> qd;
-    qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.qs = tid & 28;
-    const bool shadowed = lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
-    const QHfWalls walls = track_walls(blob, track_id, car, shadowed, options);
-    int st = 0;
-    for (int s = 0; s < nsteps; s++) {
-        StepInfo info;
-        // staged solve (recs != NULL, one step per launch): a car that is not done after max_rounds Newton rounds of its
-        // CTA is parked in its record and listed for the continuation kernel below
-        const QStage stage{recs ? max_rounds : 0, false, recs ? recs + car * QREC_DOUBLES : nullptr};
-        const bool suspended = step_car_quad(qd, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, live, info, stage);
-        if (suspended) {
-            if (live && qd.w == 0) list_out[atomicAdd(count_out, 1)] = (int32_t)car;
-            return;
-        }
-        st = status_word(info, st);
-    }
-    if (status && qd.w == 0 && live) status[car] = st;
-}
-
-// Continuation of the staged solve: a persistent grid (one CTA per SM) packs the suspended cars of the whole fleet,
-// 54 at a time, restores their solver state from the records and goes on for max_rounds more Newton rounds
-// (<= 0: to convergence); cars that are still not done are listed again.
-template <int NT>
-__global__ void __launch_bounds__(NT, 1)
-step_quad_resume_kernel(double* __restrict__ qpos, double* __restrict__ qvel, double* __restrict__ warm,
-                        const double* __restrict__ ctrl, int32_t* __restrict__ status, double* __restrict__ recs,
-                        const int32_t* __restrict__ list_in, const int32_t* __restrict__ count_in,
-                        int32_t* __restrict__ list_out, int32_t* __restrict__ count_out, int max_rounds) {
+                 int32_t* __restrict__ status, double* __restrict__ recs, const int32_t* __restrict__ list_in,
+                 const int32_t* __restrict__ count_in, int32_t* __restrict__ list_out, int32_t* __restrict__ count_out,
+                 int max_rounds, int options, const uint8_t* __restrict__ world_flag, int cpw, int resume) {
     const int tid = threadIdx.x, cib = tid >> 2;
     constexpr int KO = NT * QP_N + NT / 4 * QC_N, CARS = NT / 4;
     for (int g = tid; g < 25; g += NT) quad_const_entry(c_model, g, quad_sm + KO);
     __syncthreads();
-    const int n = *count_in;
-    QuadDev<NT, NT / 4, true> qd;
+    QuadDev<NT, NT / 4, LOCK> qd;
     qd.w = tid & 3; qd.po = tid; qd.co = NT * QP_N + cib; qd.ko = KO; qd.qs = tid & 28;
-    const QHfWalls walls = track_walls(nullptr, nullptr, 0, true, 0);   // (the position stage, which probes the walls, is behind us)
-    for (int base = blockIdx.x * CARS; base < n; base += gridDim.x * CARS) {
-        const int e = base + cib;
-        const bool live = e < n;
-        const int64_t car = list_in[live ? e : n - 1];
-        StepInfo info;
-        const QStage stage{max_rounds, true, recs + car * QREC_DOUBLES};
-        const bool suspended = step_car_quad(qd, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, live, info, stage);
+    const int64_t nwork = resume ? (int64_t)*count_in : ncars;
+    for (int64_t base = (int64_t)blockIdx.x * CARS; base < nwork; base += (int64_t)gridDim.x * CARS) {
+        const int64_t e = base + cib;
+        bool live = e < nwork;
+        int64_t car = live ? e : nwork - 1;             // padding quad: same collectives, no stores
+        if (resume) car = list_in[car];
+        else if (perm) car = perm[car];                 // cars grouped by their last Newton iteration count
+        // a world whose cars touch each other this tick is one coupled problem: world_step_kernel advances it, not this kernel
+        if (!resume && world_flag && world_flag[car / cpw]) live = false;
+        const bool shadowed = !resume && lap && lap[car * FTGP_LAP_FIELDS + FTGP_LAP_FINISHED];
+        const QHfWalls walls = track_walls(resume ? nullptr : blob, track_id, car, shadowed, options);   // (resume: the position stage is behind us)
+        const QStage stage{(resume || recs) ? max_rounds : 0, resume != 0, recs ? recs + car * QREC_DOUBLES : nullptr};
+        int st = 0;
+        bool suspended = false;
+        for (int s = 0; s < (resume ? 1 : nsteps) && !suspended; s++) {
+            StepInfo info;
+            suspended = step_car_quad(qd, c_model, qpos + car * NQ, qvel + car * NV, warm + car * NV, ctrl + 2 * car, walls, live, info, stage);
+            if (!suspended) st = status_word(info, st);
+        }
         if (live && qd.w == 0) {
             if (suspended) list_out[atomicAdd(count_out, 1)] = (int32_t)car;
-            else if (status) status[car] = status_word(info, 0);
+            else if (status) status[car] = st;
         }
-        __syncthreads();                                 // the next batch reuses the shared-memory slots
+        if (!resume) break;                             // first launch: one batch per CTA
+        __syncthreads();                                // the next batch reuses the shared-memory slots
     }
 }
 
@@ -131,7 +113,9 @@ step_quad_resume_kernel(double* __restrict__ qpos, double* __restrict__ qvel, do
 // car.  The iteration count is strongly correlated from one step to the next (measured: mean 2, max over 8 random
 // cars 3.6), so cars are grouped by (last iteration count, in wall contact or not) with a counting sort.
 constexpr int NBIN = 16;
-__device__ __forceinline__ int order_bin(int st) { return min(st & 0xFF, 7) + (((st >> 16) & 0xFF) ? 8 : 0); }
+// bit 10 of the status word: the car was within reach of a wall last step (the gate of quad_prepare).  Only such cars run the
+// wall probes, and a warp runs them if ANY of its 8 cars does -- so the cars near walls are kept together.
+__device__ __forceinline__ int order_bin(int st) { return min(st & 0xFF, 7) + ((st & 0x400) ? 8 : 0); }
 __global__ void order_hist_kernel(const int32_t* __restrict__ status, int64_t ncars, int32_t* __restrict__ hist) {
     __shared__ int h[NBIN];
     if (threadIdx.x < NBIN) h[threadIdx.x] = 0;
@@ -248,7 +232,7 @@ world_step_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, 
         world_step(cm, c_model, cpw, q, v, wm, u, walls, sh, W, kin, wi);
         if (status && (int)threadIdx.x < cpw) {
             const CarWork& C = W.car[threadIdx.x];
-            StepInfo si; si.iters = wi.iters; si.reset = wi.reset; si.ncon_wheel = C.nwheel; si.ncon_wall = C.nwall; si.ncon_ground = C.nground;
+            StepInfo si; si.iters = wi.iters; si.reset = wi.reset; si.ncon_wheel = C.nwheel; si.ncon_wall = C.nwall; si.ncon_ground = C.nground; si.near_wall = C.nwall > 0;
             status[wld * cpw + threadIdx.x] = status_word(si, 0) | 0x200;       // bit 9: advanced by the coupled world solver
         }
         __syncwarp();
@@ -260,8 +244,17 @@ world_step_kernel(const uint32_t* __restrict__ blob, double* __restrict__ qpos, 
 // launch (DESIGN.md 8 lists the measured alternatives; the A/B variants live in tests/host_harness, not in this library).
 // NOTE on the 24-lane tail warp: QuadDev's collectives use the full mask; lanes 24-31 of that warp do not exist (they
 // count as exited threads, which *_sync primitives ignore), and every quad is 4 lanes inside one warp.
+// (tools/build_variant.py compiles A/B variants of these three into separately named libraries for tools/step_ab.py;
+// the shipped library always has the defaults)
+#ifndef FTGP_AB_LOCK
+#define FTGP_AB_LOCK true
+#endif
+#ifndef FTGP_AB_ROUNDS
+#define FTGP_AB_ROUNDS 2
+#endif
 constexpr int STEP_NT = 216;
-constexpr int STAGE_ROUNDS = 2;
+constexpr int STAGE_ROUNDS = FTGP_AB_ROUNDS;
+constexpr bool STEP_LOCK = FTGP_AB_LOCK;
 constexpr int64_t ORDER_MIN_CARS = 1024, STAGE_MIN_CARS = 4096;
 
 constexpr int WORLD_SLOTS = 2048;                   // flagged worlds advanced concurrently (the rest queue behind them)
@@ -279,10 +272,8 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     constexpr size_t smem = quad_smem_bytes<STEP_NT>();
     if (!g_attr_ready[dev]) {                       // once per device, not per launch
         FTGP_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-        FTGP_CUDA(cudaFuncSetAttribute(step_quad_kernel<STEP_NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FTGP_CUDA(cudaFuncSetAttribute(step_quad_kernel<STEP_NT, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        FTGP_CUDA(cudaFuncSetAttribute(step_quad_resume_kernel<STEP_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FTGP_CUDA(cudaFuncSetAttribute(step_quad_resume_kernel<STEP_NT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        FTGP_CUDA(cudaFuncSetAttribute(step_quad_kernel<STEP_NT, STEP_LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FTGP_CUDA(cudaFuncSetAttribute(step_quad_kernel<STEP_NT, STEP_LOCK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         g_attr_ready[dev] = true;
     }
     const uint32_t* blob = g ? g->d_blob : nullptr;
@@ -350,13 +341,14 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
         }
     }
     constexpr int CARS = STEP_NT / 4;
-    step_quad_kernel<STEP_NT, true><<<(unsigned)((ncars + CARS - 1) / CARS), STEP_NT, smem, stream>>>(
-        blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status, recs, lists, counts, STAGE_ROUNDS, options,
-        cpw > 1 ? o->world_flag : nullptr, cpw);
+    step_quad_kernel<STEP_NT, STEP_LOCK><<<(unsigned)((ncars + CARS - 1) / CARS), STEP_NT, smem, stream>>>(
+        blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status, recs, nullptr, nullptr, lists, counts, STAGE_ROUNDS,
+        options, cpw > 1 ? o->world_flag : nullptr, cpw, 0);
     count_launch();
-    if (recs) {
-        step_quad_resume_kernel<STEP_NT><<<g_sm_count[dev], STEP_NT, smem, stream>>>(
-            qpos, qvel, warm, ctrl, status, recs, lists, counts, lists + ncars, counts + 1, 0);
+    if (recs) {                                     // continuation: the same kernel, persistent grid over the suspended cars
+        step_quad_kernel<STEP_NT, STEP_LOCK><<<g_sm_count[dev], STEP_NT, smem, stream>>>(
+            nullptr, qpos, qvel, warm, ctrl, track_id, nullptr, nullptr, ncars, 1, status, recs, lists, counts, lists + ncars, counts + 1, 0,
+            options, nullptr, cpw, 1);
         count_launch();
     }
     if (cpw > 1) {                                  // the coupled worlds (reads the poses the fast path left untouched)

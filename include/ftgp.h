@@ -122,7 +122,8 @@ int ftgp_reset(double* qpos, double* qvel, double* warm, double* ctrl, const dou
  * int32[ncars] or NULL, per car: bits 0-7 Newton iterations of the last step, bit 8 =
  * state was reset (MuJoCo's bad-state check), bits 16-23 contacts with walls (wheels, chassis hull
  * vertices, lidar cylinder), bits 24-27 wheel-ground contacts, bits 28-30 chassis / lidar-cylinder
- * contacts with the ground (a flipped car).  g may be NULL (open ground plane, no walls).  lap: device lap state
+ * contacts with the ground (a flipped car), bit 9 = advanced by the coupled world solver, bit 10 = within reach of a
+ * wall (the step's own regrouping hint).  g may be NULL (open ground plane, no walls).  lap: device lap state
  * (FTGP_LAP_* rows, see below) or NULL; a car whose FTGP_LAP_FINISHED field is set has been
  * shadow()ed (custom.py:1455-1464: conaffinity 0 / contype 2): it no longer collides with walls.
  * options: FTGP_OPT_* bits; FTGP_OPT_BUBBLE_WRAP = the reference's option bubble_wrap (custom.py:970-972,

@@ -60,10 +60,12 @@ def test_lidar_level_and_tilted_and_far(ft, otracks):
     poses = np.concatenate([xy, z[:, None], q], 1)
     got, _ = _scan_gpu(ft, t, poses)
     want = otracks["track"].scan(poses)
-    # rays grazing a triangle edge can legitimately flip between neighbouring facets: allow a handful
-    miss = (got < 0) != (want < 0)
-    bad = np.abs(got - want) > 1e-4
-    assert miss.mean() < 2e-4 and bad.mean() < 5e-4, (miss.sum(), bad.sum())
+    # Round 1 needed slack here (hit / miss flips on 2e-4 of the rays).  Cause, found by dumping the offending rays
+    # (tools/lidar_mismatch.py, tools/lidar_offnominal_analysis.py): every one of them started BELOW the ground plane
+    # (origin z < 0.01, possible only for a car sunk 5 cm into the floor) and ended exactly on the hfield's base plane
+    # z = -0.1, the lower face of the height slab, where fp32 rounding decided whether the flat floor cells were candidates.
+    # With a margin on that test the kernel agrees with the oracle exactly.
+    _check(got, want)
 
 
 def test_lidar_multi_car_world(ft, otracks):

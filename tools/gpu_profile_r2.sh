@@ -11,8 +11,10 @@ EXTRA="smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_ins
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -s $(( SETTLE * 7 )) -c 80 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launch_$TAG.log 2>&1
-for K in step_quad_kernel step_quad_resume_kernel lidar_kernel drivers_kernel; do
-  ncu --set full --metrics $EXTRA --clock-control none --import-source on -k regex:$K -s $SKIP -c 1 -o gpurun_out/prof_${K}_$TAG $CMD > gpurun_out/ncu_${K}_$TAG.log 2>&1
+# (step_quad_kernel is launched twice per tick: the first launch of the staged solve and its continuation; -c 2 captures both)
+for K in step_quad_kernel lidar_kernel drivers_kernel; do
+  C=1; [ "$K" = step_quad_kernel ] && C=2
+  ncu --set full --metrics $EXTRA --clock-control none --import-source on -k regex:$K -s $(( SKIP * C )) -c $C -o gpurun_out/prof_${K}_$TAG $CMD > gpurun_out/ncu_${K}_$TAG.log 2>&1
   tail -n 2 gpurun_out/ncu_${K}_$TAG.log
 done
 # config 2 (lidar only, 4 096 cars): ns/ray and the same lidar metrics
