@@ -79,8 +79,18 @@ FT_HD bool hf_near_corner(const HfView& hv, double x, double y, double radius, i
     if (cmin > cmax) return false;
     const double dx = hv.size_x / (ncol - 1), dy = hv.size_y / (nrow - 1);
     const double x0 = hv.size_x * i - 0.5 * hv.size_x, y0 = -hv.size_y * j - 0.5 * hv.size_y;
-    return x + radius >= x0 + (cmin - 1) * dx && x - radius <= x0 + (cmax + 1) * dx &&
-           y + radius >= y0 + (rmin - 1) * dy && y - radius <= y0 + (rmax + 1) * dy;
+    if (!(x + radius >= x0 + (cmin - 1) * dx && x - radius <= x0 + (cmax + 1) * dx &&
+          y + radius >= y0 + (rmin - 1) * dy && y - radius <= y0 + (rmax + 1) * dy)) return false;
+    // the bounding box of a diagonal stroke is the whole chunk: look at the vertex bits themselves -- is there a raised
+    // vertex within one cell of the square?  (one two-word extraction per vertex row)
+    int c0 = (int)floor((x - radius - x0) / dx) - 1, c1 = (int)floor((x + radius - x0) / dx) + 2;
+    int r0 = (int)floor((y - radius - y0) / dy) - 1, r1 = (int)floor((y + radius - y0) / dy) + 2;
+    c0 = c0 < cmin ? cmin : c0; c1 = c1 > cmax ? cmax : c1;
+    r0 = r0 < rmin ? rmin : r0; r1 = r1 > rmax ? rmax : r1;
+    if (c0 > c1) return false;
+    for (int r = r0; r <= r1; r++)
+        if (hf_row_bits(m, ncol, r, c0, c1 - c0 + 1)) return true;
+    return false;
 }
 
 // rule V: world point p against the surface triangle under it

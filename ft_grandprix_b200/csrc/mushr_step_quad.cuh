@@ -505,38 +505,41 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
                 for (int j = 0; j < 6; j++) B[l][j] += o.B[l][j];
         }
     }
-    // chain block: W = L L^T, diagonal keeps 1 / L_jj
+    // chain block: W = L L^T, diagonal keeps 1 / L_jj.  Right-looking (outer-product) order: column j is finished, then the
+    // trailing block is updated at once.  Every element sees exactly the same subtractions in the same order as in the
+    // dot-product form (bit-identical results), but they are issued as soon as their inputs exist, so the dependent chain
+    // per column is one multiply-add + the reciprocal square root instead of j multiply-adds + rsqrt + j multiply-adds: the
+    // factorisation is latency-bound with 1.7 warps per scheduler (profiles/ncu_summary_r12.md: the two Cholesky inner
+    // products were the two hottest lines of the kernel).
 #pragma unroll
     for (int j = 0; j < NC; j++) {
         double d = W[tri(j, j)];
-#pragma unroll
-        for (int k = 0; k < j; k++) d -= W[tri(j, k)] * W[tri(j, k)];
         if (d < MINVAL) d = MINVAL;
         const double id = inv_sqrt(d);
         W[tri(j, j)] = id;
 #pragma unroll
-        for (int i = j + 1; i < NC; i++) {
-            double s = W[tri(i, j)];
+        for (int i = j + 1; i < NC; i++) W[tri(i, j)] *= id;
 #pragma unroll
-            for (int k = 0; k < j; k++) s -= W[tri(i, k)] * W[tri(j, k)];
-            W[tri(i, j)] = s * id;
-        }
+        for (int i = j + 1; i < NC; i++)
+#pragma unroll
+            for (int k = j + 1; k <= i; k++) W[tri(i, k)] -= W[tri(i, j)] * W[tri(k, j)];
     }
-    // Y = L^-1 B and the right-hand side's chain part z = L^-1 b_c
+    // Y = L^-1 B and the right-hand side's chain part z = L^-1 b_c (column-oriented forward substitution, same order of
+    // operations per element as the row-oriented one)
     double z[NC];
 #pragma unroll
-    for (int l = 0; l < NC; l++) {
+    for (int l = 0; l < NC; l++) z[l] = qd.P(V.p + l);
 #pragma unroll
-        for (int col = 0; col < NR; col++) {
-            double s = B[l][col];
+    for (int k = 0; k < NC; k++) {
 #pragma unroll
-            for (int k = 0; k < l; k++) s -= W[tri(l, k)] * B[k][col];
-            B[l][col] = s * W[tri(l, l)];
+        for (int col = 0; col < NR; col++) B[k][col] *= W[tri(k, k)];
+        z[k] *= W[tri(k, k)];
+#pragma unroll
+        for (int l = k + 1; l < NC; l++) {
+#pragma unroll
+            for (int col = 0; col < NR; col++) B[l][col] -= W[tri(l, k)] * B[k][col];
+            z[l] -= W[tri(l, k)] * z[k];
         }
-        double s = qd.P(V.p + l);
-#pragma unroll
-        for (int k = 0; k < l; k++) s -= W[tri(l, k)] * z[k];
-        z[l] = s * W[tri(l, l)];
     }
     // lane's share of the Schur complement and of the root right-hand side, reduced across the quad
     double R[28], xr[NR];
@@ -554,29 +557,22 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
         for (int l = 0; l < NC; l++) s += B[l][i] * z[l];
         xr[i] = qd.C(V.c + i) - qd.sum(s);
     }
-    // root block (replicated in the four lanes)
+    // root block (replicated in the four lanes): right-looking Cholesky and column-oriented forward substitution, as above
 #pragma unroll
     for (int j = 0; j < NR; j++) {
         double d = R[tri(j, j)];
-#pragma unroll
-        for (int k = 0; k < j; k++) d -= R[tri(j, k)] * R[tri(j, k)];
         if (d < MINVAL) d = MINVAL;
         const double id = inv_sqrt(d);
         R[tri(j, j)] = id;
 #pragma unroll
-        for (int i = j + 1; i < NR; i++) {
-            double s = R[tri(i, j)];
+        for (int i = j + 1; i < NR; i++) R[tri(i, j)] *= id;
 #pragma unroll
-            for (int k = 0; k < j; k++) s -= R[tri(i, k)] * R[tri(j, k)];
-            R[tri(i, j)] = s * id;
-        }
-    }
+        for (int i = j + 1; i < NR; i++)
 #pragma unroll
-    for (int i = 0; i < NR; i++) {
-        double s = xr[i];
+            for (int k = j + 1; k <= i; k++) R[tri(i, k)] -= R[tri(i, j)] * R[tri(k, j)];
+        xr[j] *= id;
 #pragma unroll
-        for (int k = 0; k < i; k++) s -= R[tri(i, k)] * xr[k];
-        xr[i] = s * R[tri(i, i)];
+        for (int i = j + 1; i < NR; i++) xr[i] -= R[tri(i, j)] * xr[j];
     }
 #pragma unroll
     for (int i = NR - 1; i >= 0; i--) {
