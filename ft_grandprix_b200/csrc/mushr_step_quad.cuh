@@ -574,12 +574,12 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
 #pragma unroll
         for (int i = j + 1; i < NR; i++) xr[i] -= R[tri(i, j)] * xr[j];
     }
+    // back substitution with L^T, column-oriented (every finished x_k is subtracted from the rows above at once)
 #pragma unroll
-    for (int i = NR - 1; i >= 0; i--) {
-        double s = xr[i];
+    for (int k = NR - 1; k >= 0; k--) {
+        xr[k] *= R[tri(k, k)];
 #pragma unroll
-        for (int k = i + 1; k < NR; k++) s -= R[tri(k, i)] * xr[k];
-        xr[i] = s * R[tri(i, i)];
+        for (int i = 0; i < k; i++) xr[i] -= R[tri(k, i)] * xr[k];
     }
     // chain: x_c = W^-1 (b_c - B x_r) with the ORIGINAL border B, rebuilt from shared memory (keeping Y = L^-1 B
     // alive across the root factorisation costs 84 registers and spills; rebuilding B x_r costs ~90 DFMA)
@@ -610,19 +610,19 @@ FT_QN void quad_factor_solve(const Q& qd, const QChassis& ch, const QState& st, 
             for (int l = 0; l < NC; l++) t[l] -= o.v[l];
         }
 #pragma unroll
-        for (int l = 0; l < NC; l++) {
-            double sacc = t[l];
+        for (int l = 0; l < NC; l++) z[l] = t[l];
 #pragma unroll
-            for (int k = 0; k < l; k++) sacc -= W[tri(l, k)] * z[k];
-            z[l] = sacc * W[tri(l, l)];
+        for (int k = 0; k < NC; k++) {
+            z[k] *= W[tri(k, k)];
+#pragma unroll
+            for (int l = k + 1; l < NC; l++) z[l] -= W[tri(l, k)] * z[k];
         }
     }
 #pragma unroll
-    for (int l = NC - 1; l >= 0; l--) {
-        double s = z[l];
+    for (int k = NC - 1; k >= 0; k--) {
+        z[k] *= W[tri(k, k)];
 #pragma unroll
-        for (int k = l + 1; k < NC; k++) s -= W[tri(k, l)] * z[k];
-        z[l] = s * W[tri(l, l)];
+        for (int l = 0; l < k; l++) z[l] -= W[tri(k, l)] * z[k];
     }
 #pragma unroll
     for (int i = 0; i < NR; i++) xr[i] *= sign;
