@@ -55,6 +55,7 @@ struct WorldWork {
     int row_cc[WMAXROWS], row_rr[WMAXROWS];
     double Z[WMAXROWS][2][NP];      // H0^-1 U' columns: side 0 = car a, side 1 = car b
     double G[WMAXROWS * WMAXROWS], y[WMAXROWS];
+    double lsq[WMAXCARS][3];        // line search: each car's share of the quadratic along the line (written by its lane)
 };
 
 struct SeqComm {                    // host: one "lane" does everything
@@ -387,9 +388,17 @@ FT_HDN void world_step(const Comm& cm, const ModelConsts& mc, int ncars, double*
         cm.sync();
     };
     // the world's cost along the line as a quadratic in alpha
+    // (every lane evaluates its own car's rows, the shares are summed by everybody: evaluating all eight cars in every lane
+    // made the line search 8x the cost of the factorisations)
     auto ls_world = [&](LsPoint& pt, double alpha) {
+        for (int c = cm.lane; c < ncars; c += cm.nlanes) {
+            double a0 = 0, a1 = 0, a2 = 0;
+            ls_quad(W.car[c].ls, alpha, a0, a1, a2);
+            W.lsq[c][0] = a0; W.lsq[c][1] = a1; W.lsq[c][2] = a2;
+        }
+        cm.sync();
         double q0 = 0, q1 = 0, q2 = 0;
-        for (int c = 0; c < ncars; c++) ls_quad(W.car[c].ls, alpha, q0, q1, q2);
+        for (int c = 0; c < ncars; c++) { q0 += W.lsq[c][0]; q1 += W.lsq[c][1]; q2 += W.lsq[c][2]; }
         for (int k = 0; k < W.ncc; k++) {
             const CcContact& c = W.cc[k];
             for (int rr = 0; rr < 4; rr++) {
@@ -398,6 +407,7 @@ FT_HDN void world_step(const Comm& cm, const ModelConsts& mc, int ncars, double*
                 if (jar + alpha * jv < 0) { q0 += 0.5 * c.D * jar * jar; q1 += c.D * jar * jv; q2 += 0.5 * c.D * jv * jv; }
             }
         }
+        cm.sync();                                                       // (everybody has read the shares before they are overwritten)
         ls_point(pt, alpha, q0, q1, q2);
     };
     auto line_search_world = [&]() -> double {

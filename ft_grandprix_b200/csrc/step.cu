@@ -150,6 +150,7 @@ struct StepScratch {
     int32_t* perm = nullptr; int32_t* counters = nullptr; int64_t cap = 0;                                          // regrouping
     double* recs = nullptr; int32_t* lists = nullptr; int32_t* stage_counts = nullptr; int64_t stage_cap = 0;      // staged solve
     int32_t* world_list = nullptr; uint8_t* world_flag = nullptr; int64_t world_cap = 0;                                // coupled worlds
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;       // ... advanced beside the fast path
     uint64_t generation = 0;     // bumped whenever a buffer is (re)allocated or freed: captured graphs hold these pointers
     void release() {
         if (dev < 0) return;
@@ -161,6 +162,9 @@ struct StepScratch {
         if (lists) cudaFree(lists);
         if (stage_counts) cudaFree(stage_counts);
         if (world_list) cudaFree(world_list);
+        if (side) cudaStreamDestroy(side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         if (world_flag) cudaFree(world_flag);
         cudaSetDevice(cur);
         const uint64_t gen = generation + 1;
@@ -295,6 +299,11 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
             FTGP_CUDA(cudaMalloc(&o->world_list, (size_t)(nworlds + 1) * sizeof(int32_t)));
             FTGP_CUDA(cudaMalloc(&o->world_flag, (size_t)nworlds));
             o->world_cap = nworlds;
+            if (!o->side) {
+                FTGP_CUDA(cudaStreamCreateWithFlags(&o->side, cudaStreamNonBlocking));
+                FTGP_CUDA(cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming));
+                FTGP_CUDA(cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming));
+            }
         }
         FTGP_CUDA(cudaMemsetAsync(o->world_list + nworlds, 0, sizeof(int32_t), stream));        // the counter sits behind the list
         world_flag_kernel<<<(unsigned)((nworlds + 127) / 128), 128, 0, stream>>>(qpos, lap, nworlds, cpw, o->world_flag, o->world_list,
@@ -341,6 +350,18 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
             FTGP_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), stream));
         }
     }
+    if (cpw > 1) {
+        // The coupled worlds are advanced on a side stream, launched FIRST so that their blocks (one warp and 206 KB of shared
+        // memory each, one per flagged world) take their SMs before the fast path's CTAs fill the rest: the two kernels touch
+        // disjoint cars, and a coupled world is a millisecond-long dependent chain that would otherwise be added to the tick.
+        FTGP_CUDA(cudaEventRecord(o->ev_fork, stream));
+        FTGP_CUDA(cudaStreamWaitEvent(o->side, o->ev_fork, 0));
+        const int slots = (int)std::min<int64_t>(nworlds, g_sm_count[dev]);          // one world per SM at a time
+        world_step_kernel<<<slots, 32, sizeof(WorldWork), o->side>>>(blob, qpos, qvel, warm, ctrl, track_id, lap, cpw, status,
+                                                                     o->world_list, o->world_list + nworlds, options);
+        count_launch();
+        FTGP_CUDA(cudaEventRecord(o->ev_join, o->side));
+    }
     constexpr int CARS = STEP_NT / 4;
     step_quad_kernel<STEP_NT, STEP_LOCK><<<(unsigned)((ncars + CARS - 1) / CARS), STEP_NT, smem, stream>>>(
         blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status, recs, nullptr, nullptr, lists, counts, STAGE_ROUNDS,
@@ -352,12 +373,7 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
             options, nullptr, cpw, 1);
         count_launch();
     }
-    if (cpw > 1) {                                  // the coupled worlds (reads the poses the fast path left untouched)
-        const int slots = (int)std::min<int64_t>(nworlds, g_sm_count[dev]);          // one world per SM at a time (shared-memory workspace)
-        world_step_kernel<<<slots, 32, sizeof(WorldWork), stream>>>(blob, qpos, qvel, warm, ctrl, track_id, lap, cpw, status, o->world_list,
-                                                                    o->world_list + nworlds, options);
-        count_launch();
-    }
+    if (cpw > 1) FTGP_CUDA(cudaStreamWaitEvent(stream, o->ev_join, 0));       // join: the coupled worlds are done as well
     FTGP_CUDA(cudaGetLastError());
     return FTGP_OK;
 }
