@@ -53,7 +53,8 @@ struct WorldWork {
     CcContact cc[WMAXCC];
     int ncc, nrows;
     int row_cc[WMAXROWS], row_rr[WMAXROWS];
-    double Z[WMAXROWS][2][NP];      // H0^-1 U' columns: side 0 = car a, side 1 = car b
+    double Hinv6[WMAXCARS][6][NP];  // columns 0-5 of H_c^-1: every row of U touches only the six chassis dofs of its two cars
+    int touched[WMAXCARS];          // the car takes part in an active car-car row
     double G[WMAXROWS * WMAXROWS], y[WMAXROWS];
     double lsq[WMAXCARS][3];        // line search: each car's share of the quadratic along the line (written by its lane)
 };
@@ -307,8 +308,26 @@ FT_HDN void world_step(const Comm& cm, const ModelConsts& mc, int ncars, double*
             for (int p = 0; p < NP; p++) gnorm2 += W.car[c].s.grad[p] * W.car[c].s.grad[p];
         }
     };
-    // Newton direction by Woodbury over the active car-car rows
+    // Newton direction by Woodbury over the active car-car rows.  U's rows are non-zero only on the six chassis dofs of their
+    // two cars, so all that is needed of H_c^-1 are its first six columns (six solves per touched car, whatever the number
+    // of rows): G = D^-1 + sum_c u_rc' S_c u_sc with S_c the 6 x 6 corner of H_c^-1, and d_c = d0_c - H_c^-1[:, 0:6] w_c with
+    // w_c = sum_r y_r u_rc.  Rows of G are spread over the lanes; its Cholesky is right-looking with the rows spread likewise.
+    auto row_u = [&](int r, int side, double* u) {
+        const CcContact& k = W.cc[W.row_cc[r]];
+        const double sg = (W.row_rr[r] & 1) ? -1.0 : 1.0; const int ta = 1 + (W.row_rr[r] >> 1);
+        for (int col = 0; col < 6; col++) u[col] = side == 0 ? k.Ja[0][col] + sg * k.Ja[ta][col] : k.Jb[0][col] + sg * k.Jb[ta][col];
+    };
     auto direction = [&]() {
+        if (cm.lane == 0) {
+            W.nrows = 0;
+            for (int c = 0; c < ncars; c++) W.touched[c] = 0;
+            for (int k = 0; k < W.ncc; k++) for (int rr = 0; rr < 4; rr++) if (W.cc[k].active >> rr & 1u) {
+                W.row_cc[W.nrows] = k; W.row_rr[W.nrows] = rr; W.nrows++;
+                W.touched[W.cc[k].a] = 1; W.touched[W.cc[k].b] = 1;
+            }
+        }
+        cm.sync();
+        const int n = W.nrows;
         for (int c = cm.lane; c < ncars; c += cm.nlanes) {
             CarWork& C = W.car[c];
             C.H = C.M;
@@ -316,61 +335,55 @@ FT_HDN void world_step(const Comm& cm, const ModelConsts& mc, int ncars, double*
             arrow_factor(C.H);
             for (int p = 0; p < NP; p++) C.d0[p] = C.s.grad[p];
             arrow_solve(C.H, C.d0);
-        }
-        if (cm.lane == 0) {
-            W.nrows = 0;
-            for (int k = 0; k < W.ncc; k++) for (int rr = 0; rr < 4; rr++) if (W.cc[k].active >> rr & 1u) { W.row_cc[W.nrows] = k; W.row_rr[W.nrows] = rr; W.nrows++; }
-        }
-        cm.sync();
-        const int n = W.nrows;
-        // Z columns: one solve per (row, side), spread over the lanes by the car that owns the factor
-        for (int c = cm.lane; c < ncars; c += cm.nlanes)
-            for (int r = 0; r < n; r++) {
-                const CcContact& k = W.cc[W.row_cc[r]];
-                for (int side = 0; side < 2; side++) {
-                    if ((side == 0 ? k.a : k.b) != c) continue;
-                    const double sg = (W.row_rr[r] & 1) ? -1.0 : 1.0; const int ta = 1 + (W.row_rr[r] >> 1);
-                    double* z = W.Z[r][side];
+            if (W.touched[c])
+                for (int i = 0; i < 6; i++) {
+                    double* z = W.Hinv6[c][i];
                     for (int p = 0; p < NP; p++) z[p] = 0;
-                    for (int col = 0; col < 6; col++) z[col] = side == 0 ? k.Ja[0][col] + sg * k.Ja[ta][col] : k.Jb[0][col] + sg * k.Jb[ta][col];
-                    arrow_solve(W.car[c].H, z);
+                    z[i] = 1;
+                    arrow_solve(C.H, z);
                 }
-            }
+        }
         cm.sync();
         if (n > 0) {
-            if (cm.lane == 0) {
-                for (int r = 0; r < n; r++) {
-                    const CcContact& kr = W.cc[W.row_cc[r]];
-                    const double sgr = (W.row_rr[r] & 1) ? -1.0 : 1.0; const int tar = 1 + (W.row_rr[r] >> 1);
-                    double ua[6], ub[6], rhs = 0;
-                    for (int col = 0; col < 6; col++) { ua[col] = kr.Ja[0][col] + sgr * kr.Ja[tar][col]; ub[col] = kr.Jb[0][col] + sgr * kr.Jb[tar][col]; }
-                    for (int col = 0; col < 6; col++) rhs += ua[col] * W.car[kr.a].d0[col] + ub[col] * W.car[kr.b].d0[col];
-                    W.y[r] = rhs;
-                    for (int s2 = 0; s2 < n; s2++) {
-                        const CcContact& ks = W.cc[W.row_cc[s2]];
-                        double g = r == s2 ? 1.0 / kr.D : 0.0;
-                        for (int side = 0; side < 2; side++) {
-                            const int cs2 = side == 0 ? ks.a : ks.b;
-                            const double* z = W.Z[s2][side];
-                            if (cs2 == kr.a) for (int col = 0; col < 6; col++) g += ua[col] * z[col];
-                            if (cs2 == kr.b) for (int col = 0; col < 6; col++) g += ub[col] * z[col];
-                        }
-                        W.G[r * n + s2] = g;
-                    }
+            for (int r = cm.lane; r < n; r += cm.nlanes) {                // row r of G and of the right-hand side U d0
+                const CcContact& kr = W.cc[W.row_cc[r]];
+                double ua[6], ub[6], sa[6], sb[6], rhs = 0;
+                row_u(r, 0, ua); row_u(r, 1, ub);
+                for (int col = 0; col < 6; col++) rhs += ua[col] * W.car[kr.a].d0[col] + ub[col] * W.car[kr.b].d0[col];
+                W.y[r] = rhs;
+                // sa = S_a ua, sb = S_b ub (S symmetric: H_c^-1[i][j] = Hinv6[i][j])
+                for (int i = 0; i < 6; i++) {
+                    double ta_ = 0, tb_ = 0;
+                    for (int j = 0; j < 6; j++) { ta_ += W.Hinv6[kr.a][j][i] * ua[j]; tb_ += W.Hinv6[kr.b][j][i] * ub[j]; }
+                    sa[i] = ta_; sb[i] = tb_;
                 }
-                // dense Cholesky of G (SPD: D^-1 plus a Gram matrix), then y = G^-1 (U d0)
-                for (int j = 0; j < n; j++) {
-                    double d = W.G[j * n + j];
-                    for (int q = 0; q < j; q++) d -= W.G[j * n + q] * W.G[j * n + q];
-                    if (d < MINVAL) d = MINVAL;
-                    d = sqrt(d);
-                    W.G[j * n + j] = d;
-                    for (int i = j + 1; i < n; i++) {
-                        double t = W.G[i * n + j];
-                        for (int q = 0; q < j; q++) t -= W.G[i * n + q] * W.G[j * n + q];
-                        W.G[i * n + j] = t / d;
-                    }
+                for (int s2 = 0; s2 < n; s2++) {
+                    const CcContact& ks = W.cc[W.row_cc[s2]];
+                    double va[6], vb[6], g = r == s2 ? 1.0 / kr.D : 0.0;
+                    row_u(s2, 0, va); row_u(s2, 1, vb);
+                    if (ks.a == kr.a) for (int i = 0; i < 6; i++) g += sa[i] * va[i];
+                    if (ks.b == kr.a) for (int i = 0; i < 6; i++) g += sa[i] * vb[i];
+                    if (ks.a == kr.b) for (int i = 0; i < 6; i++) g += sb[i] * va[i];
+                    if (ks.b == kr.b) for (int i = 0; i < 6; i++) g += sb[i] * vb[i];
+                    W.G[r * n + s2] = g;
                 }
+            }
+            cm.sync();
+            for (int j = 0; j < n; j++) {                                // G = L L' (SPD: D^-1 plus a Gram matrix)
+                double d = W.G[j * n + j];
+                if (d < MINVAL) d = MINVAL;
+                d = sqrt(d);
+                cm.sync();                                               // (everybody has read G[j][j])
+                if (cm.lane == j % cm.nlanes) W.G[j * n + j] = d;
+                for (int i = j + 1 + cm.lane; i < n; i += cm.nlanes) W.G[i * n + j] /= d;
+                cm.sync();
+                for (int i = j + 1 + cm.lane; i < n; i += cm.nlanes) {
+                    const double lij = W.G[i * n + j];
+                    for (int q = j + 1; q <= i; q++) W.G[i * n + q] -= lij * W.G[q * n + j];
+                }
+                cm.sync();
+            }
+            if (cm.lane == 0) {                                          // y = G^-1 (U d0)
                 for (int i = 0; i < n; i++) { double t = W.y[i]; for (int q = 0; q < i; q++) t -= W.G[i * n + q] * W.y[q]; W.y[i] = t / W.G[i * n + i]; }
                 for (int i = n - 1; i >= 0; i--) { double t = W.y[i]; for (int q = i + 1; q < n; q++) t -= W.G[q * n + i] * W.y[q]; W.y[i] = t / W.G[i * n + i]; }
             }
@@ -378,16 +391,19 @@ FT_HDN void world_step(const Comm& cm, const ModelConsts& mc, int ncars, double*
         }
         for (int c = cm.lane; c < ncars; c += cm.nlanes) {
             CarWork& C = W.car[c];
-            for (int r = 0; r < n; r++) {
-                const CcContact& k = W.cc[W.row_cc[r]];
-                for (int side = 0; side < 2; side++)
-                    if ((side == 0 ? k.a : k.b) == c) for (int p = 0; p < NP; p++) C.d0[p] -= W.y[r] * W.Z[r][side][p];
+            if (n > 0 && W.touched[c]) {
+                double w6[6] = {0, 0, 0, 0, 0, 0}, u[6];
+                for (int r = 0; r < n; r++) {
+                    const CcContact& k = W.cc[W.row_cc[r]];
+                    if (k.a == c) { row_u(r, 0, u); for (int i = 0; i < 6; i++) w6[i] += W.y[r] * u[i]; }
+                    if (k.b == c) { row_u(r, 1, u); for (int i = 0; i < 6; i++) w6[i] += W.y[r] * u[i]; }
+                }
+                for (int i = 0; i < 6; i++) for (int p = 0; p < NP; p++) C.d0[p] -= w6[i] * W.Hinv6[c][i][p];
             }
             for (int p = 0; p < NP; p++) C.s.search[p] = -C.d0[p];
         }
         cm.sync();
     };
-    // the world's cost along the line as a quadratic in alpha
     // (every lane evaluates its own car's rows, the shares are summed by everybody: evaluating all eight cars in every lane
     // made the line search 8x the cost of the factorisations)
     auto ls_world = [&](LsPoint& pt, double alpha) {
