@@ -495,7 +495,8 @@ def run_gpu(args):
                 v, dt = cpu_units_per_s(wl, sc, nt, threads)
                 line["cpu_baseline"] = {"value": v, "unit": unit, "cores": threads, "kind": "port",
                                         "host_cores_available": os.cpu_count(), "mujoco_probe": "import mujoco failed",
-                                        "sample": f"{sc} cars x {nt} tick(s) after {CPU_SETTLE_TICKS} settle ticks, C oracle single thread ({dt:.1f} s)"}
+                                        "sample": (f"{sc} cars x 90 rays at the bench poses, C oracle single thread ({dt:.1f} s)" if wl == "lidar" else
+                                                   f"{sc} cars x {nt} tick(s) after {CPU_SETTLE_TICKS} settle ticks, C oracle single thread ({dt:.1f} s)")}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -260,6 +260,25 @@ __device__ __noinline__ double ray_other_car(double px, double py, double pz, do
 // other block's instructions are not issued at all for a handful of lanes
 // (the first version traced beams l, l+32, l+64 per lane with nested loops: 6.5 of 32 lanes active).
 enum { ST_IDLE = 0, ST_CHUNK = 1, ST_SWEEP = 2, ST_ADV = 3 };
+// scheduling knobs of the state machine (tools/build_variant.py experiments; the defaults are what ships)
+#ifndef FTGP_AB_HYST_A
+#define FTGP_AB_HYST_A 0            // > 0: keep sweeping while at least A lanes sweep ...
+#endif
+#ifndef FTGP_AB_HYST_B
+#define FTGP_AB_HYST_B 0            // ... and keep walking while at least B lanes walk (0/0: plain majority vote)
+#endif
+#ifndef FTGP_AB_WALK_MAX
+#define FTGP_AB_WALK_MAX 5          // at most this many empty chunks per round (0: unbounded; measured 1.30 -> 1.14 ms at 65,536 cars)
+#endif
+#ifndef FTGP_AB_WALK_VOTE
+#define FTGP_AB_WALK_VOTE 0         // K > 0: the walk goes on while at least K/4 of the lanes that started it are still walking
+#endif
+#ifndef FTGP_AB_LINE_MAX
+#define FTGP_AB_LINE_MAX 0          // > 0: at most this many candidate-free lines per round
+#endif
+#ifndef FTGP_AB_REFILL
+#define FTGP_AB_REFILL 8            // idle lanes that trigger a refill
+#endif
 constexpr int BATCH = 8;              // max cars per warp batch (a batch holds whole worlds of 1..8 cars)
 constexpr int FRAME_DOUBLES = 18;     // p[3], R[9], suspension travel [4], front steering angle [2]
 
@@ -352,9 +371,10 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
         int next = 0;
         Lane L;
         L.state = ST_IDLE;
+        int mode = ST_CHUNK;
         for (;;) {
             const unsigned idle = __ballot_sync(0xffffffffu, L.state == ST_IDLE);
-            const bool refill = next < nrays && (__popc(idle) >= 8 || idle == 0xffffffffu);
+            const bool refill = next < nrays && (__popc(idle) >= FTGP_AB_REFILL || idle == 0xffffffffu);
             if (!refill && idle == 0xffffffffu) break;
             if (refill) {
                 const int r = next + __popc(idle & lt);
@@ -460,7 +480,12 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
             // ---------------- which block runs this round: the state with the most lanes
             const int n_chunk = __popc(__ballot_sync(0xffffffffu, L.state == ST_CHUNK || L.state == ST_ADV));
             const int n_sweep = __popc(__ballot_sync(0xffffffffu, L.state == ST_SWEEP));
-            const int pick = n_chunk >= n_sweep ? ST_CHUNK : ST_SWEEP;
+            int pick = n_chunk >= n_sweep ? ST_CHUNK : ST_SWEEP;
+            if (FTGP_AB_HYST_A > 0) {
+                if (mode == ST_SWEEP) pick = (n_sweep >= FTGP_AB_HYST_A || n_chunk == 0) ? ST_SWEEP : ST_CHUNK;
+                else pick = (n_chunk >= FTGP_AB_HYST_B && n_chunk > 0) || n_sweep == 0 ? ST_CHUNK : ST_SWEEP;
+                mode = pick;
+            }
             // ---------------- leave the previous chunk (exit side face, step of the chunk DDA) ...
             if (pick == ST_CHUNK && L.state == ST_ADV) {
                 bool done = false;
@@ -487,7 +512,11 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                 const int hc = th->hc, vc = th->vc;
                 const uint16_t* index = reinterpret_cast<const uint16_t*>(geo + th->index_off);
                 uint32_t cid;
-                for (;;) {
+                bool more = false;
+                const int entered = FTGP_AB_WALK_VOTE > 0 ? __popc(__activemask()) : 0;
+                for (int hop = 0;; hop++) {
+                    if (FTGP_AB_WALK_MAX > 0 && hop == FTGP_AB_WALK_MAX) { more = true; break; }
+                    if (FTGP_AB_WALK_VOTE > 0 && hop > 0 && __popc(__activemask()) * 4 < entered * FTGP_AB_WALK_VOTE) { more = true; break; }
                     const float tmx = L.inv_dgx != 0.f ? ((float)(L.ix - L.ix0 + (L.stepx > 0 ? 1 : 0)) - L.fx0) * L.inv_dgx : BIG;
                     const float tmy = L.inv_dgy != 0.f ? ((float)(L.iy - L.iy0 + (L.stepy > 0 ? 1 : 0)) - L.fy0) * L.inv_dgy : BIG;
                     L.exit_axis = tmx <= tmy ? 0 : 1;
@@ -500,7 +529,7 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                     if (L.ix < 0 || L.ix >= hc || L.iy < 0 || L.iy >= vc) { finish(L, L.best < BIG ? L.best : -1.f, ranges, min_range, base_car); break; }
                     L.t0 = L.t1; L.entry_axis = L.exit_axis;
                 }
-                L.nonempty = L.state == ST_CHUNK;
+                L.nonempty = L.state == ST_CHUNK && !more;
                 if (L.nonempty) L.state = ST_ADV;           // unless the sweep below takes over (or a face ends the ray)
                 if (L.nonempty) {
                     const uint32_t* m = geo + th->chunks_off + cid * CHUNK_WORDS;
@@ -567,7 +596,7 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                 uint32_t cand, lineA, lineB;
                 const uint32_t* mk = L.major_x ? L.m + 15 : L.m;        // row-major masks for rows, transposed for columns
                 const int nline = L.major_x ? L.nrow : L.ncol;          // vertices per line
-                for (;;) {
+                for (int hop = 0;; hop++) {
                     float s0 = 0.f, s1 = L.span;
                     if (L.inv_dM != 0.f) {
                         const float e0 = ((float)(L.c + (L.sg > 0 ? 0 : 1)) - L.Ma) * L.inv_dM;
@@ -584,6 +613,7 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                     const uint32_t range = (2u << rhi) - (1u << rlo);   // cells rlo..rhi
                     cand = L.floor_reach ? range : (occ & range);
                     if (cand || L.c == L.cend) break;
+                    if (FTGP_AB_LINE_MAX > 0 && hop + 1 == FTGP_AB_LINE_MAX) break;      // (cand == 0: the tail below moves on one line)
                     L.c += L.sg;
                 }
                 float found = BIG;

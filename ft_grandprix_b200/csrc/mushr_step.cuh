@@ -249,6 +249,31 @@ FT_HDN void arrow_solve(const Arrow& A, double* x) {
     }
 }
 
+// Right-hand sides that live on the root dofs only (a car-car contact row touches nothing but the six chassis dofs): the
+// forward pass over the chains has nothing to do, so  x_r = S b_r  with S the inverse of the root Schur complement (two
+// 7 x 7 triangular solves) and  x_w = -L_w^{-T} (Y_w x_r).
+// S6[i][j] = (A^{-1})[j][i] for the root unit vectors i < 6, root rows j < NR
+FT_HDN void arrow_root_inverse6(const Arrow& A, double S6[6][NR]) {
+    const double* L = A.R;
+    for (int c = 0; c < 6; c++) {
+        double* x = S6[c];
+        for (int i = 0; i < NR; i++) x[i] = i == c ? 1.0 : 0.0;
+        for (int i = c; i < NR; i++) { double s = x[i]; for (int k = c; k < i; k++) s -= L[tri(i, k)] * x[k]; x[i] = s * L[tri(i, i)]; }
+        for (int i = NR - 1; i >= 0; i--) { double s = x[i]; for (int k = i + 1; k < NR; k++) s -= L[tri(k, i)] * x[k]; x[i] = s * L[tri(i, i)]; }
+    }
+}
+// x <- A^{-1} (b_r, 0): b_r in x[0..NR), chain parts of x are overwritten
+FT_HDN void arrow_solve_root_rhs(const Arrow& A, double* x) {
+    const double* L = A.R;
+    for (int i = 0; i < NR; i++) { double s = x[i]; for (int k = 0; k < i; k++) s -= L[tri(i, k)] * x[k]; x[i] = s * L[tri(i, i)]; }
+    for (int i = NR - 1; i >= 0; i--) { double s = x[i]; for (int k = i + 1; k < NR; k++) s -= L[tri(k, i)] * x[k]; x[i] = s * L[tri(i, i)]; }
+    for (int w = 0; w < 4; w++) {
+        const double* Lw = A.W[w]; double* xc = x + NR + NC * w;
+        for (int l = 0; l < NC; l++) { double s = 0; for (int j = 0; j < NR; j++) s += A.B[w][l][j] * x[j]; xc[l] = -s; }
+        for (int l = NC - 1; l >= 0; l--) { double s = xc[l]; for (int k = l + 1; k < NC; k++) s -= Lw[tri(k, l)] * xc[k]; xc[l] = s * Lw[tri(l, l)]; }
+    }
+}
+
 // ---- per-step workspace ---------------------------------------------------------------------------------
 struct Contact {
     double J[3][12];    // rows: normal, tangent1, tangent2; cols: chassis dofs 0-5, chain slots 0-5 (susp, steer, throttle, ball)

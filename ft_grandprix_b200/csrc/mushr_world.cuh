@@ -53,7 +53,7 @@ struct WorldWork {
     CcContact cc[WMAXCC];
     int ncc, nrows;
     int row_cc[WMAXROWS], row_rr[WMAXROWS];
-    double Hinv6[WMAXCARS][6][NP];  // columns 0-5 of H_c^-1: every row of U touches only the six chassis dofs of its two cars
+    double S6[WMAXCARS][6][NR];     // root rows of columns 0-5 of H_c^-1: every row of U touches only the six chassis dofs of its two cars
     int touched[WMAXCARS];          // the car takes part in an active car-car row
     double G[WMAXROWS * WMAXROWS], y[WMAXROWS];
     double lsq[WMAXCARS][3];        // line search: each car's share of the quadratic along the line (written by its lane)
@@ -154,6 +154,10 @@ FT_HDN void world_detect(const ModelConsts& mc, int ncars, const double* const* 
     for (int A = 0; A < ncars; A++) for (int B = 0; B < ncars; B++) {
         if (A == B || W.car[A].shadowed || W.car[B].shadowed) continue;
         const CarWork& ca = W.car[A]; const CarWork& cb = W.car[B];
+        {   // both hulls lie within 0.125 m of their body origins: far pairs have no vertex in the other's box
+            const double dx = ca.p1[0] - cb.p1[0], dy = ca.p1[1] - cb.p1[1], dz = ca.p1[2] - cb.p1[2];
+            if (dx * dx + dy * dy + dz * dz > 0.26 * 0.26) continue;
+        }
         for (int v = 0; v < MUSHR_CHASSIS_NHULL && W.ncc < WMAXCC; v++) {
             double pw[3], rel[3], ql[3];
             mat_vec3(pw, ca.R1, hull[v]);
@@ -309,9 +313,8 @@ FT_HDN void world_step(const Comm& cm, const ModelConsts& mc, int ncars, double*
         }
     };
     // Newton direction by Woodbury over the active car-car rows.  U's rows are non-zero only on the six chassis dofs of their
-    // two cars, so all that is needed of H_c^-1 are its first six columns (six solves per touched car, whatever the number
-    // of rows): G = D^-1 + sum_c u_rc' S_c u_sc with S_c the 6 x 6 corner of H_c^-1, and d_c = d0_c - H_c^-1[:, 0:6] w_c with
-    // w_c = sum_r y_r u_rc.  Rows of G are spread over the lanes; its Cholesky is right-looking with the rows spread likewise.
+    // two cars: G = D^-1 + sum_c u_rc' S_c u_sc needs only S_c, the 6 x 6 corner of H_c^-1 (root-only solves with the Schur
+    // factor, no chain work), and d_c = d0_c - H_c^-1 (w_c, 0) with w_c = sum_r y_r u_rc is one more root-only right-hand side.  Rows of G are spread over the lanes; its Cholesky is right-looking with the rows spread likewise.
     auto row_u = [&](int r, int side, double* u) {
         const CcContact& k = W.cc[W.row_cc[r]];
         const double sg = (W.row_rr[r] & 1) ? -1.0 : 1.0; const int ta = 1 + (W.row_rr[r] >> 1);
@@ -335,13 +338,7 @@ FT_HDN void world_step(const Comm& cm, const ModelConsts& mc, int ncars, double*
             arrow_factor(C.H);
             for (int p = 0; p < NP; p++) C.d0[p] = C.s.grad[p];
             arrow_solve(C.H, C.d0);
-            if (W.touched[c])
-                for (int i = 0; i < 6; i++) {
-                    double* z = W.Hinv6[c][i];
-                    for (int p = 0; p < NP; p++) z[p] = 0;
-                    z[i] = 1;
-                    arrow_solve(C.H, z);
-                }
+            if (W.touched[c]) arrow_root_inverse6(C.H, W.S6[c]);
         }
         cm.sync();
         if (n > 0) {
@@ -351,10 +348,10 @@ FT_HDN void world_step(const Comm& cm, const ModelConsts& mc, int ncars, double*
                 row_u(r, 0, ua); row_u(r, 1, ub);
                 for (int col = 0; col < 6; col++) rhs += ua[col] * W.car[kr.a].d0[col] + ub[col] * W.car[kr.b].d0[col];
                 W.y[r] = rhs;
-                // sa = S_a ua, sb = S_b ub (S symmetric: H_c^-1[i][j] = Hinv6[i][j])
+                // sa = S_a ua, sb = S_b ub (S symmetric: H_c^-1[i][j] = S6[i][j])
                 for (int i = 0; i < 6; i++) {
                     double ta_ = 0, tb_ = 0;
-                    for (int j = 0; j < 6; j++) { ta_ += W.Hinv6[kr.a][j][i] * ua[j]; tb_ += W.Hinv6[kr.b][j][i] * ub[j]; }
+                    for (int j = 0; j < 6; j++) { ta_ += W.S6[kr.a][j][i] * ua[j]; tb_ += W.S6[kr.b][j][i] * ub[j]; }
                     sa[i] = ta_; sb[i] = tb_;
                 }
                 for (int s2 = 0; s2 < n; s2++) {
@@ -398,7 +395,10 @@ FT_HDN void world_step(const Comm& cm, const ModelConsts& mc, int ncars, double*
                     if (k.a == c) { row_u(r, 0, u); for (int i = 0; i < 6; i++) w6[i] += W.y[r] * u[i]; }
                     if (k.b == c) { row_u(r, 1, u); for (int i = 0; i < 6; i++) w6[i] += W.y[r] * u[i]; }
                 }
-                for (int i = 0; i < 6; i++) for (int p = 0; p < NP; p++) C.d0[p] -= w6[i] * W.Hinv6[c][i][p];
+                double dl[NP];                                           // H_c^-1 (w, 0): a right-hand side on the root dofs only
+                for (int p = 0; p < NP; p++) dl[p] = p < 6 ? w6[p] : 0.0;
+                arrow_solve_root_rhs(C.H, dl);
+                for (int p = 0; p < NP; p++) C.d0[p] -= dl[p];
             }
             for (int p = 0; p < NP; p++) C.s.search[p] = -C.d0[p];
         }
