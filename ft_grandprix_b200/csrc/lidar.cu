@@ -280,7 +280,7 @@ enum { ST_IDLE = 0, ST_CHUNK = 1, ST_SWEEP = 2, ST_ADV = 3 };
 #define FTGP_AB_REFILL 8            // idle lanes that trigger a refill
 #endif
 constexpr int BATCH = 8;              // max cars per warp batch (a batch holds whole worlds of 1..8 cars)
-constexpr int FRAME_DOUBLES = 18;     // p[3], R[9], suspension travel [4], front steering angle [2]
+constexpr int FRAME_DOUBLES = 21;     // p[3], R[9], suspension travel [4], front steering angle [2], centre of the car's bounding sphere [3]
 
 struct Lane {
     // ray
@@ -355,6 +355,7 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                 const bool full = stride >= FTGP_NQ;
                 F[12] = full ? q[8] : 0.0; F[13] = full ? q[15] : 0.0; F[14] = full ? q[22] : 0.0; F[15] = full ? q[28] : 0.0;
                 F[16] = full ? q[9] : 0.0; F[17] = full ? q[16] : 0.0;
+                F[18] = F[0] + 0.02 * F[5]; F[19] = F[1] + 0.02 * F[8]; F[20] = F[2] + 0.02 * F[11];      // car-frame (0, 0, 0.02)
             }
             int tid = track_id ? track_id[base_car + lane] : 0;
             if (tid < 0 || tid >= gh->ntracks) tid = 0;
@@ -409,6 +410,12 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
                             for (int oc = w0; oc < w0 + cpw && oc < nb; oc++) {
                                 if (oc == car || (meta[oc] & 0x100)) continue;      // bodyexclude / invisible
                                 const double* Q = frames + oc * FRAME_DOUBLES;
+                                {   // ray_other_car's bounding-sphere cull, in the world frame: most pairs end here, before the
+                                    // ray is rotated into the other car's frame (the predicate is rotation-invariant)
+                                    const double sx = owx - Q[18], sy = owy - Q[19], sz = owz - Q[20];
+                                    const double bq = sx * dwx + sy * dwy + sz * dwz, cq = sx * sx + sy * sy + sz * sz - 0.145 * 0.145;
+                                    if (cq > 1e-9 && (bq > 1e-9 || bq * bq - cq < -1e-9)) continue;
+                                }
                                 const double ex = owx - Q[0], ey = owy - Q[1], ez = owz - Q[2];
                                 const double px = Q[3] * ex + Q[6] * ey + Q[9] * ez;
                                 const double py = Q[4] * ex + Q[7] * ey + Q[10] * ez;

@@ -116,23 +116,30 @@ constexpr int NBIN = 16;
 // bit 10 of the status word: the car was within reach of a wall last step (the gate of quad_prepare).  Only such cars run the
 // wall probes, and a warp runs them if ANY of its 8 cars does -- so the cars near walls are kept together.
 __device__ __forceinline__ int order_bin(int st) { return min(st & 0xFF, 7) + ((st & 0x400) ? 8 : 0); }
-__global__ void order_hist_kernel(const int32_t* __restrict__ status, int64_t ncars, int32_t* __restrict__ hist) {
+// (cars of a world flagged as coupled sit in the last bin whatever their status word says: inside the fused tick their solver
+// is already running beside these kernels and rewrites those words)
+__device__ __forceinline__ int order_bin_of(const int32_t* __restrict__ status, const uint8_t* __restrict__ world_flag, int cpw, int64_t i) {
+    if (world_flag && world_flag[i / cpw]) return NBIN - 1;
+    return order_bin(status[i]);
+}
+__global__ void order_hist_kernel(const int32_t* __restrict__ status, const uint8_t* __restrict__ world_flag, int cpw, int64_t ncars,
+                                  int32_t* __restrict__ hist) {
     __shared__ int h[NBIN];
     if (threadIdx.x < NBIN) h[threadIdx.x] = 0;
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < ncars) atomicAdd(&h[order_bin(status[i])], 1);
+    if (i < ncars) atomicAdd(&h[order_bin_of(status, world_flag, cpw, i)], 1);
     __syncthreads();
     if (threadIdx.x < NBIN && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
 }
-__global__ void order_scatter_kernel(const int32_t* __restrict__ status, int64_t ncars, const int32_t* __restrict__ hist,
-                                     int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+__global__ void order_scatter_kernel(const int32_t* __restrict__ status, const uint8_t* __restrict__ world_flag, int cpw, int64_t ncars,
+                                     const int32_t* __restrict__ hist, int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
     __shared__ int h[NBIN], base[NBIN];
     if (threadIdx.x < NBIN) h[threadIdx.x] = 0;
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int bin = 0, rank = 0;
-    if (i < ncars) { bin = order_bin(status[i]); rank = atomicAdd(&h[bin], 1); }
+    if (i < ncars) { bin = order_bin_of(status, world_flag, cpw, i); rank = atomicAdd(&h[bin], 1); }
     __syncthreads();
     if (threadIdx.x < NBIN) {
         int start = 0;
@@ -151,6 +158,8 @@ struct StepScratch {
     double* recs = nullptr; int32_t* lists = nullptr; int32_t* stage_counts = nullptr; int64_t stage_cap = 0;      // staged solve
     int32_t* world_list = nullptr; uint8_t* world_flag = nullptr; int64_t world_cap = 0;                                // coupled worlds
     void* world_spill = nullptr;                                                                                         // workspaces of warps 1.. of world_step_kernel
+    double* qpos_snap = nullptr; int64_t snap_cap = 0;      // fused tick: the poses the rangefinders read while the coupled worlds already move
+    bool world_inflight = false;                            // the coupled worlds of this step were started by launch_worlds_early
     cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;       // ... advanced beside the fast path
     uint64_t generation = 0;     // bumped whenever a buffer is (re)allocated or freed: captured graphs hold these pointers
     void release() {
@@ -168,6 +177,7 @@ struct StepScratch {
         if (ev_join) cudaEventDestroy(ev_join);
         if (world_flag) cudaFree(world_flag);
         if (world_spill) cudaFree(world_spill);
+        if (qpos_snap) cudaFree(qpos_snap);
         cudaSetDevice(cur);
         const uint64_t gen = generation + 1;
         *this = StepScratch();
@@ -275,6 +285,91 @@ constexpr int64_t ORDER_MIN_CARS = 1024, STAGE_MIN_CARS = 4096;
 
 static_assert(sizeof(WorldWork) <= 227 * 1024, "the coupled world's workspace must fit one SM's shared memory");
 
+static int step_device_ready(int dev) {             // caller holds g_step_mutex; once per device, not per launch
+    int rc = ensure_model(dev); if (rc) return rc;
+    if (!g_attr_ready[dev]) {
+        constexpr size_t smem = quad_smem_bytes<STEP_NT>();
+        FTGP_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+        FTGP_CUDA(cudaFuncSetAttribute(step_quad_kernel<STEP_NT, STEP_LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FTGP_CUDA(cudaFuncSetAttribute(step_quad_kernel<STEP_NT, STEP_LOCK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        FTGP_CUDA(cudaFuncSetAttribute(world_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WorldWork)));
+        g_attr_ready[dev] = true;
+    }
+    return FTGP_OK;
+}
+
+// worlds of several cars: list the worlds whose cars touch (they leave the fast path) ...
+static int world_flag_launch(StepScratch* o, int dev, const double* qpos, const int32_t* lap, int64_t nworlds, int cpw, cudaStream_t stream) {
+    if (o->world_cap < nworlds) {
+        if (o->world_list) cudaFree(o->world_list);
+        if (o->world_flag) cudaFree(o->world_flag);
+        o->world_list = nullptr; o->world_flag = nullptr; o->world_cap = 0; o->generation++;
+        FTGP_CUDA(cudaMalloc(&o->world_list, (size_t)(nworlds + 1) * sizeof(int32_t)));
+        FTGP_CUDA(cudaMalloc(&o->world_flag, (size_t)nworlds));
+        o->world_cap = nworlds;
+        if (WORLD_WARPS > 1 && !o->world_spill) FTGP_CUDA(cudaMalloc(&o->world_spill, (size_t)g_sm_count[dev] * (WORLD_WARPS - 1) * sizeof(WorldWork)));
+        if (!o->side) {
+            FTGP_CUDA(cudaStreamCreateWithFlags(&o->side, cudaStreamNonBlocking));
+            FTGP_CUDA(cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming));
+            FTGP_CUDA(cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming));
+        }
+    }
+    FTGP_CUDA(cudaMemsetAsync(o->world_list + nworlds, 0, sizeof(int32_t), stream));        // the counter sits behind the list
+    world_flag_kernel<<<(unsigned)((nworlds + 127) / 128), 128, 0, stream>>>(qpos, lap, nworlds, cpw, o->world_flag, o->world_list,
+                                                                           o->world_list + nworlds);
+    count_launch();
+    return FTGP_OK;
+}
+// ... and advance them on a side stream: one warp and 183 KB of shared memory per listed world, launched before the fast
+// path's kernel so that its blocks take their SMs first; the two kernels touch disjoint cars, and a coupled world is a
+// millisecond-long dependent chain that would otherwise be added to the tick.  The caller joins on ev_join.
+static int world_fork_launch(StepScratch* o, int dev, const uint32_t* blob, double* qpos, double* qvel, double* warm, const double* ctrl,
+                             const int32_t* track_id, const int32_t* lap, int64_t nworlds, int cpw, int32_t* status, int options,
+                             cudaStream_t stream) {
+    FTGP_CUDA(cudaEventRecord(o->ev_fork, stream));
+    FTGP_CUDA(cudaStreamWaitEvent(o->side, o->ev_fork, 0));
+    const int slots = (int)std::min<int64_t>((nworlds + WORLD_WARPS - 1) / WORLD_WARPS, g_sm_count[dev]);
+    world_step_kernel<<<slots, 32 * WORLD_WARPS, sizeof(WorldWork), o->side>>>(blob, qpos, qvel, warm, ctrl, track_id, lap, cpw, status,
+                                                                               o->world_list, o->world_list + nworlds, options,
+                                                                               static_cast<WorldWork*>(o->world_spill));
+    count_launch();
+    FTGP_CUDA(cudaEventRecord(o->ev_join, o->side));
+    return FTGP_OK;
+}
+
+// Fused tick, worlds of several cars: the coupled worlds are listed and their solver is started BEFORE the rangefinder
+// kernel, which then reads a copy of the poses taken here (mj_step evaluates the rangefinders from the pre-step pose,
+// custom.py:1425) while the solver already moves its cars.  launch_step() of the same tick finds the worlds in flight, runs
+// only the fast path and joins.  *lidar_qpos receives the copy (row stride FTGP_NQ).
+int launch_worlds_early(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl, const int32_t* track_id,
+                        const int32_t* lap, int64_t ncars, int cpw, int32_t* status, int options, cudaStream_t stream,
+                        const double** lidar_qpos) {
+    if (cpw < 2 || cpw > WMAXCARS || ncars % cpw) { set_error("ftgp_tick: cars_per_world must be 1..8 and divide ncars"); return FTGP_ERR_ARG; }
+    int dev = 0;
+    FTGP_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) { set_error("ftgp_tick: device index %d not supported", dev); return FTGP_ERR_UNSUPPORTED; }
+    std::lock_guard<std::mutex> lock(g_step_mutex);
+    int rc = step_device_ready(dev); if (rc) return rc;
+    StepScratch* o = step_scratch(dev, stream);
+    const int64_t nworlds = ncars / cpw;
+    if (o->world_inflight) {                        // (a tick that failed between the fork and its step: join before starting over)
+        o->world_inflight = false;
+        FTGP_CUDA(cudaStreamWaitEvent(stream, o->ev_join, 0));
+    }
+    if ((rc = world_flag_launch(o, dev, qpos, lap, nworlds, cpw, stream))) return rc;
+    if (o->snap_cap < ncars) {
+        if (o->qpos_snap) cudaFree(o->qpos_snap);
+        o->qpos_snap = nullptr; o->snap_cap = 0; o->generation++;
+        FTGP_CUDA(cudaMalloc(&o->qpos_snap, (size_t)ncars * NQ * sizeof(double)));
+        o->snap_cap = ncars;
+    }
+    FTGP_CUDA(cudaMemcpyAsync(o->qpos_snap, qpos, (size_t)ncars * NQ * sizeof(double), cudaMemcpyDeviceToDevice, stream));
+    if ((rc = world_fork_launch(o, dev, g ? g->d_blob : nullptr, qpos, qvel, warm, ctrl, track_id, lap, nworlds, cpw, status, options, stream))) return rc;
+    o->world_inflight = true;
+    *lidar_qpos = o->qpos_snap;
+    return FTGP_OK;
+}
+
 int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, const double* ctrl,
                 const int32_t* track_id, const int32_t* lap, int64_t ncars, int cpw, int nsteps, int32_t* status,
                 int options, cudaStream_t stream) {
@@ -284,42 +379,16 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
     FTGP_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 16) { set_error("ftgp_step: device index %d not supported", dev); return FTGP_ERR_UNSUPPORTED; }
     std::lock_guard<std::mutex> lock(g_step_mutex);
-    int rc = ensure_model(dev); if (rc) return rc;
+    int rc = step_device_ready(dev); if (rc) return rc;
     constexpr size_t smem = quad_smem_bytes<STEP_NT>();
-    if (!g_attr_ready[dev]) {                       // once per device, not per launch
-        FTGP_CUDA(cudaDeviceGetAttribute(&g_sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-        FTGP_CUDA(cudaFuncSetAttribute(step_quad_kernel<STEP_NT, STEP_LOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        FTGP_CUDA(cudaFuncSetAttribute(step_quad_kernel<STEP_NT, STEP_LOCK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        FTGP_CUDA(cudaFuncSetAttribute(world_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WorldWork)));
-        g_attr_ready[dev] = true;
-    }
     const uint32_t* blob = g ? g->d_blob : nullptr;
     const bool big = ncars < (int64_t)1 << 31;
     const bool reorder = status && big && ncars >= ORDER_MIN_CARS;
     const bool staged = nsteps == 1 && big && ncars >= STAGE_MIN_CARS;
     StepScratch* o = (reorder || staged || cpw > 1) ? step_scratch(dev, stream) : nullptr;
-    // worlds of several cars: flag the worlds whose cars touch (they leave the fast path)
     const int64_t nworlds = ncars / cpw;
-    if (cpw > 1) {
-        if (o->world_cap < nworlds) {
-            if (o->world_list) cudaFree(o->world_list);
-            if (o->world_flag) cudaFree(o->world_flag);
-            o->world_list = nullptr; o->world_flag = nullptr; o->world_cap = 0; o->generation++;
-            FTGP_CUDA(cudaMalloc(&o->world_list, (size_t)(nworlds + 1) * sizeof(int32_t)));
-            FTGP_CUDA(cudaMalloc(&o->world_flag, (size_t)nworlds));
-            o->world_cap = nworlds;
-            if (WORLD_WARPS > 1 && !o->world_spill) FTGP_CUDA(cudaMalloc(&o->world_spill, (size_t)g_sm_count[dev] * (WORLD_WARPS - 1) * sizeof(WorldWork)));
-            if (!o->side) {
-                FTGP_CUDA(cudaStreamCreateWithFlags(&o->side, cudaStreamNonBlocking));
-                FTGP_CUDA(cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming));
-                FTGP_CUDA(cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming));
-            }
-        }
-        FTGP_CUDA(cudaMemsetAsync(o->world_list + nworlds, 0, sizeof(int32_t), stream));        // the counter sits behind the list
-        world_flag_kernel<<<(unsigned)((nworlds + 127) / 128), 128, 0, stream>>>(qpos, lap, nworlds, cpw, o->world_flag, o->world_list,
-                                                                               o->world_list + nworlds);
-        count_launch();
-    }
+    const bool fork_here = cpw > 1 && !o->world_inflight;          // (inside the fused tick the worlds are in flight already)
+    if (fork_here && (rc = world_flag_launch(o, dev, qpos, lap, nworlds, cpw, stream))) return rc;
     // cars grouped by (last Newton iteration count, wall contact) for the kernel that runs 54 cars in lock-step
     const int32_t* perm = nullptr;
     if (reorder) {
@@ -332,8 +401,9 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
         }
         FTGP_CUDA(cudaMemsetAsync(o->counters, 0, 2 * NBIN * sizeof(int32_t), stream));
         const unsigned nb = (unsigned)((ncars + 255) / 256);
-        order_hist_kernel<<<nb, 256, 0, stream>>>(status, ncars, o->counters);
-        order_scatter_kernel<<<nb, 256, 0, stream>>>(status, ncars, o->counters, o->counters + NBIN, o->perm);
+        const uint8_t* wf = cpw > 1 ? o->world_flag : nullptr;
+        order_hist_kernel<<<nb, 256, 0, stream>>>(status, wf, cpw, ncars, o->counters);
+        order_scatter_kernel<<<nb, 256, 0, stream>>>(status, wf, cpw, ncars, o->counters, o->counters + NBIN, o->perm);
         count_launch(2);
         perm = o->perm;
     }
@@ -360,19 +430,7 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
             FTGP_CUDA(cudaMemsetAsync(counts, 0, 4 * sizeof(int32_t), stream));
         }
     }
-    if (cpw > 1) {
-        // The coupled worlds are advanced on a side stream, launched FIRST so that their blocks (one warp and 206 KB of shared
-        // memory each, one per flagged world) take their SMs before the fast path's CTAs fill the rest: the two kernels touch
-        // disjoint cars, and a coupled world is a millisecond-long dependent chain that would otherwise be added to the tick.
-        FTGP_CUDA(cudaEventRecord(o->ev_fork, stream));
-        FTGP_CUDA(cudaStreamWaitEvent(o->side, o->ev_fork, 0));
-        const int slots = (int)std::min<int64_t>((nworlds + WORLD_WARPS - 1) / WORLD_WARPS, g_sm_count[dev]);
-        world_step_kernel<<<slots, 32 * WORLD_WARPS, sizeof(WorldWork), o->side>>>(blob, qpos, qvel, warm, ctrl, track_id, lap, cpw, status,
-                                                                                   o->world_list, o->world_list + nworlds, options,
-                                                                                   static_cast<WorldWork*>(o->world_spill));
-        count_launch();
-        FTGP_CUDA(cudaEventRecord(o->ev_join, o->side));
-    }
+    if (fork_here && (rc = world_fork_launch(o, dev, blob, qpos, qvel, warm, ctrl, track_id, lap, nworlds, cpw, status, options, stream))) return rc;
     constexpr int CARS = STEP_NT / 4;
     step_quad_kernel<STEP_NT, STEP_LOCK><<<(unsigned)((ncars + CARS - 1) / CARS), STEP_NT, smem, stream>>>(
         blob, qpos, qvel, warm, ctrl, track_id, lap, perm, ncars, nsteps, status, recs, nullptr, nullptr, lists, counts, STAGE_ROUNDS,
@@ -384,7 +442,10 @@ int launch_step(const ftgp_geom* g, double* qpos, double* qvel, double* warm, co
             options, nullptr, cpw, 1);
         count_launch();
     }
-    if (cpw > 1) FTGP_CUDA(cudaStreamWaitEvent(stream, o->ev_join, 0));       // join: the coupled worlds are done as well
+    if (cpw > 1) {                                  // join: the coupled worlds are done as well
+        o->world_inflight = false;
+        FTGP_CUDA(cudaStreamWaitEvent(stream, o->ev_join, 0));
+    }
     FTGP_CUDA(cudaGetLastError());
     return FTGP_OK;
 }
@@ -411,7 +472,11 @@ static int issue_tick(const ftgp_tick_args* a, int32_t steps, int32_t* steps_dev
     // custom.py:1395-1423 driver on the ranges of the previous mj_step, control write
     if ((rc = launch_drivers(a->ranges, a->driver_kind, a->default_driver, a->lap, a->ctrl, a->ncars, s, steps_dev))) return rc;
     // custom.py:1425 mj_step: rangefinders are evaluated from the pre-step pose, then the state advances
-    if ((rc = launch_lidar(a->geom, a->qpos, FTGP_NQ, a->track_id, nullptr, a->lap, a->ncars, a->cars_per_world, a->ranges,
+    // (worlds of several cars: the coupled worlds' solver starts here, beside the rangefinders, which read a copy of the poses)
+    const double* lidar_qpos = a->qpos;
+    if (a->cars_per_world > 1 && (rc = launch_worlds_early(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars,
+                                                           a->cars_per_world, a->status, a->options, s, &lidar_qpos))) return rc;
+    if ((rc = launch_lidar(a->geom, lidar_qpos, FTGP_NQ, a->track_id, nullptr, a->lap, a->ncars, a->cars_per_world, a->ranges,
                            nullptr, s))) return rc;
     return launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, a->cars_per_world, 1, a->status, a->options, s);
 }

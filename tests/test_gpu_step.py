@@ -640,3 +640,38 @@ def test_car_car_contacts_match_the_oracle_world_solver(ft, oracle, otracks):
     assert ncc_total > 300 and coupled > 300
     far = np.arange(n).reshape(nworlds, cpw)[::3].ravel()
     assert ((fleet.status.cpu().numpy()[far] >> 9) & 1).sum() == 0    # the spread-out worlds never left the fast path
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nworlds", [6, 2600])
+def test_fused_tick_of_coupled_worlds_equals_the_separate_calls(ft, nworlds):
+    """Worlds of 8 cars in a queue that run into each other: inside ftgp_tick the coupled worlds' solver is started before
+    the rangefinder kernel (which reads a copy of the poses) and runs beside it and beside the fast path; the result must
+    equal lap_update / drive / lidar / step issued one after the other bit for bit -- for a small fleet (CUDA-graph replay
+    with the side stream inside the capture) and for one above the graph limit (20,800 cars)."""
+    t = ft.Track.bundled("track")
+    cpw = 8
+    n = cpw * nworlds
+    rng = np.random.default_rng(5)
+    xy = np.zeros((n, 2)); yaw = np.zeros(n)
+    for w in range(nworlds):
+        k = int(rng.integers(0, 100)); d = t.path[(k + 1) % 100] - t.path[k]
+        h = float(np.arctan2(d[1], d[0]))
+        spacing = 0.2 if w % 2 == 0 else 0.5                          # every other world: cars that touch within a few ticks
+        for c in range(cpw):
+            xy[w * cpw + c] = t.path[k] + np.array([np.cos(h), np.sin(h)]) * spacing * c
+            yaw[w * cpw + c] = h + rng.normal(0, 0.03)
+    a = ft.Fleet(t, n, cars_per_world=cpw); b = ft.Fleet(t, n, cars_per_world=cpw)
+    kinds = ["nidc" if c % 2 == 0 else "fast" for c in range(cpw)] * nworlds
+    a.set_driver_kinds(kinds); b.set_driver_kinds(kinds)
+    a.reset(xy, yaw); b.reset(xy, yaw)
+    coupled = 0
+    for chunk in (1, 2, 20, 1, 36):
+        a.tick(chunk)
+        for _ in range(chunk):
+            b.lap_update(); b.drive(); b.lidar(); b.step(1)
+        a.sync(); b.sync()
+        coupled += int(((a.status.cpu().numpy() >> 9) & 1).sum())
+        for k in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "status"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (k, chunk)
+    assert coupled > 0                                                # the coupled solver really ran inside the fused tick
