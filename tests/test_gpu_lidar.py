@@ -93,21 +93,25 @@ def test_lidar_multi_car_world(ft, otracks):
     assert (np.abs(alone - want) > 1e-3).sum() > 50       # the other cars really are seen
 
 
-def test_lidar_multi_car_world_pitched_cars_see_chassis_and_wheels(ft, otracks):
+@pytest.mark.parametrize("seed,spread,tilt,seen", [(12, 0.22, 0.2, 300), (13, 0.08, 0.5, 300), (14, 1.2, 0.35, 40)])
+def test_lidar_multi_car_world_pitched_cars_see_chassis_and_wheels(ft, otracks, seed, spread, tilt, seen):
     """f1: mj_ray also ends on the other cars' chassis mesh and wheel ellipsoids (suspension travel and steering angle from
-    the state rows); on level ground those lie below the beams, so the cars here are pitched, rolled and lifted."""
+    the state rows); on level ground those lie below the beams, so the cars here are pitched, rolled and lifted.  The kernel
+    finds these hits in a pass of its own over the window of beams that can reach the other car's bounding sphere: packs so
+    tight that the window is the whole circle (spread 0.08 m, interpenetrating cars), loose ones where it is a few beams, and
+    every azimuth (the window wraps around beam 89 -> 0) must all agree with the oracle, which tests every ray against every car."""
     t = ft.Track.bundled("track")
     nworlds, cpw = 48, 8
     n = nworlds * cpw
-    rng = np.random.default_rng(12)
+    rng = np.random.default_rng(seed)
     q = np.zeros((n, 34)); q[:, [11, 18, 24, 30]] = 1.0
     for w in range(nworlds):
         cx, cy = t.path[rng.integers(0, 100)]
         for c in range(cpw):
-            yaw, pitch, roll = rng.uniform(-3, 3), rng.normal(0, 0.2), rng.normal(0, 0.2)
+            yaw, pitch, roll = rng.uniform(-3.2, 3.2), rng.normal(0, tilt), rng.normal(0, tilt)
             a, b, cc_, d, e, f = np.cos(yaw / 2), np.sin(yaw / 2), np.cos(pitch / 2), np.sin(pitch / 2), np.cos(roll / 2), np.sin(roll / 2)
             i = w * cpw + c
-            q[i, :3] = [cx + rng.normal(0, 0.22), cy + rng.normal(0, 0.22), 0.02 + rng.uniform(0, 0.06)]
+            q[i, :3] = [cx + rng.normal(0, spread), cy + rng.normal(0, spread), 0.02 + rng.uniform(0, 0.06)]
             q[i, 3:7] = [e * cc_ * a + f * d * b, f * cc_ * a - e * d * b, e * d * a + f * cc_ * b, e * cc_ * b - f * d * a]
             q[i, [8, 15, 22, 28]] = rng.uniform(-0.03, 0, 4); q[i, [9, 16]] = rng.uniform(-0.6, 0.6, 2)
             q[i, [10, 17, 23, 29]] = rng.uniform(-3, 3, 4)
@@ -124,7 +128,7 @@ def test_lidar_multi_car_world_pitched_cars_see_chassis_and_wheels(ft, otracks):
     assert miss.sum() == 0 and bad.mean() < 2e-4, (miss.sum(), bad.sum(), np.abs(got - want).max())
     # the new targets matter: compare with a scan that only knows the other cars' lidar cylinders' nominal neighbours
     alone = ot.scan(q[:, :7])
-    assert (np.abs(alone - want) > 1e-3).sum() > 300
+    assert (np.abs(alone - want) > 1e-3).sum() > seen
 
 
 def test_lidar_host_entry_and_ragged(ft, otracks):
