@@ -317,6 +317,9 @@ enum { ST_IDLE = 0, ST_CHUNK = 1, ST_SWEEP = 2, ST_ADV = 3 };
 #ifndef FTGP_AB_WALK_MAX
 #define FTGP_AB_WALK_MAX 5          // at most this many empty chunks per round (0: unbounded; measured 1.30 -> 1.14 ms at 65,536 cars)
 #endif
+#ifndef FTGP_AB_VOTE_BIAS
+#define FTGP_AB_VOTE_BIAS 0         // the walk block runs when n_walk + bias >= n_sweep (and somebody walks)
+#endif
 #ifndef FTGP_AB_WALK_VOTE
 #define FTGP_AB_WALK_VOTE 0         // K > 0: the walk goes on while at least K/4 of the lanes that started it are still walking
 #endif
@@ -579,7 +582,8 @@ lidar_kernel(const uint32_t* __restrict__ blob, int lidar_words, const double* _
             // ---------------- which block runs this round: the state with the most lanes
             const int n_chunk = __popc(__ballot_sync(0xffffffffu, L.state == ST_CHUNK || L.state == ST_ADV));
             const int n_sweep = __popc(__ballot_sync(0xffffffffu, L.state == ST_SWEEP));
-            int pick = n_chunk >= n_sweep ? ST_CHUNK : ST_SWEEP;
+            int pick = (n_chunk + FTGP_AB_VOTE_BIAS >= n_sweep && (n_chunk > 0 || n_sweep == 0)) ? ST_CHUNK : ST_SWEEP;
+            if (FTGP_AB_VOTE_BIAS < 0 && n_sweep == 0) pick = ST_CHUNK;
             if (FTGP_AB_HYST_A > 0) {
                 if (mode == ST_SWEEP) pick = (n_sweep >= FTGP_AB_HYST_A || n_chunk == 0) ? ST_SWEEP : ST_CHUNK;
                 else pick = (n_chunk >= FTGP_AB_HYST_B && n_chunk > 0) || n_sweep == 0 ? ST_CHUNK : ST_SWEEP;
