@@ -69,6 +69,13 @@ class Fleet:
         self.track_id = None if track_id is None else torch.as_tensor(track_id, dtype=torch.int32).to(dev).contiguous()
         self.driver_kind = None
         self.steps = 0
+        # options manual_control / always_invoke_driver / detach_control of the loop's driver block (custom.py:952-957,1401-1423)
+        self.manual_control = False          # the watched car takes (speed, steering) from the operator
+        self.always_invoke_driver = True     # ... while the drivers are still invoked (reference default)
+        self.detach_control = False          # drivers run, data.ctrl is not written
+        self.watching = None                 # car id (custom.py: self.watching)
+        self.manual_speed, self.manual_steering = 0.0, 0.0        # self.mv.speed, self.mv.steering_angle
+        self.driver_out = None               # [ncars, 2]: vehicle_state.speed / steering_angle of the last tick (only kept with the options on)
         torch.cuda.synchronize(dev)
 
     @property
@@ -141,10 +148,46 @@ class Fleet:
                                        self._s), "ftgp_lidar")
         return self.ranges
 
+    def _control_options(self):
+        return self.manual_control or self.detach_control
+
+    def set_manual_control(self, on, watching=None, speed=0.0, steering_angle=0.0, always_invoke_driver=True):
+        """Options manual_control / always_invoke_driver (custom.py:954-957): the watched car is driven by (speed,
+        steering_angle) -- the reference's keyboard state self.mv -- instead of its driver."""
+        self.manual_control = bool(on)
+        self.watching = None if watching is None else int(watching)
+        self.manual_speed, self.manual_steering = float(speed), float(steering_angle)
+        self.always_invoke_driver = bool(always_invoke_driver)
+
     def drive(self):
-        """Built-in batched drivers + control write (custom.py:1398-1423)."""
-        _lib.check(self.lib.ftgp_drivers(_ptr(self.ranges), _ptr(self.driver_kind), self.default_driver,
-                                         _ptr(self.lap), _ptr(self.ctrl), self.ncars, self._s), "ftgp_drivers")
+        """Built-in batched drivers + control write (custom.py:1398-1423), with the options of that block:
+        `always_invoke_driver or not manual_control` decides whether the drivers run at all (else (0, 0)); under
+        manual_control the watched car takes the operator's (speed, steering), and a released throttle decays
+        (speed = ctrl * 0.99 while ctrl > 0, custom.py:1413-1416); under detach_control the result goes to
+        vehicle_state.speed / steering_angle (driver_out) only and data.ctrl keeps its values (custom.py:1421-1423)."""
+        special = self._control_options()
+        if special:
+            with torch.cuda.stream(self.stream):
+                prev = self.ctrl.clone()
+        if self.always_invoke_driver or not self.manual_control:
+            _lib.check(self.lib.ftgp_drivers(_ptr(self.ranges), _ptr(self.driver_kind), self.default_driver,
+                                             _ptr(self.lap), _ptr(self.ctrl), self.ncars, self._s), "ftgp_drivers")
+        else:
+            with torch.cuda.stream(self.stream):
+                self.ctrl.zero_()
+        if special:
+            with torch.cuda.stream(self.stream):
+                if self.manual_control and self.watching is not None:
+                    w = self.watching
+                    if self.manual_speed == 0.0:
+                        sp = torch.where(prev[w, 0] > 0.0, prev[w, 0] * 0.99, torch.zeros_like(prev[w, 0]))
+                    else:
+                        sp = torch.full_like(prev[w, 0], self.manual_speed)
+                    self.ctrl[w, 0] = sp
+                    self.ctrl[w, 1] = self.manual_steering
+                self.driver_out = self.ctrl.clone()
+                if self.detach_control:
+                    self.ctrl.copy_(prev)
         return self.ctrl
 
     def drive_host(self, drivers):
@@ -157,8 +200,10 @@ class Fleet:
         ctrl = self.ctrl.cpu().numpy()
         finished = self.lap[:, LAP["finished"]].cpu().numpy()
         snaps = None
+        prev = ctrl.copy()
+        invoke = self.always_invoke_driver or not self.manual_control        # custom.py:1403
         for i, d in enumerate(drivers):
-            if finished[i]:                          # shadow() swapped in LobotomyDriver (custom.py:1437)
+            if finished[i] or not invoke:            # shadow() swapped in LobotomyDriver (custom.py:1437) / nobody is asked
                 ctrl[i] = (0.0, 0.0)
                 continue
             try:
@@ -171,6 +216,16 @@ class Fleet:
                 ctrl[i] = (float(sp), float(st))
             except Exception as e:                                          # custom.py:1409-1411
                 print(f"Error in vehicle `{i}`: `{e}`")
+        if self.manual_control and self.watching is not None:               # custom.py:1413-1416
+            w = self.watching
+            sp = self.manual_speed
+            if sp == 0.0 and prev[w, 0] > 0.0:
+                sp = prev[w, 0] * 0.99
+            ctrl[w] = (sp, self.manual_steering)
+        if self._control_options():
+            self.driver_out = torch.from_numpy(ctrl.copy()).to(self.device)
+        if self.detach_control:                                             # custom.py:1421-1423
+            ctrl = prev
         self.ctrl.copy_(torch.from_numpy(ctrl))
         return self.ctrl
 
@@ -215,6 +270,10 @@ class Fleet:
 
     def tick(self, nticks=1):
         """nticks iterations of the physics loop (custom.py:1337-1426), all on device."""
+        if self._control_options():                   # operator options: the driver block needs the host's say every tick
+            for _ in range(int(nticks)):
+                self.lap_update(); self.drive(); self.lidar(); self.step(1)
+            return
         a = self.tick_args()
         _lib.check(self.lib.ftgp_tick(C.byref(a), int(nticks), self._s), "ftgp_tick")
         self.steps += int(nticks)

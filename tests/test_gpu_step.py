@@ -675,3 +675,53 @@ def test_fused_tick_of_coupled_worlds_equals_the_separate_calls(ft, nworlds):
         for k in ("qpos", "qvel", "warm", "ctrl", "ranges", "lap", "status"):
             assert torch.equal(getattr(a, k), getattr(b, k)), (k, chunk)
     assert coupled > 0                                                # the coupled solver really ran inside the fused tick
+
+
+def test_manual_control_always_invoke_driver_and_detach_control(ft):
+    """The options of the loop's driver block (custom.py:952-957,1401-1423): under manual_control the watched car takes the
+    operator's (speed, steering) -- a released throttle decays by 0.99 per tick while ctrl > 0 --, the others keep their
+    drivers if always_invoke_driver (else everybody else gets (0, 0)); under detach_control the drivers' answers go to
+    vehicle_state.speed / steering_angle (driver_out) and data.ctrl is left alone."""
+    t = ft.Track.bundled("track")
+    n, w = 16, 5
+    a = ft.Fleet(t, n); b = ft.Fleet(t, n)
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, 100, n); nxt = (idx + 1) % 100
+    xy = t.path[idx] + rng.normal(0, 0.05, (n, 2))
+    yaw = np.arctan2(t.path[nxt, 1] - t.path[idx, 1], t.path[nxt, 0] - t.path[idx, 0])
+    a.reset(xy, yaw); b.reset(xy, yaw)
+    others = [i for i in range(n) if i != w]
+    a.set_manual_control(True, watching=w, speed=2.0, steering_angle=0.3)
+    for k in range(30):
+        a.tick(1); b.tick(1)
+    a.sync(); b.sync()
+    ca, cb = a.ctrl.cpu().numpy(), b.ctrl.cpu().numpy()
+    assert ca[w].tolist() == [2.0, 0.3]
+    assert np.array_equal(ca[others], cb[others])                 # single-car worlds: the other cars never notice
+    assert np.array_equal(a.qpos.cpu().numpy()[others], b.qpos.cpu().numpy()[others])
+    assert not np.array_equal(a.qpos.cpu().numpy()[w], b.qpos.cpu().numpy()[w])
+    # throttle released: speed = ctrl * 0.99 per tick (custom.py:1415-1416)
+    a.set_manual_control(True, watching=w, speed=0.0, steering_angle=-0.1)
+    a.tick(10); a.sync()
+    got = a.ctrl.cpu().numpy()[w]
+    want = 2.0
+    for _ in range(10):
+        want = want * 0.99
+    assert got[0] == want and got[1] == -0.1
+    # always_invoke_driver off: nobody but the operator drives
+    a.set_manual_control(True, watching=w, speed=1.0, steering_angle=0.0, always_invoke_driver=False)
+    a.tick(3); a.sync()
+    ca = a.ctrl.cpu().numpy()
+    assert ca[w].tolist() == [1.0, 0.0] and np.abs(ca[others]).max() == 0.0
+    # detach_control: ctrl frozen, driver_out follows the drivers
+    a.set_manual_control(False)
+    a.tick(5); a.sync()
+    frozen = a.ctrl.clone()
+    a.detach_control = True
+    a.tick(20); a.sync()
+    assert torch.equal(a.ctrl, frozen)
+    out = a.driver_out.clone()
+    assert float(out.abs().sum()) > 0.0 and not torch.equal(out, frozen)
+    a.detach_control = False
+    a.tick(1); a.sync()
+    assert not torch.equal(a.ctrl, frozen)                        # control attached again: the drivers' answers land in ctrl
