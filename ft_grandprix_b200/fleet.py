@@ -139,13 +139,14 @@ class Fleet:
         self.reset(xy, yaw)
 
     # ------------------------------------------------------------------ the per-tick pieces
-    def lidar(self, visible=None, min_range=None, shadow_finished=True):
+    def lidar(self, visible=None, min_range=None, shadow_finished=True, qpos=None, stream=None):
         """data.sensordata[vehicle_state.sensors] for every car (custom.py:1395).  Finished cars are shadowed as in
-        the reference (stale ranges, invisible to the others) unless shadow_finished is False."""
-        _lib.check(self.lib.ftgp_lidar(self.geom._ptr, _ptr(self.qpos), NQ, _ptr(self.track_id), _ptr(visible),
-                                       _ptr(self.lap) if shadow_finished else None,
+        the reference (stale ranges, invisible to the others) unless shadow_finished is False.  qpos / stream: scan a copy
+        of the poses on another stream (tick_readback runs the scan beside the vehicle step that way)."""
+        _lib.check(self.lib.ftgp_lidar(self.geom._ptr, _ptr(self.qpos if qpos is None else qpos), NQ, _ptr(self.track_id),
+                                       _ptr(visible), _ptr(self.lap) if shadow_finished else None,
                                        self.ncars, self.cars_per_world, _ptr(self.ranges), _ptr(min_range),
-                                       self._s), "ftgp_lidar")
+                                       self._s if stream is None else C.c_void_p(stream.cuda_stream)), "ftgp_lidar")
         return self.ranges
 
     def _control_options(self):
@@ -288,20 +289,30 @@ class Fleet:
         if not hasattr(self, "_copy_stream"):
             with torch.cuda.device(self.device):
                 self._copy_stream = torch.cuda.Stream(device=self.device)
-            self._ev = [torch.cuda.Event() for _ in range(4)]      # lap ready, ranges ready, lap copied, ranges copied
+                self._scan_stream = torch.cuda.Stream(device=self.device)
+            self._ev = [torch.cuda.Event() for _ in range(5)]      # lap ready, ranges ready, lap copied, ranges copied, poses copied
             self._ev[2].record(self._copy_stream); self._ev[3].record(self._copy_stream)
-        s, c = self.stream, self._copy_stream
-        lap_ready, ranges_ready, lap_copied, ranges_copied = self._ev
+            self._qpos_scan = torch.empty_like(self.qpos)
+        s, c, l = self.stream, self._copy_stream, self._scan_stream
+        lap_ready, ranges_ready, lap_copied, ranges_copied, poses_copied = self._ev
         with torch.cuda.stream(s):
             s.wait_event(lap_copied)                 # the previous copy of the lap state has left
             self.lap_update()
             lap_ready.record(s)
             self.drive()
+            # the rangefinders see the pre-step pose (custom.py:1425): they scan a copy of it on their own stream while
+            # the vehicle step advances the state on this one (as ftgp_tick does)
+            self._qpos_scan.copy_(self.qpos, non_blocking=True)
+            poses_copied.record(s)
+        with torch.cuda.stream(l):
+            l.wait_event(poses_copied)
             if ranges_host is not None:
-                s.wait_event(ranges_copied)          # ... and of the ranges
-            self.lidar()
-            ranges_ready.record(s)
+                l.wait_event(ranges_copied)          # ... and the previous copy of the ranges
+            self.lidar(qpos=self._qpos_scan, stream=l)
+            ranges_ready.record(l)
+        with torch.cuda.stream(s):
             self.step(1)
+            s.wait_event(ranges_ready)               # join: the next tick's drivers read these ranges
         with torch.cuda.stream(c):
             c.wait_event(lap_ready)
             lap_host.copy_(self.lap, non_blocking=True)
@@ -315,6 +326,7 @@ class Fleet:
     def sync_readback(self):
         self.stream.synchronize()
         if hasattr(self, "_copy_stream"):
+            self._scan_stream.synchronize()
             self._copy_stream.synchronize()
 
     # ------------------------------------------------------------------ v2 driver input (custom.py:149-160)
