@@ -161,6 +161,7 @@ struct StepScratch {
     double* qpos_snap = nullptr; int64_t snap_cap = 0;      // fused tick: the poses the rangefinders read while the coupled worlds already move
     bool world_inflight = false;                            // the coupled worlds of this step were started by launch_worlds_early
     cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;       // ... advanced beside the fast path
+    cudaStream_t scan = nullptr; cudaEvent_t ev_scan_fork = nullptr, ev_scan_join = nullptr;    // fused tick: the rangefinders beside the step
     uint64_t generation = 0;     // bumped whenever a buffer is (re)allocated or freed: captured graphs hold these pointers
     void release() {
         if (dev < 0) return;
@@ -175,6 +176,9 @@ struct StepScratch {
         if (side) cudaStreamDestroy(side);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (scan) cudaStreamDestroy(scan);
+        if (ev_scan_fork) cudaEventDestroy(ev_scan_fork);
+        if (ev_scan_join) cudaEventDestroy(ev_scan_join);
         if (world_flag) cudaFree(world_flag);
         if (world_spill) cudaFree(world_spill);
         if (qpos_snap) cudaFree(qpos_snap);
@@ -461,32 +465,34 @@ int launch_lap(const ftgp_geom* g, const double* qpos, int64_t stride, const int
 
 int launch_flatten(double* qpos, int64_t stride, int64_t ncars, cudaStream_t stream);
 
-// Single-car worlds inside the fused tick: the rangefinder kernel runs on a side stream against a copy of the poses (mj_step
+// Inside the fused tick the rangefinder kernel runs on a side stream against a copy of the poses (mj_step
 // evaluates the rangefinders from the pre-step pose, custom.py:1425) while the vehicle step advances the state on the main
 // stream.  The two kernels cannot share an SM (227 KB + 80 KB of shared memory), so on a full GPU all there is to win are
 // the tails of each other's waves (65,536 cars: 2.97 -> 2.90 ms per tick); small fleets fill the GPU with neither kernel and
 // win more (256 cars 0.35 -> 0.28 ms, 1,024 cars 0.52 -> 0.45, 4,096 cars 0.71 -> 0.66, 16,384 cars 1.21 -> 1.13).  Results
 // are bit-identical to the serial order (tools/tick_ab.py; tests/test_gpu_step.py, graph-replayed and eager).
-static int overlap_fork(double* qpos, int64_t ncars, cudaStream_t stream, const double** snap, cudaStream_t* side, cudaEvent_t* join) {
+static int overlap_fork(double* qpos, int64_t ncars, bool copy, cudaStream_t stream, const double** snap, cudaStream_t* side, cudaEvent_t* join) {
     int dev = 0;
     FTGP_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_step_mutex);
     StepScratch* o = step_scratch(dev, stream);
-    if (!o->side) {
-        FTGP_CUDA(cudaStreamCreateWithFlags(&o->side, cudaStreamNonBlocking));
-        FTGP_CUDA(cudaEventCreateWithFlags(&o->ev_fork, cudaEventDisableTiming));
-        FTGP_CUDA(cudaEventCreateWithFlags(&o->ev_join, cudaEventDisableTiming));
+    if (!o->scan) {
+        FTGP_CUDA(cudaStreamCreateWithFlags(&o->scan, cudaStreamNonBlocking));
+        FTGP_CUDA(cudaEventCreateWithFlags(&o->ev_scan_fork, cudaEventDisableTiming));
+        FTGP_CUDA(cudaEventCreateWithFlags(&o->ev_scan_join, cudaEventDisableTiming));
     }
-    if (o->snap_cap < ncars) {
-        if (o->qpos_snap) cudaFree(o->qpos_snap);
-        o->qpos_snap = nullptr; o->snap_cap = 0; o->generation++;
-        FTGP_CUDA(cudaMalloc(&o->qpos_snap, (size_t)ncars * NQ * sizeof(double)));
-        o->snap_cap = ncars;
+    if (copy) {                                     // (worlds of several cars: launch_worlds_early has taken the copy already)
+        if (o->snap_cap < ncars) {
+            if (o->qpos_snap) cudaFree(o->qpos_snap);
+            o->qpos_snap = nullptr; o->snap_cap = 0; o->generation++;
+            FTGP_CUDA(cudaMalloc(&o->qpos_snap, (size_t)ncars * NQ * sizeof(double)));
+            o->snap_cap = ncars;
+        }
+        FTGP_CUDA(cudaMemcpyAsync(o->qpos_snap, qpos, (size_t)ncars * NQ * sizeof(double), cudaMemcpyDeviceToDevice, stream));
     }
-    FTGP_CUDA(cudaMemcpyAsync(o->qpos_snap, qpos, (size_t)ncars * NQ * sizeof(double), cudaMemcpyDeviceToDevice, stream));
-    FTGP_CUDA(cudaEventRecord(o->ev_fork, stream));
-    FTGP_CUDA(cudaStreamWaitEvent(o->side, o->ev_fork, 0));
-    *snap = o->qpos_snap; *side = o->side; *join = o->ev_join;
+    FTGP_CUDA(cudaEventRecord(o->ev_scan_fork, stream));
+    FTGP_CUDA(cudaStreamWaitEvent(o->scan, o->ev_scan_fork, 0));
+    *snap = o->qpos_snap; *side = o->scan; *join = o->ev_scan_join;
     return FTGP_OK;
 }
 
@@ -500,23 +506,18 @@ static int issue_tick(const ftgp_tick_args* a, int32_t steps, int32_t* steps_dev
                          a->cars_per_world, steps, a->lap_target, s, steps_dev))) return rc;
     // custom.py:1395-1423 driver on the ranges of the previous mj_step, control write
     if ((rc = launch_drivers(a->ranges, a->driver_kind, a->default_driver, a->lap, a->ctrl, a->ncars, s, steps_dev))) return rc;
-    // custom.py:1425 mj_step: rangefinders are evaluated from the pre-step pose, then the state advances
-    // (worlds of several cars: the coupled worlds' solver starts here, beside the rangefinders, which read a copy of the poses)
-    if (a->cars_per_world == 1) {
-        const double* snap; cudaStream_t side; cudaEvent_t join;
-        if ((rc = overlap_fork(a->qpos, a->ncars, s, &snap, &side, &join))) return rc;
-        if ((rc = launch_lidar(a->geom, snap, FTGP_NQ, a->track_id, nullptr, a->lap, a->ncars, 1, a->ranges, nullptr, side))) return rc;
-        FTGP_CUDA(cudaEventRecord(join, side));
-        rc = launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, 1, 1, a->status, a->options, s);
-        FTGP_CUDA(cudaStreamWaitEvent(s, join, 0));       // (also after a failed step: the side stream must rejoin a capture)
-        return rc;
-    }
-    const double* lidar_qpos = a->qpos;
+    // custom.py:1425 mj_step: rangefinders are evaluated from the pre-step pose, then the state advances.  The rangefinder
+    // kernel scans a copy of the poses on a stream of its own beside the step; in worlds of several cars the coupled worlds'
+    // solver starts here as well, on a third stream (launch_worlds_early takes the copy in that case).
+    const double* snap = nullptr; cudaStream_t scan; cudaEvent_t join;
     if (a->cars_per_world > 1 && (rc = launch_worlds_early(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars,
-                                                           a->cars_per_world, a->status, a->options, s, &lidar_qpos))) return rc;
-    if ((rc = launch_lidar(a->geom, lidar_qpos, FTGP_NQ, a->track_id, nullptr, a->lap, a->ncars, a->cars_per_world, a->ranges,
-                           nullptr, s))) return rc;
-    return launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, a->cars_per_world, 1, a->status, a->options, s);
+                                                           a->cars_per_world, a->status, a->options, s, &snap))) return rc;
+    if ((rc = overlap_fork(a->qpos, a->ncars, a->cars_per_world == 1, s, &snap, &scan, &join))) return rc;
+    if ((rc = launch_lidar(a->geom, snap, FTGP_NQ, a->track_id, nullptr, a->lap, a->ncars, a->cars_per_world, a->ranges, nullptr, scan))) return rc;
+    FTGP_CUDA(cudaEventRecord(join, scan));
+    rc = launch_step(a->geom, a->qpos, a->qvel, a->warm, a->ctrl, a->track_id, a->lap, a->ncars, a->cars_per_world, 1, a->status, a->options, s);
+    FTGP_CUDA(cudaStreamWaitEvent(s, join, 0));           // (also after a failed step: the side stream must rejoin a capture)
+    return rc;
 }
 
 // ---- small fleets: the tick is launch-bound (4-9 launches of a few microseconds of work each), so it is captured once
