@@ -38,3 +38,30 @@ extern "C" int hw_world_has_contact(const double* qpos, int n, const unsigned ch
     for (int c = 0; c < n; c++) { q[c] = qpos + 34 * c; sh[c] = shadowed && shadowed[c]; }
     return world_has_contact(n, q, sh) ? 1 : 0;
 }
+
+// TEST SUPPORT: the two root-only solves of the coupled-world direction against the full block-arrow solve.
+// dense: [NP x NP] SPD matrix with the block-arrow pattern (root 7x7, four 6x6 chain blocks, borders chain x root), row-major.
+// out[0] = max |S6[i][j] - (A^-1 e_i)[j]| over i < 6, j < NR;  out[1] = max |arrow_solve_root_rhs(b) - arrow_solve((b, 0))|.
+extern "C" void hw_arrow_root_check(const double* dense, const double* br, double* out2) {
+    std::unique_ptr<Arrow> A(new Arrow());
+    for (int i = 0; i < NR; i++) for (int j = 0; j <= i; j++) A->R[tri(i, j)] = dense[i * NP + j];
+    for (int w = 0; w < 4; w++) {
+        for (int l = 0; l < NC; l++) for (int k = 0; k <= l; k++) A->W[w][tri(l, k)] = dense[(NR + NC * w + l) * NP + NR + NC * w + k];
+        for (int l = 0; l < NC; l++) for (int j = 0; j < NR; j++) A->B[w][l][j] = dense[(NR + NC * w + l) * NP + j];
+    }
+    arrow_factor(*A);
+    double S6[6][NR], worst_s = 0, worst_r = 0;
+    arrow_root_inverse6(*A, S6);
+    for (int i = 0; i < 6; i++) {
+        double e[NP];
+        for (int p = 0; p < NP; p++) e[p] = p == i ? 1.0 : 0.0;
+        arrow_solve(*A, e);
+        for (int j = 0; j < NR; j++) worst_s = fmax(worst_s, fabs(S6[i][j] - e[j]));
+    }
+    double x[NP], y[NP];
+    for (int p = 0; p < NP; p++) x[p] = y[p] = p < NR ? br[p] : 0.0;
+    arrow_solve_root_rhs(*A, x);
+    arrow_solve(*A, y);
+    for (int p = 0; p < NP; p++) worst_r = fmax(worst_r, fabs(x[p] - y[p]));
+    out2[0] = worst_s; out2[1] = worst_r;
+}

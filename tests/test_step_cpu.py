@@ -824,3 +824,23 @@ def test_warp_of_quads_with_walls_and_shadowed_cars_is_deadlock_free(host_quad_k
     out = subprocess.run([sys.executable, script, ROOT, lib, "160"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.startswith("ok") and int(out.stdout.split()[1]) > 50          # wall contacts really happened
+
+
+def test_root_only_solves_of_the_coupled_direction_equal_the_full_arrow_solve(host_world_kernel):
+    """A car-car contact row touches only the six chassis dofs, so the Woodbury pieces of the coupled-world direction are
+    right-hand sides on the root dofs: arrow_root_inverse6 (root rows of the first six columns of H^-1) and
+    arrow_solve_root_rhs (H^-1 (b, 0)) skip the chain forward pass.  Both must equal the full block-arrow solve."""
+    rng = np.random.default_rng(8)
+    NP, NR, NC = 31, 7, 6
+    out = np.zeros(2)
+    for trial in range(20):
+        A = np.zeros((NP, NP))
+        G = rng.normal(size=(NR, NR)); A[:NR, :NR] = G @ G.T + NR * np.eye(NR)
+        for w in range(4):
+            o = NR + NC * w
+            G = rng.normal(size=(NC, NC)); A[o:o + NC, o:o + NC] = G @ G.T + NC * np.eye(NC)
+            B = 0.3 * rng.normal(size=(NC, NR)); A[o:o + NC, :NR] = B; A[:NR, o:o + NC] = B.T
+        assert np.linalg.eigvalsh(A).min() > 0
+        br = rng.normal(size=NR); br[6] = 0.0
+        host_world_kernel.hw_arrow_root_check(P(A), P(br), P(out))
+        assert out[0] < 1e-13 and out[1] < 1e-13, (trial, out)
